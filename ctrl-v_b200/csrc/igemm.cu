@@ -1,0 +1,561 @@
+// tcgen05 implicit-GEMM contraction: the one tensor-core kernel behind every Linear, 3x3 conv,
+// stride-2 conv, skip-concat conv, fused 1x1 shortcut and (3,1,1) temporal conv of the
+// Box2Video denoise step.
+//
+//   D[m][n] = sum over K segments s, channels c:  A_s[coord(m) + shift_s][c] * W[n][k(s, c)]
+//
+// * A operand: channels-last activations, fetched by TMA as 4-D boxes (64 channels x bx x by x bz
+//   sites = up to 128 rows) straight into 128B-swizzled shared memory; conv halos, temporal halos
+//   and ragged tiles are TMA out-of-bounds zero fill — no im2col, no padding copies.
+// * B operand: weights [N][K] (K contiguous), 2-D TMA boxes of 64 x BN.
+// * tcgen05.mma (cta_group::1, M=128, N=BN, K=16) issued by one thread, fp32 accumulators in
+//   TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the main loop of
+//   tile i+1.  Persistent CTAs (one per SM), static round-robin tile schedule.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue
+//   (each owns the TMEM lane quarter warp_id % 4; one accumulator row per thread).
+#include "common.cuh"
+#include "../../include/ctrlv_b200.h"
+
+namespace ctrlv {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+
+struct IgemmSeg {
+  int map, c0, nchunk, dx, dy, dz;
+};
+
+struct IgemmParams {
+  CUtensorMap tmA[CTRLV_MAX_SRC];
+  CUtensorMap tmB;
+  IgemmSeg seg[CTRLV_MAX_SEG];
+  int nseg, kblocks;
+  int X, Y, Z, bx, by, bz;
+  int tiles_x, tiles_y, tiles_z, tiles_n, tiles_total;
+  int BN, N, stages, a_bytes, stage_bytes, tmem_cols;
+  ctrlv_epilogue ep;
+};
+
+__device__ __forceinline__ int rowbias_index(const ctrlv_epilogue& ep, int m) {
+  int a = m / ep.rb_div;
+  if (ep.rb_mode == 1) return a;
+  if (ep.rb_mode == 2) return a % ep.rb_mod;
+  return (a * ep.rb_mod + m % ep.rb_mod) % ep.rb_B;
+}
+
+// scale, add residual streams, convert and store NV consecutive outputs of row m starting at
+// output column o0 (all loops compile-time so v[] stays in registers)
+template <int NV>
+__device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, long long m, int o0,
+                                          int n_store) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] *= ep.s_acc;
+  if (o0 + NV <= n_store) {
+    if (ep.res1) {
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res1) +
+                                                       (size_t)m * ep.ld_res1 + o0);
+#pragma unroll
+      for (int j = 0; j < NV; j += 8) {
+        const uint4 u = __ldg(rp + (j >> 3));
+        float2 f;
+        f = unpack_bf16x2(u.x); v[j] += ep.s_res1 * f.x; v[j + 1] += ep.s_res1 * f.y;
+        f = unpack_bf16x2(u.y); v[j + 2] += ep.s_res1 * f.x; v[j + 3] += ep.s_res1 * f.y;
+        f = unpack_bf16x2(u.z); v[j + 4] += ep.s_res1 * f.x; v[j + 5] += ep.s_res1 * f.y;
+        f = unpack_bf16x2(u.w); v[j + 6] += ep.s_res1 * f.x; v[j + 7] += ep.s_res1 * f.y;
+      }
+    }
+    if (ep.res2) {
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res2) +
+                                                       (size_t)m * ep.ld_res2 + o0);
+#pragma unroll
+      for (int j = 0; j < NV; j += 8) {
+        const uint4 u = __ldg(rp + (j >> 3));
+        float2 f;
+        f = unpack_bf16x2(u.x); v[j] += ep.s_res2 * f.x; v[j + 1] += ep.s_res2 * f.y;
+        f = unpack_bf16x2(u.y); v[j + 2] += ep.s_res2 * f.x; v[j + 3] += ep.s_res2 * f.y;
+        f = unpack_bf16x2(u.z); v[j + 4] += ep.s_res2 * f.x; v[j + 5] += ep.s_res2 * f.y;
+        f = unpack_bf16x2(u.w); v[j + 6] += ep.s_res2 * f.x; v[j + 7] += ep.s_res2 * f.y;
+      }
+    }
+    if (ep.out) {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)m * ep.ld_out + o0);
+#pragma unroll
+      for (int j = 0; j < NV; j += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(v[j], v[j + 1]);
+        u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        u.z = pack_bf16x2(v[j + 4], v[j + 5]);
+        u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        op[j >> 3] = u;
+      }
+    }
+    if (ep.out_f32) {
+      float4* op = reinterpret_cast<float4*>(ep.out_f32 + (size_t)m * ep.ld_out_f32 + o0);
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) op[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  } else {
+    // ragged tail of a padded-N problem (e.g. conv_out with 4 real channels): scalar, predicated
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int o = o0 + j;
+      if (o < n_store) {
+        float t = v[j];
+        if (ep.res1)
+          t += ep.s_res1 * __bfloat162float(reinterpret_cast<const bf16*>(ep.res1)[(size_t)m * ep.ld_res1 + o]);
+        if (ep.res2)
+          t += ep.s_res2 * __bfloat162float(reinterpret_cast<const bf16*>(ep.res2)[(size_t)m * ep.ld_res2 + o]);
+        if (ep.out) reinterpret_cast<bf16*>(ep.out)[(size_t)m * ep.ld_out + o] = __float2bfloat16(t);
+        if (ep.out_f32) ep.out_f32[(size_t)m * ep.ld_out_f32 + o] = t;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  // 1024-byte aligned tile ring
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nseg; ++i) tma_prefetch_desc(&p.tmA[p.seg[i].map]);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int nloc = (p.tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < nloc; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int nt = tile % p.tiles_n;
+        int mt = tile / p.tiles_n;
+        const int tx = mt % p.tiles_x;
+        mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int tz = mt / p.tiles_y;
+        const int x0 = tx * p.bx, y0 = ty * p.by, z0 = tz * p.bz;
+        int kb = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const IgemmSeg sg = p.seg[s];
+          for (int ch = 0; ch < sg.nchunk; ++ch, ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+            uint8_t* sb = sa + kBM * kBK * 2;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + p.BN * kBK * 2));
+            tma_load_4d(sa, &p.tmA[sg.map], &full_bar[stage], sg.c0 + ch * kBK, x0 + sg.dx,
+                        y0 + sg.dy, z0 + sg.dz);
+            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * kBK, nt * p.BN);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kBM, p.BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < nloc; ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t sb = sa + kBM * kBK * 2;
+          const uint64_t da = make_sdesc(sa, 16, 1024);
+          const uint64_t db = make_sdesc(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 32 bytes (16 bf16) inside the 128B swizzle atom: +2 in the >>4 address field
+            umma_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                    (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else {
+    // ================================ epilogue ====================================
+    const int q = warp & 3;  // TMEM lane quarter owned by this warp
+    const int r = q * 32 + lane;
+    const ctrlv_epilogue& ep = p.ep;
+    const int n_out_total = ep.geglu ? p.N / 2 : p.N;
+    const int n_store = ep.n_store > 0 ? ep.n_store : n_out_total;
+    for (int it = 0; it < nloc; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int nt = tile % p.tiles_n;
+      int mt = tile / p.tiles_n;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int tz = mt / p.tiles_y;
+      const int ix = r % p.bx;
+      const int iy = (r / p.bx) % p.by;
+      const int iz = r / (p.bx * p.by);
+      const int x = tx * p.bx + ix, y = ty * p.by + iy, z = tz * p.bz + iz;
+      const bool valid = (iz < p.bz) && (x < p.X) && (y < p.Y) && (z < p.Z);
+      const long long m = ((long long)z * p.Y + y) * p.X + x;
+
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+
+      const float* rb = nullptr;
+      if (ep.rb_mode != 0 && valid)
+        rb = ep.rowbias + (size_t)rowbias_index(ep, (int)m) * ep.ld_rowbias;
+
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
+      for (int c = 0; c < p.BN / 32; ++c) {
+        __syncwarp();
+        uint32_t raw[32];
+        tmem_ld32(t_row + (uint32_t)(c * 32), raw);
+        tmem_ld_wait();
+        const int n0 = nt * p.BN + c * 32;  // first GEMM column of this chunk
+        if (!valid || n0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (rb) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(rb + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (ep.geglu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * gelu_erf_f(v[2 * j + 1]);
+          ep_finish<16>(v, ep, m, n0 >> 1, n_store);
+        } else {
+          ep_finish<32>(v, ep, m, n0, n_store);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int g_max_smem = 0;
+
+static int device_props() {
+  if (g_num_sms) return CTRLV_OK;
+  int dev = 0;
+  CTRLV_CUDA(cudaGetDevice(&dev));
+  int sms = 0, smem = 0;
+  CTRLV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CTRLV_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  cudaFuncAttributes fa;
+  CTRLV_CUDA(cudaFuncGetAttributes(&fa, igemm_kernel));
+  smem -= (int)fa.sharedSizeBytes;  // static shared memory (barriers) counts against the limit
+  CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  g_max_smem = smem;
+  g_num_sms = sms;
+  return CTRLV_OK;
+}
+
+// choose the (bx, by, bz) row box (<= 128 rows) that wastes the fewest MMA rows
+static void choose_box(int X, int Y, int Z, int* bx, int* by, int* bz) {
+  double best = -1.0;
+  int bbx = 1, bby = 1, bbz = 1;
+  for (int cx = 1; cx <= (X < 128 ? X : 128); ++cx) {
+    if (!((X % cx == 0) || (cx == 128))) continue;
+    if (cx > 256) break;
+    for (int cy = 1; cy <= Y && cx * cy <= 128; ++cy) {
+      for (int cz = 1; cz <= Z && cx * cy * cz <= 128; ++cz) {
+        const long long tiles = (long long)((X + cx - 1) / cx) * ((Y + cy - 1) / cy) * ((Z + cz - 1) / cz);
+        const double eff = (double)X * Y * Z / ((double)tiles * 128.0);
+        // tie-break: prefer wide x (long contiguous TMA rows), then y
+        const double score = eff + 1e-6 * cx + 1e-9 * cy;
+        if (score > best) {
+          best = score;
+          bbx = cx; bby = cy; bbz = cz;
+        }
+      }
+    }
+  }
+  *bx = bbx; *by = bby; *bz = bbz;
+}
+
+static int choose_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0) return 128;
+  if (N % 192 == 0) return 192;
+  if (N % 96 == 0) return 96;
+  if (N % 64 == 0) return 64;
+  return 0;
+}
+
+static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
+  int rc = device_props();
+  if (rc) return rc;
+  CTRLV_CHECK_ARG(d != nullptr, "igemm: null descriptor");
+  CTRLV_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= CTRLV_MAX_SRC, "igemm: nsrc=%d out of range", d->nsrc);
+  CTRLV_CHECK_ARG(d->nseg >= 1 && d->nseg <= CTRLV_MAX_SEG, "igemm: nseg=%d out of range", d->nseg);
+  CTRLV_CHECK_ARG(d->X > 0 && d->Y > 0 && d->Z > 0, "igemm: empty row space %dx%dx%d", d->X, d->Y, d->Z);
+  CTRLV_CHECK_ARG(d->N > 0 && d->N % 32 == 0, "igemm: N=%d must be a positive multiple of 32", d->N);
+  CTRLV_CHECK_ARG(d->W != nullptr, "igemm: null weights");
+  CTRLV_CHECK_ARG((reinterpret_cast<uintptr_t>(d->W) & 15) == 0, "igemm: weights not 16B aligned");
+
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.X = d->X; p.Y = d->Y; p.Z = d->Z;
+  choose_box(d->X, d->Y, d->Z, &p.bx, &p.by, &p.bz);
+  p.tiles_x = (d->X + p.bx - 1) / p.bx;
+  p.tiles_y = (d->Y + p.by - 1) / p.by;
+  p.tiles_z = (d->Z + p.bz - 1) / p.bz;
+  p.N = d->N;
+  p.BN = d->bn > 0 ? d->bn : choose_bn(d->N);
+  if (p.BN == 0) {
+    // ragged N: largest 32-multiple tile, TMA zero-fills the weight rows past N
+    p.BN = d->N >= 256 ? 256 : ((d->N + 31) / 32) * 32;
+  }
+  CTRLV_CHECK_ARG(p.BN % 32 == 0 && p.BN >= 32 && p.BN <= 256, "igemm: bad n-tile %d", p.BN);
+  p.tiles_n = (d->N + p.BN - 1) / p.BN;
+  p.tiles_total = p.tiles_x * p.tiles_y * p.tiles_z * p.tiles_n;
+
+  int kblocks = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    const ctrlv_seg& sg = d->seg[s];
+    CTRLV_CHECK_ARG(sg.src >= 0 && sg.src < d->nsrc, "igemm: seg %d source %d out of range", s, sg.src);
+    CTRLV_CHECK_ARG(sg.nchunk > 0 && sg.c0 % 64 == 0 && sg.c0 + sg.nchunk * 64 <= d->src[sg.src].C,
+                    "igemm: seg %d channel range [%d,+%d*64) outside source C=%d", s, sg.c0, sg.nchunk,
+                    d->src[sg.src].C);
+    p.seg[s].map = sg.src; p.seg[s].c0 = sg.c0; p.seg[s].nchunk = sg.nchunk;
+    p.seg[s].dx = sg.dx; p.seg[s].dy = sg.dy; p.seg[s].dz = sg.dz;
+    kblocks += sg.nchunk;
+  }
+  CTRLV_CHECK_ARG(kblocks * 64 == d->K, "igemm: K=%d does not match segments (%d)", d->K, kblocks * 64);
+  p.nseg = d->nseg;
+  p.kblocks = kblocks;
+
+  for (int i = 0; i < d->nsrc; ++i) {
+    const ctrlv_src& s = d->src[i];
+    CTRLV_CHECK_ARG(s.ptr != nullptr && (reinterpret_cast<uintptr_t>(s.ptr) & 15) == 0,
+                    "igemm: source %d null or not 16B aligned", i);
+    CTRLV_CHECK_ARG(s.C % 64 == 0 && s.sx % 8 == 0 && s.sy % 8 == 0 && s.sz % 8 == 0,
+                    "igemm: source %d needs C%%64==0 and strides %%8==0", i);
+    uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)d->X, (uint64_t)d->Y, (uint64_t)d->Z};
+    uint64_t strides[3] = {(uint64_t)s.sx * 2, (uint64_t)s.sy * 2, (uint64_t)s.sz * 2};
+    uint32_t box[4] = {64, (uint32_t)p.bx, (uint32_t)p.by, (uint32_t)p.bz};
+    rc = encode_tmap_bf16(&p.tmA[i], s.ptr, 4, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+    uint64_t strides[1] = {(uint64_t)d->K * 2};
+    uint32_t box[2] = {64, (uint32_t)p.BN};
+    rc = encode_tmap_bf16(&p.tmB, d->W, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  p.a_bytes = 64 * p.bx * p.by * p.bz * 2;
+  p.stage_bytes = kBM * kBK * 2 + p.BN * kBK * 2;
+  int stages = (g_max_smem - 2048) / p.stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  CTRLV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for 2 stages");
+  p.stages = stages;
+  p.tmem_cols = 2 * p.BN <= 128 ? 128 : (2 * p.BN <= 256 ? 256 : 512);
+  p.ep = d->ep;
+  if (p.ep.s_acc == 0.0f && p.ep.res1 == nullptr && p.ep.res2 == nullptr) p.ep.s_acc = 1.0f;
+  CTRLV_CHECK_ARG(p.ep.out != nullptr || p.ep.out_f32 != nullptr, "igemm: no output");
+  if (p.ep.geglu) CTRLV_CHECK_ARG(d->N % 64 == 0, "igemm: GEGLU needs N %% 64 == 0");
+  if (p.ep.rb_mode != 0)
+    CTRLV_CHECK_ARG(p.ep.rowbias != nullptr && p.ep.rb_div > 0, "igemm: rowbias mode without table");
+  if (p.ep.rb_mode == 2 || p.ep.rb_mode == 3)
+    CTRLV_CHECK_ARG(p.ep.rb_mod > 0 && (p.ep.rb_mode == 2 || p.ep.rb_B > 0), "igemm: bad rowbias modulus");
+  // vector paths need 16B-aligned rows
+  const int n_out = p.ep.geglu ? d->N / 2 : d->N;
+  const int n_store = p.ep.n_store > 0 ? p.ep.n_store : n_out;
+  if (n_store >= 16) {
+    if (p.ep.out) CTRLV_CHECK_ARG(p.ep.ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(p.ep.out) & 15) == 0, "igemm: out must be 16B aligned (ld %% 8)");
+    if (p.ep.res1) CTRLV_CHECK_ARG(p.ep.ld_res1 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.ep.res1) & 15) == 0, "igemm: res1 must be 16B aligned");
+    if (p.ep.res2) CTRLV_CHECK_ARG(p.ep.ld_res2 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.ep.res2) & 15) == 0, "igemm: res2 must be 16B aligned");
+    if (p.ep.out_f32) CTRLV_CHECK_ARG(p.ep.ld_out_f32 % 4 == 0, "igemm: out_f32 ld %% 4");
+  }
+
+  const int grid = p.tiles_total < g_num_sms ? p.tiles_total : g_num_sms;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  igemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+  CTRLV_CUDA(cudaGetLastError());
+  return CTRLV_OK;
+}
+
+}  // namespace ctrlv
+
+using namespace ctrlv;
+
+extern "C" int ctrlv_igemm(const ctrlv_igemm_desc* desc, void* stream) {
+  return igemm_launch(desc, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ctrlv_linear(const void* A, int64_t lda, int32_t M, int32_t K, const void* W,
+                            int32_t N, const ctrlv_epilogue* ep, void* stream) {
+  CTRLV_CHECK_ARG(ep != nullptr, "linear: null epilogue");
+  CTRLV_CHECK_ARG(K % 64 == 0, "linear: K=%d must be a multiple of 64", K);
+  ctrlv_igemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.nsrc = 1;
+  d.src[0].ptr = A; d.src[0].C = K; d.src[0].sx = lda; d.src[0].sy = lda * (int64_t)M; d.src[0].sz = lda * (int64_t)M;
+  d.X = M; d.Y = 1; d.Z = 1;
+  d.nseg = 1;
+  d.seg[0].src = 0; d.seg[0].c0 = 0; d.seg[0].nchunk = K / 64;
+  d.W = W; d.N = N; d.K = K;
+  d.ep = *ep;
+  return igemm_launch(&d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ctrlv_conv3x3(const void* src0, int32_t C0, const void* src1, int32_t C1,
+                             int32_t frames, int32_t H, int32_t Wd, int32_t stride,
+                             const void* sc0, int32_t SC0, const void* sc1, int32_t SC1,
+                             const void* W, int32_t N, const ctrlv_epilogue* ep, void* stream) {
+  CTRLV_CHECK_ARG(ep != nullptr, "conv3x3: null epilogue");
+  CTRLV_CHECK_ARG(stride == 1 || stride == 2, "conv3x3: stride %d unsupported", stride);
+  CTRLV_CHECK_ARG(src0 != nullptr && C0 > 0 && C0 % 64 == 0 && C1 % 64 == 0 && SC0 % 64 == 0 && SC1 % 64 == 0,
+                  "conv3x3: channel counts must be multiples of 64");
+  const int Cin = C0 + (src1 ? C1 : 0);
+  ctrlv_igemm_desc d;
+  memset(&d, 0, sizeof(d));
+  int nseg = 0;
+  if (stride == 1) {
+    d.X = Wd; d.Y = H; d.Z = frames;
+    d.nsrc = 0;
+    const int i0 = d.nsrc++;
+    d.src[i0].ptr = src0; d.src[i0].C = C0; d.src[i0].sx = C0; d.src[i0].sy = (int64_t)C0 * Wd; d.src[i0].sz = (int64_t)C0 * Wd * H;
+    int i1 = -1;
+    if (src1) {
+      i1 = d.nsrc++;
+      d.src[i1].ptr = src1; d.src[i1].C = C1; d.src[i1].sx = C1; d.src[i1].sy = (int64_t)C1 * Wd; d.src[i1].sz = (int64_t)C1 * Wd * H;
+    }
+    // K order: [tap][src0 channels | src1 channels], then the optional raw shortcut sources
+    for (int t = 0; t < 9; ++t) {
+      ctrlv_seg& s = d.seg[nseg++];
+      s.src = i0; s.c0 = 0; s.nchunk = C0 / 64; s.dx = t % 3 - 1; s.dy = t / 3 - 1; s.dz = 0;
+      if (src1) {
+        ctrlv_seg& s1 = d.seg[nseg++];
+        s1.src = i1; s1.c0 = 0; s1.nchunk = C1 / 64; s1.dx = t % 3 - 1; s1.dy = t / 3 - 1; s1.dz = 0;
+      }
+    }
+    if (sc0) {
+      const int j0 = d.nsrc++;
+      d.src[j0].ptr = sc0; d.src[j0].C = SC0; d.src[j0].sx = SC0; d.src[j0].sy = (int64_t)SC0 * Wd; d.src[j0].sz = (int64_t)SC0 * Wd * H;
+      ctrlv_seg& s = d.seg[nseg++];
+      s.src = j0; s.c0 = 0; s.nchunk = SC0 / 64; s.dx = s.dy = s.dz = 0;
+      if (sc1) {
+        const int j1 = d.nsrc++;
+        d.src[j1].ptr = sc1; d.src[j1].C = SC1; d.src[j1].sx = SC1; d.src[j1].sy = (int64_t)SC1 * Wd; d.src[j1].sz = (int64_t)SC1 * Wd * H;
+        ctrlv_seg& s2 = d.seg[nseg++];
+        s2.src = j1; s2.c0 = 0; s2.nchunk = SC1 / 64; s2.dx = s2.dy = s2.dz = 0;
+      }
+    }
+    d.K = 9 * Cin + (sc0 ? SC0 + (sc1 ? SC1 : 0) : 0);
+  } else {
+    CTRLV_CHECK_ARG(src1 == nullptr && sc0 == nullptr, "conv3x3: stride 2 takes one source, no shortcut");
+    CTRLV_CHECK_ARG(H % 2 == 0 && Wd % 2 == 0, "conv3x3: stride 2 needs even H, W");
+    const int Ho = H / 2, Wo = Wd / 2;
+    d.X = Wo; d.Y = Ho; d.Z = frames;
+    // four parity sub-lattices of the input: (py, px); input pixel (2*oy + dy - 1, 2*ox + dx - 1)
+    d.nsrc = 4;
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        ctrlv_src& s = d.src[py * 2 + px];
+        s.ptr = reinterpret_cast<const bf16*>(src0) + ((int64_t)py * Wd + px) * C0;
+        s.C = C0; s.sx = 2 * (int64_t)C0; s.sy = 2 * (int64_t)C0 * Wd; s.sz = (int64_t)C0 * Wd * H;
+      }
+    for (int t = 0; t < 9; ++t) {
+      const int dy = t / 3 - 1, dx = t % 3 - 1;
+      const int py = dy & 1, px = dx & 1;          // -1 -> 1, 0 -> 0, 1 -> 1
+      const int oy = (dy - py) / 2, ox = (dx - px) / 2;  // -1 -> -1, 0 -> 0, 1 -> 0
+      ctrlv_seg& s = d.seg[nseg++];
+      s.src = py * 2 + px; s.c0 = 0; s.nchunk = C0 / 64; s.dx = ox; s.dy = oy; s.dz = 0;
+    }
+    d.K = 9 * C0;
+  }
+  d.nseg = nseg;
+  d.W = W; d.N = N;
+  d.ep = *ep;
+  return igemm_launch(&d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ctrlv_conv_t3(const void* src, int32_t C, int32_t B, int32_t T, int32_t HW,
+                             const void* W, int32_t N, const ctrlv_epilogue* ep, void* stream) {
+  CTRLV_CHECK_ARG(ep != nullptr, "conv_t3: null epilogue");
+  CTRLV_CHECK_ARG(C % 64 == 0, "conv_t3: C=%d must be a multiple of 64", C);
+  ctrlv_igemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.nsrc = 1;
+  d.src[0].ptr = src; d.src[0].C = C; d.src[0].sx = C; d.src[0].sy = (int64_t)C * HW; d.src[0].sz = (int64_t)C * HW * T;
+  d.X = HW; d.Y = T; d.Z = B;
+  d.nseg = 3;
+  for (int t = 0; t < 3; ++t) {
+    d.seg[t].src = 0; d.seg[t].c0 = 0; d.seg[t].nchunk = C / 64; d.seg[t].dx = 0; d.seg[t].dy = t - 1; d.seg[t].dz = 0;
+  }
+  d.W = W; d.N = N; d.K = 3 * C;
+  d.ep = *ep;
+  return igemm_launch(&d, reinterpret_cast<cudaStream_t>(stream));
+}

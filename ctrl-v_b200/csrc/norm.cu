@@ -1,0 +1,266 @@
+// GroupNorm (statistics + apply [+ SiLU], one or two channel-concatenated sources) and LayerNorm
+// on channels-last bf16 rows.  HBM-bound kernels: 16-byte vector loads/stores, fp32 statistics,
+// deterministic two-stage reduction (no float atomics in global memory).
+#include "common.cuh"
+#include "../../include/ctrlv_b200.h"
+
+namespace ctrlv {
+
+constexpr int kGroups = 32;
+constexpr int kMaxSplit = 256;
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm statistics: partial[unit][split][group][2] = (sum, sum of squares)
+// Thread layout: nthreads = vpr * rows_par (vpr = 16B vectors per row); thread t owns vector
+// column t % vpr for the whole kernel, so consecutive threads read consecutive 16 B.
+// ------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict__ src1,
+                                int C1, int rows_per_unit, int rows_per_split, int nsplit,
+                                float* __restrict__ partial) {
+  __shared__ float bins[kGroups * 2];
+  const int C = C0 + C1;
+  const int vpr = C >> 3;
+  const int cg = C / kGroups;
+  const int unit = blockIdx.x / nsplit;
+  const int split = blockIdx.x % nsplit;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kGroups * 2; i += blockDim.x) bins[i] = 0.f;
+  __syncthreads();
+  const int vec = tid % vpr;
+  const int rpar = blockDim.x / vpr;
+  const int rsub = tid / vpr;
+  const int c = vec << 3;
+  const bf16* base;
+  int ld;
+  if (c < C0) { base = src0 + c; ld = C0; } else { base = src1 + (c - C0); ld = C1; }
+  const int r_begin = split * rows_per_split;
+  int r_end = r_begin + rows_per_split;
+  if (r_end > rows_per_unit) r_end = rows_per_unit;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  const size_t row0 = (size_t)unit * rows_per_unit;
+  for (int r = r_begin + rsub; r < r_end; r += rpar) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (row0 + r) * ld));
+    float2 f;
+    f = unpack_bf16x2(u.x); s[0] += f.x + f.y; q[0] += f.x * f.x + f.y * f.y;
+    f = unpack_bf16x2(u.y); s[1] += f.x + f.y; q[1] += f.x * f.x + f.y * f.y;
+    f = unpack_bf16x2(u.z); s[2] += f.x + f.y; q[2] += f.x * f.x + f.y * f.y;
+    f = unpack_bf16x2(u.w); s[3] += f.x + f.y; q[3] += f.x * f.x + f.y * f.y;
+  }
+#pragma unroll
+  for (int pidx = 0; pidx < 4; ++pidx) {
+    const int g = (c + 2 * pidx) / cg;
+    atomicAdd(&bins[g * 2], s[pidx]);
+    atomicAdd(&bins[g * 2 + 1], q[pidx]);
+  }
+  __syncthreads();
+  for (int i = tid; i < kGroups * 2; i += blockDim.x)
+    partial[((size_t)unit * nsplit + split) * (kGroups * 2) + i] = bins[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm apply (+SiLU): out[row][C0+C1] = act((x - mean) * rstd * gamma + beta)
+// grid = n_units * blocks_per_unit; a block stays inside one statistics unit.
+// ------------------------------------------------------------------------------------------
+__global__ void gn_apply_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict__ src1,
+                                int C1, int rows_per_unit, int blocks_per_unit, int nsplit,
+                                const float* __restrict__ partial, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int silu,
+                                bf16* __restrict__ out) {
+  __shared__ float mean_s[kGroups], rstd_s[kGroups];
+  const int C = C0 + C1;
+  const int vpr = C >> 3;
+  const int cg = C / kGroups;
+  const int unit = blockIdx.x / blocks_per_unit;
+  const int blk = blockIdx.x % blocks_per_unit;
+  const int tid = threadIdx.x;
+  for (int gi = tid; gi < kGroups; gi += blockDim.x) {
+    // fixed-order (deterministic) reduction of the split partials; fp64 only for this tiny sum
+    double s = 0.0, q = 0.0;
+    const float* pp = partial + (size_t)unit * nsplit * (kGroups * 2) + gi * 2;
+    for (int i = 0; i < nsplit; ++i) {
+      s += (double)pp[(size_t)i * kGroups * 2];
+      q += (double)pp[(size_t)i * kGroups * 2 + 1];
+    }
+    const double cnt = (double)rows_per_unit * cg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_s[gi] = (float)mean;
+    rstd_s[gi] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int vec = tid % vpr;
+  const int rpar = blockDim.x / vpr;
+  const int rsub = tid / vpr;
+  const int c = vec << 3;
+  const bf16* base;
+  int ld;
+  if (c < C0) { base = src0 + c; ld = C0; } else { base = src1 + (c - C0); ld = C1; }
+  // per-channel scale/shift (fold mean/rstd into gamma/beta)
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cg;
+    const float ga = __ldg(gamma + c + j), be = __ldg(beta + c + j);
+    sc[j] = rstd_s[g] * ga;
+    sh[j] = be - mean_s[g] * sc[j];
+  }
+  const int rows_per_blk = (rows_per_unit + blocks_per_unit - 1) / blocks_per_unit;
+  const int r_begin = blk * rows_per_blk;
+  int r_end = r_begin + rows_per_blk;
+  if (r_end > rows_per_unit) r_end = rows_per_unit;
+  const size_t row0 = (size_t)unit * rows_per_unit;
+  for (int r = r_begin + rsub; r < r_end; r += rpar) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (row0 + r) * ld));
+    float v[8];
+    float2 f;
+    f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+    f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+    f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+    f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = v[j] * sc[j] + sh[j];
+      v[j] = silu ? silu_f(t) : t;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + (row0 + r) * C + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers (C <= 2048), two-pass statistics.
+// ------------------------------------------------------------------------------------------
+constexpr int kLnMaxIter = 8;
+
+__global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, int M, int C,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float eps, const float* __restrict__ rowbias, int ld_rowbias,
+                                 int rb_div, int rb_mod, bf16* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int vpr = C >> 3;
+  const bf16* xr = x + (size_t)warp * ldx;
+  const float* rb = rowbias ? rowbias + (size_t)((warp / rb_div) % rb_mod) * ld_rowbias : nullptr;
+  float v[kLnMaxIter][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxIter; ++i) {
+    const int vec = lane + 32 * i;
+    if (vec < vpr) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + vec * 8));
+      float2 f;
+      f = unpack_bf16x2(u.x); v[i][0] = f.x; v[i][1] = f.y;
+      f = unpack_bf16x2(u.y); v[i][2] = f.x; v[i][3] = f.y;
+      f = unpack_bf16x2(u.z); v[i][4] = f.x; v[i][5] = f.y;
+      f = unpack_bf16x2(u.w); v[i][6] = f.x; v[i][7] = f.y;
+      if (rb) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(rb + vec * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(rb + vec * 8 + 4));
+        v[i][0] += a.x; v[i][1] += a.y; v[i][2] += a.z; v[i][3] += a.w;
+        v[i][4] += b.x; v[i][5] += b.y; v[i][6] += b.z; v[i][7] += b.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxIter; ++i) {
+    const int vec = lane + 32 * i;
+    if (vec < vpr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+  bf16* orow = out + (size_t)warp * C;
+#pragma unroll
+  for (int i = 0; i < kLnMaxIter; ++i) {
+    const int vec = lane + 32 * i;
+    if (vec < vpr) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8 + 4));
+      float o[8];
+      o[0] = (v[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[i][1] - mean) * rstd * g0.y + b0.y;
+      o[2] = (v[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[i][3] - mean) * rstd * g0.w + b0.w;
+      o[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
+      o[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(orow + vec * 8) = u;
+    }
+  }
+}
+
+}  // namespace ctrlv
+
+using namespace ctrlv;
+
+extern "C" int64_t ctrlv_groupnorm_workspace(int32_t n_units) {
+  return (int64_t)n_units * kMaxSplit * kGroups * 2 * sizeof(float);
+}
+
+extern "C" int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, int32_t C1,
+                               int32_t n_units, int32_t rows_per_unit, const float* gamma,
+                               const float* beta, float eps, int32_t silu, void* out,
+                               void* workspace, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!src1) C1 = 0;
+  const int C = C0 + C1;
+  CTRLV_CHECK_ARG(src0 && out && workspace && gamma && beta, "groupnorm: null pointer");
+  CTRLV_CHECK_ARG(C0 % 8 == 0 && C1 % 8 == 0 && C % 64 == 0, "groupnorm: C0=%d C1=%d need %%8 and sum %%64", C0, C1);
+  CTRLV_CHECK_ARG(n_units > 0 && rows_per_unit > 0, "groupnorm: empty input");
+  const int vpr = C / 8;
+  CTRLV_CHECK_ARG(vpr <= 1024, "groupnorm: C=%d too wide", C);
+  int rpar = 512 / vpr;
+  if (rpar < 1) rpar = 1;
+  if (rpar > rows_per_unit) rpar = rows_per_unit;
+  const int nthreads = vpr * rpar;
+  // split each unit so that the grid has a few hundred blocks
+  int nsplit = (592 + n_units - 1) / n_units;
+  const int max_by_rows = (rows_per_unit + rpar - 1) / rpar;
+  if (nsplit > max_by_rows) nsplit = max_by_rows;
+  if (nsplit > kMaxSplit) nsplit = kMaxSplit;
+  if (nsplit < 1) nsplit = 1;
+  int rows_per_split = (rows_per_unit + nsplit - 1) / nsplit;
+  nsplit = (rows_per_unit + rows_per_split - 1) / rows_per_split;
+  float* partial = reinterpret_cast<float*>(workspace);
+  gn_stats_kernel<<<n_units * nsplit, nthreads, 0, stream>>>(
+      reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1, rows_per_unit,
+      rows_per_split, nsplit, partial);
+  CTRLV_CUDA(cudaGetLastError());
+  gn_apply_kernel<<<n_units * nsplit, nthreads, 0, stream>>>(
+      reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1, rows_per_unit,
+      nsplit, nsplit, partial, gamma, beta, eps, silu, reinterpret_cast<bf16*>(out));
+  CTRLV_CUDA(cudaGetLastError());
+  return CTRLV_OK;
+}
+
+extern "C" int ctrlv_layernorm(const void* x, int64_t ldx, int32_t M, int32_t C, const float* gamma,
+                               const float* beta, float eps, const float* rowbias,
+                               int32_t ld_rowbias, int32_t rb_div, int32_t rb_mod, void* out,
+                               void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTRLV_CHECK_ARG(x && out && gamma && beta, "layernorm: null pointer");
+  CTRLV_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * kLnMaxIter, "layernorm: C=%d unsupported", C);
+  CTRLV_CHECK_ARG(ldx % 8 == 0, "layernorm: ldx %% 8");
+  if (rowbias) CTRLV_CHECK_ARG(rb_div > 0 && rb_mod > 0 && ld_rowbias % 4 == 0, "layernorm: bad rowbias args");
+  const int warps_per_block = 8;
+  const int blocks = (M + warps_per_block - 1) / warps_per_block;
+  layernorm_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(
+      reinterpret_cast<const bf16*>(x), ldx, M, C, gamma, beta, eps, rowbias, ld_rowbias, rb_div,
+      rb_mod, reinterpret_cast<bf16*>(out));
+  CTRLV_CUDA(cudaGetLastError());
+  return CTRLV_OK;
+}

@@ -1,0 +1,198 @@
+/*
+ * ctrlv_b200 — C-ABI of the B200-native Box2Video denoise step.
+ *
+ * The reference (oooolga/Ctrl-V) has no native layer of its own: its hot path
+ *   src/ctrlv/pipelines/pipeline_video_control.py:298-343   (loop body)
+ *   src/ctrlv/models/controlnet.py:226-351                  (ControlNetModel.forward)
+ *   src/ctrlv/models/unet_spatio_temporal_condition.py:31-171 (UNet forward with residuals)
+ * dispatches through diffusers==0.27.2 modules to cuDNN / cuBLAS / SDPA.  The entry points
+ * below are what a replacement of that dispatch binds (ctypes stub: INTEGRATION.md).  Each
+ * one cites the reference op it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller; the library allocates nothing
+ *    on the hot path; every call is asynchronous on the `stream` passed (a cudaStream_t);
+ *  - activations are channels-last bf16: a tensor the reference holds as [frames, C, h, w]
+ *    is a row-major matrix [frames*h*w, C] here ("rows" = spatial sites, "cols" = channels);
+ *  - return value: 0 = ok, negative = error (ctrlv_last_error() gives the message); no C++
+ *    exception crosses the boundary.
+ */
+#ifndef CTRLV_B200_H_
+#define CTRLV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTRLV_OK 0
+#define CTRLV_ERR_INVALID (-1)
+#define CTRLV_ERR_CUDA (-2)
+#define CTRLV_ERR_UNSUPPORTED (-3)
+
+/* Last error message of the calling thread ("" if none). */
+const char* ctrlv_last_error(void);
+/* Library version string and the SM architecture it was compiled for ("sm_100a"). */
+const char* ctrlv_version(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), negative otherwise. */
+int ctrlv_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused epilogue of every tensor-core contraction (acc = fp32 accumulator of element (m, n)):
+ *     v   = acc + bias[n] + rowbias[ridx(m)][n]
+ *     v   = geglu ? v_value * gelu_erf(v_gate) : v          (columns interleaved value/gate)
+ *     out = s_acc * v + s_res1 * res1[m][n] + s_res2 * res2[m][n]
+ * This one form covers, in the reference:  Linear/Conv bias; ResnetBlock2D's
+ * `+ time_emb_proj(silu(temb))[:, :, None, None]`; GEGLU (diffusers FeedForward);
+ * residual adds; AlphaBlender `a*x_spatial + (1-a)*x_temporal`; the degenerate 1-token
+ * cross-attention (a per-sample vector); ControlNet `* conditioning_scale`
+ * (controlnet.py:343-344).
+ *   rb_mode 0: no rowbias        1: ridx = m / rb_div        2: ridx = (m / rb_div) % rb_mod
+ *   rb_mode 3: ridx = ((m / rb_div) * rb_mod + m % rb_mod) % rb_B   (diffusers-0.27.2
+ *              S-major `time_context` broadcast)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct ctrlv_epilogue {
+  const float* bias;    /* [N] fp32 or NULL */
+  const float* rowbias; /* [R][ld_rowbias] fp32 or NULL */
+  int32_t ld_rowbias;
+  int32_t rb_mode, rb_div, rb_mod, rb_B;
+  int32_t geglu;     /* 1: N/2 outputs per row */
+  float s_acc;       /* scale of the accumulator term */
+  const void* res1;  /* bf16 [M][ld_res1] or NULL */
+  int32_t ld_res1;
+  float s_res1;
+  const void* res2;  /* bf16 [M][ld_res2] or NULL */
+  int32_t ld_res2;
+  float s_res2;
+  void* out;         /* bf16 [M][ld_out] or NULL */
+  int32_t ld_out;
+  float* out_f32;    /* fp32 [M][ld_out_f32] or NULL */
+  int32_t ld_out_f32;
+  int32_t n_store;   /* number of valid output columns (0 = all) */
+} ctrlv_epilogue;
+
+/* One operand source of the implicit GEMM: a channels-last view [Z][Y][X][C] with element
+ * strides (sz, sy, sx, 1). */
+typedef struct ctrlv_src {
+  const void* ptr; /* bf16 */
+  int32_t C;       /* channels addressable in this source (multiple of 64) */
+  int64_t sx, sy, sz;
+} ctrlv_src;
+
+/* One K segment: `nchunk` chunks of 64 channels, starting at channel c0 of source `src`,
+ * read at coordinates (x+dx, y+dy, z+dz); out-of-range coordinates read zeros. */
+typedef struct ctrlv_seg {
+  int32_t src, c0, nchunk, dx, dy, dz;
+} ctrlv_seg;
+
+#define CTRLV_MAX_SRC 4
+#define CTRLV_MAX_SEG 20
+
+typedef struct ctrlv_igemm_desc {
+  int32_t nsrc;
+  ctrlv_src src[CTRLV_MAX_SRC];
+  int32_t X, Y, Z; /* output rows m = (z*Y + y)*X + x */
+  int32_t nseg;
+  ctrlv_seg seg[CTRLV_MAX_SEG];
+  const void* W;   /* bf16 [N][K], K = 64 * sum(nchunk), K contiguous */
+  int32_t N, K;
+  int32_t bn;      /* n-tile override (0 = auto) */
+  ctrlv_epilogue ep;
+} ctrlv_igemm_desc;
+
+/* The generic tcgen05 implicit-GEMM contraction (TMA-fed, TMEM accumulators, persistent).
+ * Everything below that is a convolution or a Linear is a thin wrapper over it. */
+int ctrlv_igemm(const ctrlv_igemm_desc* desc, void* stream);
+
+/* nn.Linear (diffusers Attention.to_q/k/v/to_out, FeedForward, proj_in/out, 1x1 convs incl. the
+ * ControlNet zero-convs controlnet.py:148-185,331-339):  out[M][N] = A[M][K] * W[N][K]^T. */
+int ctrlv_linear(const void* A, int64_t lda, int32_t M, int32_t K, const void* W, int32_t N,
+                 const ctrlv_epilogue* ep, void* stream);
+
+/* nn.Conv2d 3x3, padding 1, stride 1 or 2 (ResnetBlock2D.conv1/conv2, Downsample2D,
+ * Upsample2D.conv, conv_in, conv_out) on channels-last frames [frames][H][W][C].
+ *  - up to two input sources (src1 may be NULL): channel concat of the UNet skip connection
+ *    (torch.cat in the up blocks) without materialising it;
+ *  - optional fused 1x1 `conv_shortcut` over up to two raw sources appended to the K loop;
+ *    weights W[N][9*(C0+C1) + (SC0+SC1)], tap-major then channel. */
+int ctrlv_conv3x3(const void* src0, int32_t C0, const void* src1, int32_t C1, int32_t frames,
+                  int32_t H, int32_t Wd, int32_t stride, const void* sc0, int32_t SC0,
+                  const void* sc1, int32_t SC1, const void* W, int32_t N,
+                  const ctrlv_epilogue* ep, void* stream);
+
+/* nn.Conv3d kernel (3,1,1), padding (1,0,0) of TemporalResnetBlock on [B][T][HW][C]
+ * (zero halo per clip); weights W[N][3*C], tap-major. */
+int ctrlv_conv_t3(const void* src, int32_t C, int32_t B, int32_t T, int32_t HW, const void* W,
+                  int32_t N, const ctrlv_epilogue* ep, void* stream);
+
+/* nn.GroupNorm(32, C0+C1, eps) [+ SiLU] over `n_units` statistics units of `rows_per_unit`
+ * consecutive rows each (spatial norm: unit = one frame; TemporalResnetBlock norm: unit = one
+ * clip, i.e. statistics across frames).  Reads one or two sources (channel concat), writes the
+ * normalised (and activated) concat as bf16 [rows][C0+C1].
+ * `workspace` : fp32, at least ctrlv_groupnorm_workspace(n_units) bytes. */
+int64_t ctrlv_groupnorm_workspace(int32_t n_units);
+int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, int32_t C1, int32_t n_units,
+                    int32_t rows_per_unit, const float* gamma, const float* beta, float eps,
+                    int32_t silu, void* out, void* workspace, void* stream);
+
+/* nn.LayerNorm(C, eps) over rows, with an optional fp32 row-bias added first
+ * (x + rowbias[(m / rb_div) % rb_mod]): the frame-position embedding of
+ * TransformerSpatioTemporalModel. */
+int ctrlv_layernorm(const void* x, int64_t ldx, int32_t M, int32_t C, const float* gamma,
+                    const float* beta, float eps, const float* rowbias, int32_t ld_rowbias,
+                    int32_t rb_div, int32_t rb_mod, void* out, void* stream);
+
+/* Self-attention core (F.scaled_dot_product_attention in AttnProcessor2_0), head_dim 64, no
+ * mask, on a fused projection buffer qkv[rows][3*C] (q | k | v, heads of 64 channels).
+ *  spatial : rows = frames*S, sequences are the S sites of one frame;
+ *  temporal: rows = B*T*S, sequences are the T frames of one site (row stride S between
+ *            sequence elements) — no permute copy.
+ * out: bf16 [rows][C]. */
+int ctrlv_attn_spatial(const void* qkv, int32_t frames, int32_t S, int32_t heads, float scale,
+                       void* out, void* stream);
+int ctrlv_attn_temporal(const void* qkv, int32_t B, int32_t T, int32_t S, int32_t heads,
+                        float scale, void* out, void* stream);
+
+/* Small-M dense layers on CUDA cores (embedding MLPs, time_emb_proj, 1-token cross-attention
+ * value path): y[M][N] = act_in(x)[M][K] * W[N][K]^T + b, M <= 32; x, y fp32; W bf16.
+ * act_in: 0 none, 1 SiLU.  act_out: 0 none, 1 SiLU. */
+int ctrlv_small_linear(const float* x, int32_t M, int32_t K, const void* W, const float* bias,
+                       int32_t N, int32_t act_in, int32_t act_out, float* y, void* stream);
+
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): out[n][dim] =
+ * [cos(t*f_k) | sin(t*f_k)], f_k = exp(-ln(10000) k / (dim/2)); t fp32 [n]. `round_bf16`
+ * rounds the result through bf16 (the reference casts to the model dtype). */
+int ctrlv_sinusoid(const float* t, int32_t n, int32_t dim, int32_t round_bf16, float* out,
+                   void* stream);
+
+/* Loop-body glue of pipeline_video_control.py:300-304: builds the channels-last, 64-channel
+ * padded model input  [2B or B][T][h][w][64] = [latents/sqrt(sigma^2+1) | image_latents |
+ * control_cond | 0...]  from NCHW fp32 latents [B][T][4][h][w] and NCHW bf16/fp32 conditioning. */
+int ctrlv_prep_input(const float* latents, const float* image_latents, const float* control_cond,
+                     int32_t B, int32_t cfg, int32_t T, int32_t h, int32_t w, float sigma,
+                     void* out, void* stream);
+
+/* CFG combine + EulerDiscreteScheduler.step (v-prediction), pipeline_video_control.py:327-332:
+ * latents (fp32 NCHW [B][T][4][h][w]) updated in place from the model output
+ * noise [2B or B][T*h*w][ld_noise] fp32 channels-last (first 4 columns). guidance: [T] fp32. */
+int ctrlv_cfg_euler(float* latents, const float* noise, int32_t ld_noise, int32_t B, int32_t cfg,
+                    int32_t T, int32_t h, int32_t w, const float* guidance, float sigma,
+                    float sigma_next, int32_t round_bf16, void* stream);
+
+/* Elementwise / layout helpers. */
+int ctrlv_upsample2x(const void* src, int32_t frames, int32_t H, int32_t Wd, int32_t C, void* out,
+                     void* stream); /* F.interpolate(scale_factor=2, mode="nearest"), NHWC */
+int ctrlv_axpby(const void* x, const void* y, float a, float b, int64_t n, void* out,
+                void* stream); /* out = a*x + b*y, bf16 */
+/* [frames][C][HW] (fp32 or bf16) -> columns c_off..c_off+C of out[frames*HW][Cpad] (bf16); other
+ * columns are left untouched (zero-initialise the buffer once). */
+int ctrlv_nchw_to_nhwc(const void* src, int32_t src_is_f32, int32_t frames, int32_t C, int32_t HW,
+                       int32_t Cpad, int32_t c_off, void* out, void* stream);
+int ctrlv_nhwc_to_nchw(const void* src, int32_t src_is_f32, int64_t ld, int32_t frames, int32_t C,
+                       int32_t HW, int32_t out_is_f32, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTRLV_B200_H_ */
