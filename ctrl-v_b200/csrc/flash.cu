@@ -1,11 +1,343 @@
-// placeholder until the tcgen05 attention kernels land (next commit)
+// tcgen05 flash attention, head_dim 64, no mask — the core of diffusers' AttnProcessor2_0
+// (F.scaled_dot_product_attention) for both attention flavours of TransformerSpatioTemporalModel.
+//
+//  MODE 0, spatial : one CTA per (128-query tile, head, frame); keys/values streamed in blocks
+//                    of 128 through a 3-slot TMA ring; online softmax.
+//  MODE 1, temporal: sequences are the T frames of one spatial site.  G = 128/T sites are packed
+//                    into one 128-row tile (row = t*G + g) fetched by ONE 4-D TMA box straight
+//                    from the [B][T][S][3C] projection buffer (no permute copies); a block-diagonal
+//                    mask (same site) restricts each query to its own T keys.  HBM-bound.
+//
+//  S = Q K^T      : tcgen05.mma  M=128 N=128 K=64, both operands K-major from TMA (128B swizzle)
+//  softmax        : one thread per query row (TMEM lane == row): no shuffles; exp2 on raw scores
+//  O_blk = P V    : P written as bf16 to swizzled smem (K-major A operand), V used as loaded
+//                   (MN-major B operand); block result folded into fp32 registers with the
+//                   running-max rescale.
+//  TMEM: S 128 cols + O 64 cols (256 allocated) and ~97 KB smem -> 2 CTAs per SM overlap each
+//  other's softmax and MMA phases.
 #include "common.cuh"
 #include "../../include/ctrlv_b200.h"
-extern "C" int ctrlv_attn_spatial(const void*, int32_t, int32_t, int32_t, float, void*, void*) {
-  ctrlv::set_last_error("attn_spatial: not built yet");
-  return CTRLV_ERR_UNSUPPORTED;
+
+namespace ctrlv {
+
+constexpr int kAttnThreads = 192;
+constexpr int kTile = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
+
+struct AttnParams {
+  CUtensorMap tm;
+  int C, S, T, G, heads, nkv, box_bytes;
+  float c;  // softmax scale * log2(e)
+  bf16* out;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-extern "C" int ctrlv_attn_temporal(const void*, int32_t, int32_t, int32_t, int32_t, float, void*, void*) {
-  ctrlv::set_last_error("attn_temporal: not built yet");
-  return CTRLV_ERR_UNSUPPORTED;
+
+template <int MODE>
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_full, s_full, p_full, o_full;
+  __shared__ __align__(8) uint64_t kv_full[3], kv_empty[3];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + kTile;      // 3 slots
+  uint8_t* sP = smem + 4 * kTile;   // 2 atoms of [128 x 64]
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int nkv = p.nkv;
+
+  if (MODE == 1) {
+    // the temporal box covers G*T < 128 rows; the rest must be zero (0 * garbage would be NaN)
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < 4 * kTile / 16; i += kAttnThreads) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm);
+    mbar_init(&q_full, 1);
+    mbar_init(&s_full, 1);
+    mbar_init(&p_full, 4);
+    mbar_init(&o_full, 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tS = tmem_base;
+  const uint32_t tO = tmem_base + 128;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      const int colq = head * 64, colk = p.C + head * 64, colv = 2 * p.C + head * 64;
+      mbar_expect_tx(&q_full, (uint32_t)p.box_bytes);
+      if (MODE == 0)
+        tma_load_3d(sQ, &p.tm, &q_full, colq, blockIdx.x * 128, blockIdx.z);
+      else
+        tma_load_4d(sQ, &p.tm, &q_full, colq, blockIdx.x * p.G, 0, blockIdx.z);
+      for (int n = 0; n < 2 * nkv; ++n) {
+        const int slot = n % 3;
+        const uint32_t ph = (uint32_t)((n / 3) & 1);
+        mbar_wait(&kv_empty[slot], ph ^ 1);
+        mbar_expect_tx(&kv_full[slot], (uint32_t)p.box_bytes);
+        const int j = n >> 1;
+        const int col = (n & 1) ? colv : colk;
+        if (MODE == 0)
+          tma_load_3d(sKV + slot * kTile, &p.tm, &kv_full[slot], col, j * 128, blockIdx.z);
+        else
+          tma_load_4d(sKV + slot * kTile, &p.tm, &kv_full[slot], col, blockIdx.x * p.G, 0, blockIdx.z);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc(128, 128, 0, 0);
+      const uint32_t idesc_pv = make_idesc(128, 64, 0, 1);  // B (= V) is MN-major
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aKV = smem_u32(sKV);
+      auto issue_qk = [&](int j) {
+        const int n = 2 * j, slot = n % 3;
+        mbar_wait(&kv_full[slot], (uint32_t)((n / 3) & 1));
+        tc_fence_after();
+        const uint32_t aK = aKV + slot * kTile;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tS, make_sdesc(aQ + k * 32, 16, 1024), make_sdesc(aK + k * 32, 16, 1024), idesc_qk,
+                  (uint32_t)(k != 0));
+        umma_commit(&kv_empty[slot]);
+        umma_commit(&s_full);
+      };
+      mbar_wait(&q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&p_full, (uint32_t)(j & 1));  // P_j in smem, S_j consumed
+        tc_fence_after();
+        if (j + 1 < nkv) issue_qk(j + 1);
+        const int n = 2 * j + 1, slot = n % 3;
+        mbar_wait(&kv_full[slot], (uint32_t)((n / 3) & 1));
+        tc_fence_after();
+        const uint32_t aV = aKV + slot * kTile;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tO, make_sdesc(aP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+                  make_sdesc(aV + k * 2048, 1024, 1024), idesc_pv, (uint32_t)(k != 0));
+        umma_commit(&kv_empty[slot]);
+        umma_commit(&o_full);
+      }
+    }
+  } else {
+    // ============================ softmax / epilogue ==============================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float o_acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const int rg = (MODE == 1) ? (r % p.G) : 0;
+    // temporal mode: the T keys of this row's site sit at columns rg + t*G (block-diagonal mask)
+    uint32_t tmask[4] = {0u, 0u, 0u, 0u};
+    if (MODE == 1) {
+      for (int t = 0; t < p.T; ++t) {
+        const int col = rg + t * p.G;
+        tmask[col >> 5] |= 1u << (col & 31);
+      }
+    }
+    auto chunk_mask = [&](int kv0, int c) -> uint32_t {
+      if (MODE == 1) return c == 0 ? tmask[0] : (c == 1 ? tmask[1] : (c == 2 ? tmask[2] : tmask[3]));
+      const int nvalid = p.S - kv0 - c * 32;
+      return nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
+    };
+    uint8_t* prow = sP + r * 128;
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      const int kv0 = j * 128;
+      // ---- pass 1: row max over the valid columns
+      float m_blk = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tS + lane_off + c * 32, raw);
+        tmem_ld_wait();
+        const uint32_t okm = chunk_mask(kv0, c);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if ((okm >> i) & 1u) m_blk = fmaxf(m_blk, __uint_as_float(raw[i]));
+      }
+      const float m_new = fmaxf(m_run, m_blk);
+      const float alpha = ex2f((m_run - m_new) * p.c);
+      // ---- fold the previous block's P V into the fp32 accumulator (also frees the P buffer)
+      if (j > 0) {
+        mbar_wait(&o_full, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tO + lane_off + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(raw[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) o_acc[i] *= alpha;
+      l_run *= alpha;
+      m_run = m_new;
+      const float mc = m_new * p.c;
+      // ---- pass 2: P = exp2(s*c - m*c) as bf16 into swizzled smem
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tS + lane_off + c * 32, raw);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        const uint32_t okm = chunk_mask(kv0, c);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float pv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            pv[e] = ((okm >> (i + e)) & 1u) ? ex2f(__uint_as_float(raw[i + e]) * p.c - mc) : 0.f;
+          l_run += pv[0] + pv[1];
+          pk[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+        }
+        uint8_t* atom = prow + (c >> 1) * kTile;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ch = (c & 1) * 4 + i;
+          *reinterpret_cast<uint4*>(atom + ((ch ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full);
+    }
+    // ---- last block's P V, normalise, store
+    mbar_wait(&o_full, (uint32_t)((nkv - 1) & 1));
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tO + lane_off + c * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(raw[i]);
+    }
+    const float inv = 1.0f / l_run;
+    long long orow;
+    bool valid;
+    if (MODE == 0) {
+      const int s = blockIdx.x * 128 + r;
+      valid = s < p.S;
+      orow = (long long)blockIdx.z * p.S + s;
+    } else {
+      const int t = r / p.G;
+      const int s = blockIdx.x * p.G + rg;
+      valid = (t < p.T) && (s < p.S);
+      orow = ((long long)blockIdx.z * p.T + t) * p.S + s;
+    }
+    if (valid) {
+      uint4* op = reinterpret_cast<uint4*>(p.out + orow * p.C + head * 64);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(o_acc[8 * i] * inv, o_acc[8 * i + 1] * inv);
+        u.y = pack_bf16x2(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
+        u.z = pack_bf16x2(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv);
+        u.w = pack_bf16x2(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv);
+        op[i] = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static bool g_attn_init = false;
+static int attn_init() {
+  if (g_attn_init) return CTRLV_OK;
+  const int smem = 6 * kTile + 1024;
+  CTRLV_CUDA(cudaFuncSetAttribute(attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CTRLV_CUDA(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  g_attn_init = true;
+  return CTRLV_OK;
+}
+
+}  // namespace ctrlv
+
+using namespace ctrlv;
+
+extern "C" int ctrlv_attn_spatial(const void* qkv, int32_t frames, int32_t S, int32_t heads,
+                                  float scale, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = attn_init();
+  if (rc) return rc;
+  CTRLV_CHECK_ARG(qkv && out && frames > 0 && S > 0 && heads > 0, "attn_spatial: bad arguments");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = heads * 64; p.S = S; p.T = 1; p.G = 1; p.heads = heads;
+  p.nkv = (S + 127) / 128;
+  p.box_bytes = kTile;
+  p.c = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<bf16*>(out);
+  const uint64_t ld = 3ull * p.C;
+  uint64_t dims[3] = {ld, (uint64_t)S, (uint64_t)frames};
+  uint64_t strides[2] = {ld * 2, ld * 2 * (uint64_t)S};
+  uint32_t box[3] = {64, 128, 1};
+  rc = encode_tmap_bf16(&p.tm, qkv, 3, dims, strides, box, true);
+  if (rc) return rc;
+  dim3 grid((S + 127) / 128, heads, frames);
+  attn_kernel<0><<<grid, kAttnThreads, 6 * kTile + 1024, stream>>>(p);
+  CTRLV_CUDA(cudaGetLastError());
+  return CTRLV_OK;
+}
+
+extern "C" int ctrlv_attn_temporal(const void* qkv, int32_t B, int32_t T, int32_t S, int32_t heads,
+                                   float scale, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = attn_init();
+  if (rc) return rc;
+  CTRLV_CHECK_ARG(qkv && out && B > 0 && S > 0 && heads > 0, "attn_temporal: bad arguments");
+  CTRLV_CHECK_ARG(T >= 1 && T <= 128, "attn_temporal: T=%d unsupported (1..128)", T);
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = heads * 64; p.S = S; p.T = T; p.heads = heads;
+  p.G = 128 / T;
+  if (p.G > S) p.G = S;
+  p.nkv = 1;
+  p.box_bytes = 64 * p.G * T * 2;
+  p.c = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<bf16*>(out);
+  const uint64_t ld = 3ull * p.C;
+  uint64_t dims[4] = {ld, (uint64_t)S, (uint64_t)T, (uint64_t)B};
+  uint64_t strides[3] = {ld * 2, ld * 2 * (uint64_t)S, ld * 2 * (uint64_t)S * (uint64_t)T};
+  uint32_t box[4] = {64, (uint32_t)p.G, (uint32_t)T, 1};
+  rc = encode_tmap_bf16(&p.tm, qkv, 4, dims, strides, box, true);
+  if (rc) return rc;
+  dim3 grid((S + p.G - 1) / p.G, heads, B);
+  attn_kernel<1><<<grid, kAttnThreads, 6 * kTile + 1024, stream>>>(p);
+  CTRLV_CUDA(cudaGetLastError());
+  return CTRLV_OK;
 }

@@ -117,3 +117,167 @@ def conv_t3(x: torch.Tensor, B: int, T: int, HW: int, w: torch.Tensor, **kw) -> 
     check(lib().ctrlv_conv_t3(x.data_ptr(), Cc, B, T, HW, w.data_ptr(), N, C.byref(ep), _stream()),
           "ctrlv_conv_t3")
     return kw["out"] if kw.get("out") is not None else kw["out_f32"]
+
+
+_gn_ws = {}
+
+
+def _gn_workspace(n_units: int) -> torch.Tensor:
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    need = lib().ctrlv_groupnorm_workspace(n_units)
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() * 4 < need:
+        ws = torch.empty(max(need // 4, 1 << 16), dtype=torch.float32, device="cuda")
+        _gn_ws[key] = ws
+    return ws
+
+
+def groupnorm(x: torch.Tensor, n_units: int, rows_per_unit: int, gamma: torch.Tensor, beta: torch.Tensor,
+              eps: float, silu: bool, src1: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(32) [+SiLU] over statistics units of `rows_per_unit` rows; x (| src1) -> out."""
+    _req(x, BF16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    assert x.is_contiguous() and x.shape[0] == n_units * rows_per_unit
+    C0 = x.shape[1]
+    C1 = 0
+    if src1 is not None:
+        _req(src1, BF16, "src1"); assert src1.is_contiguous() and src1.shape[0] == x.shape[0]
+        C1 = src1.shape[1]
+    assert gamma.numel() == C0 + C1 and beta.numel() == C0 + C1
+    if out is None:
+        out = torch.empty((x.shape[0], C0 + C1), dtype=BF16, device="cuda")
+    if ws is None:
+        ws = _gn_workspace(n_units)
+    check(lib().ctrlv_groupnorm(x.data_ptr(), C0, _p(src1), C1, n_units, rows_per_unit, gamma.data_ptr(),
+                                beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), ws.data_ptr(),
+                                _stream()), "ctrlv_groupnorm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              rowbias: Optional[torch.Tensor] = None, rb_div: int = 1, rb_mod: int = 1,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, BF16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    M, Cc = x.shape
+    assert x.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, Cc), dtype=BF16, device="cuda")
+    if rowbias is not None:
+        _req(rowbias, torch.float32, "rowbias")
+    check(lib().ctrlv_layernorm(x.data_ptr(), x.stride(0), M, Cc, gamma.data_ptr(), beta.data_ptr(), eps,
+                                _p(rowbias), rowbias.stride(0) if rowbias is not None else 0, rb_div,
+                                rb_mod, out.data_ptr(), _stream()), "ctrlv_layernorm")
+    return out
+
+
+def attn_spatial(qkv: torch.Tensor, frames: int, S: int, heads: int, scale: Optional[float] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(qkv, BF16, "qkv")
+    Cc = heads * 64
+    assert qkv.is_contiguous() and qkv.shape == (frames * S, 3 * Cc), (qkv.shape, frames, S, heads)
+    if out is None:
+        out = torch.empty((frames * S, Cc), dtype=BF16, device="cuda")
+    check(lib().ctrlv_attn_spatial(qkv.data_ptr(), frames, S, heads, scale if scale is not None else 0.125,
+                                   out.data_ptr(), _stream()), "ctrlv_attn_spatial")
+    return out
+
+
+def attn_temporal(qkv: torch.Tensor, B: int, T: int, S: int, heads: int, scale: Optional[float] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(qkv, BF16, "qkv")
+    Cc = heads * 64
+    assert qkv.is_contiguous() and qkv.shape == (B * T * S, 3 * Cc)
+    if out is None:
+        out = torch.empty((B * T * S, Cc), dtype=BF16, device="cuda")
+    check(lib().ctrlv_attn_temporal(qkv.data_ptr(), B, T, S, heads, scale if scale is not None else 0.125,
+                                    out.data_ptr(), _stream()), "ctrlv_attn_temporal")
+    return out
+
+
+def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 act_in: bool = False, act_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = act_out(act_in(x) @ w^T + b) for M <= 64 rows; x, y fp32, w bf16."""
+    _req(x, torch.float32, "x"); _req(w, BF16, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.is_contiguous() and w.is_contiguous() and w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    check(lib().ctrlv_small_linear(x.data_ptr(), M, K, w.data_ptr(), _p(bias), N, 1 if act_in else 0,
+                                   1 if act_out else 0, out.data_ptr(), _stream()), "ctrlv_small_linear")
+    return out
+
+
+def sinusoid(t: torch.Tensor, dim: int, round_bf16: bool = True) -> torch.Tensor:
+    _req(t, torch.float32, "t")
+    t = t.contiguous()
+    out = torch.empty((t.numel(), dim), dtype=torch.float32, device="cuda")
+    check(lib().ctrlv_sinusoid(t.data_ptr(), t.numel(), dim, 1 if round_bf16 else 0, out.data_ptr(), _stream()),
+          "ctrlv_sinusoid")
+    return out
+
+
+def prep_input(latents: torch.Tensor, image_latents: Optional[torch.Tensor], control_cond: Optional[torch.Tensor],
+               cfg: bool, sigma: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(latents, torch.float32, "latents")
+    B, T, c4, h, w = latents.shape
+    assert c4 == 4 and latents.is_contiguous()
+    nb = 2 * B if cfg else B
+    for t in (image_latents, control_cond):
+        if t is not None:
+            _req(t, torch.float32, "cond"); assert t.is_contiguous() and t.shape == (nb, T, 4, h, w), t.shape
+    if out is None:
+        out = torch.empty((nb * T * h * w, 64), dtype=BF16, device="cuda")
+    check(lib().ctrlv_prep_input(latents.data_ptr(), _p(image_latents), _p(control_cond), B, 1 if cfg else 0,
+                                 T, h, w, float(sigma), out.data_ptr(), _stream()), "ctrlv_prep_input")
+    return out
+
+
+def cfg_euler(latents: torch.Tensor, noise: torch.Tensor, cfg: bool, guidance: Optional[torch.Tensor],
+              sigma: float, sigma_next: float, round_bf16: bool = False) -> torch.Tensor:
+    _req(latents, torch.float32, "latents"); _req(noise, torch.float32, "noise")
+    B, T, c4, h, w = latents.shape
+    assert latents.is_contiguous() and noise.stride(1) == 1
+    check(lib().ctrlv_cfg_euler(latents.data_ptr(), noise.data_ptr(), noise.stride(0), B, 1 if cfg else 0, T, h,
+                                w, _p(guidance), float(sigma), float(sigma_next), 1 if round_bf16 else 0,
+                                _stream()), "ctrlv_cfg_euler")
+    return latents
+
+
+def upsample2x(x: torch.Tensor, frames: int, H: int, W: int) -> torch.Tensor:
+    _req(x, BF16, "x")
+    Cc = x.shape[1]
+    assert x.is_contiguous() and x.shape[0] == frames * H * W
+    out = torch.empty((frames * 4 * H * W, Cc), dtype=BF16, device="cuda")
+    check(lib().ctrlv_upsample2x(x.data_ptr(), frames, H, W, Cc, out.data_ptr(), _stream()), "ctrlv_upsample2x")
+    return out
+
+
+def axpby(x: torch.Tensor, y: torch.Tensor, a: float = 1.0, b: float = 1.0,
+          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, BF16, "x"); _req(y, BF16, "y")
+    assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().ctrlv_axpby(x.data_ptr(), y.data_ptr(), a, b, x.numel(), out.data_ptr(), _stream()), "ctrlv_axpby")
+    return out
+
+
+def nchw_to_nhwc(src: torch.Tensor, out: torch.Tensor, c_off: int = 0) -> torch.Tensor:
+    """src [frames, C, H, W] (fp32/bf16, contiguous) -> columns c_off.. of out [frames*H*W, Cpad] bf16."""
+    assert src.is_contiguous() and src.dtype in (torch.float32, BF16)
+    frames, Cc, H, W = src.shape
+    _req(out, BF16, "out")
+    assert out.is_contiguous() and out.shape[0] == frames * H * W
+    check(lib().ctrlv_nchw_to_nhwc(src.data_ptr(), 1 if src.dtype == torch.float32 else 0, frames, Cc, H * W,
+                                   out.shape[1], c_off, out.data_ptr(), _stream()), "ctrlv_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(src: torch.Tensor, frames: int, Cc: int, H: int, W: int, dtype=torch.float32) -> torch.Tensor:
+    assert src.stride(1) == 1 and src.dtype in (torch.float32, BF16) and dtype in (torch.float32, BF16)
+    out = torch.empty((frames, Cc, H, W), dtype=dtype, device="cuda")
+    check(lib().ctrlv_nhwc_to_nchw(src.data_ptr(), 1 if src.dtype == torch.float32 else 0, src.stride(0), frames,
+                                   Cc, H * W, 1 if dtype == torch.float32 else 0, out.data_ptr(), _stream()),
+          "ctrlv_nhwc_to_nchw")
+    return out
