@@ -88,10 +88,10 @@ SIGNATURES = {
     "ctrlv_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _I, _P, _P]),
     "ctrlv_attn_spatial": (_I, [_P, _I, _I, _I, _F, _P, _P]),
     "ctrlv_attn_temporal": (_I, [_P, _I, _I, _I, _I, _F, _P, _P]),
-    "ctrlv_small_linear": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
+    "ctrlv_small_linear": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ctrlv_sinusoid": (_I, [_P, _I, _I, _I, _P, _P]),
-    "ctrlv_prep_input": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
-    "ctrlv_cfg_euler": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _F, _F, _I, _P]),
+    "ctrlv_prep_input": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "ctrlv_cfg_euler": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "ctrlv_upsample2x": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "ctrlv_axpby": (_I, [_P, _P, _F, _F, _L, _P, _P]),
     "ctrlv_nchw_to_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -11,7 +11,8 @@ namespace ctrlv {
 // ------------------------------------------------------------------------------------------
 __global__ void small_linear_kernel(const float* __restrict__ x, int M, int K,
                                     const bf16* __restrict__ W, const float* __restrict__ bias,
-                                    int N, int act_in, int act_out, float* __restrict__ y) {
+                                    int N, int act_in, int act_out, int accumulate,
+                                    float* __restrict__ y) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -46,7 +47,9 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int M, int K,
       const float s = warp_sum(acc[mi]);
       if (lane == 0 && m0 + mi < M) {
         float t = s + (bias ? bias[n] : 0.f);
-        y[(size_t)(m0 + mi) * N + n] = act_out ? silu_f(t) : t;
+        t = act_out ? silu_f(t) : t;
+        float* yp = y + (size_t)(m0 + mi) * N + n;
+        *yp = accumulate ? *yp + t : t;
       }
     }
   }
@@ -75,7 +78,9 @@ __global__ void sinusoid_kernel(const float* __restrict__ t, int n, int dim, int
 //                              control_cond[bb] (4) | zeros]
 __global__ void prep_input_kernel(const float* __restrict__ lat, const float* __restrict__ img,
                                   const float* __restrict__ ctl, int B, int nb, int T, int hw,
-                                  float inv_scale, bf16* __restrict__ out) {
+                                  const float* __restrict__ sigma_dev, bf16* __restrict__ out) {
+  const float sg = __ldg(sigma_dev);
+  const float inv_scale = rsqrtf(sg * sg + 1.0f);
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)nb * T * hw;
   if (idx >= total) return;
@@ -106,7 +111,8 @@ __global__ void prep_input_kernel(const float* __restrict__ lat, const float* __
 // CFG combine + Euler (v-prediction) update, in fp32
 __global__ void cfg_euler_kernel(float* __restrict__ lat, const float* __restrict__ noise, int ldn,
                                  int B, int cfg, int T, int hw, const float* __restrict__ guidance,
-                                 float sigma, float sigma_next, int round_bf16) {
+                                 const float* __restrict__ sigma_dev, int round_bf16) {
+  const float sigma = __ldg(sigma_dev), sigma_next = __ldg(sigma_dev + 1);
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * T * hw;
   if (idx >= total) return;
@@ -197,13 +203,13 @@ static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) 
 
 extern "C" int ctrlv_small_linear(const float* x, int32_t M, int32_t K, const void* W,
                                   const float* bias, int32_t N, int32_t act_in, int32_t act_out,
-                                  float* y, void* stream_) {
+                                  int32_t accumulate, float* y, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTRLV_CHECK_ARG(x && W && y, "small_linear: null pointer");
   CTRLV_CHECK_ARG(M > 0 && M <= 64 && K % 8 == 0 && N > 0, "small_linear: M=%d K=%d N=%d unsupported", M, K, N);
   const int wpb = 8;
   small_linear_kernel<<<nblk(N, wpb), wpb * 32, 0, stream>>>(x, M, K, reinterpret_cast<const bf16*>(W),
-                                                            bias, N, act_in, act_out, y);
+                                                            bias, N, act_in, act_out, accumulate, y);
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }
@@ -219,27 +225,25 @@ extern "C" int ctrlv_sinusoid(const float* t, int32_t n, int32_t dim, int32_t ro
 
 extern "C" int ctrlv_prep_input(const float* latents, const float* image_latents,
                                 const float* control_cond, int32_t B, int32_t cfg, int32_t T,
-                                int32_t h, int32_t w, float sigma, void* out, void* stream_) {
+                                int32_t h, int32_t w, const float* sigma_dev, void* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CTRLV_CHECK_ARG(latents && out, "prep_input: null pointer");
+  CTRLV_CHECK_ARG(latents && out && sigma_dev, "prep_input: null pointer");
   const int nb = cfg ? 2 * B : B;
   const long long total = (long long)nb * T * h * w;
   prep_input_kernel<<<nblk(total, 256), 256, 0, stream>>>(latents, image_latents, control_cond, B, nb,
-                                                          T, h * w, 1.0f / sqrtf(sigma * sigma + 1.0f),
-                                                          reinterpret_cast<bf16*>(out));
+                                                          T, h * w, sigma_dev, reinterpret_cast<bf16*>(out));
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }
 
 extern "C" int ctrlv_cfg_euler(float* latents, const float* noise, int32_t ld_noise, int32_t B,
                                int32_t cfg, int32_t T, int32_t h, int32_t w, const float* guidance,
-                               float sigma, float sigma_next, int32_t round_bf16, void* stream_) {
+                               const float* sigma_dev, int32_t round_bf16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CTRLV_CHECK_ARG(latents && noise && ld_noise >= 4, "cfg_euler: bad arguments");
-  CTRLV_CHECK_ARG(sigma > 0.f, "cfg_euler: sigma must be positive");
+  CTRLV_CHECK_ARG(latents && noise && sigma_dev && ld_noise >= 4, "cfg_euler: bad arguments");
   const long long total = (long long)B * T * h * w;
   cfg_euler_kernel<<<nblk(total, 256), 256, 0, stream>>>(latents, noise, ld_noise, B, cfg, T, h * w,
-                                                         guidance, sigma, sigma_next, round_bf16);
+                                                         guidance, sigma_dev, round_bf16);
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }

@@ -1,0 +1,731 @@
+"""Drop-in models of the Box2Video hot path on the sm_100a kernels.
+
+Mirrors the reference's module interface for this path (same class names, forward signatures,
+argument meaning and error behaviour):
+
+  ControlNetModel.forward(sample, timestep, encoder_hidden_states, added_time_ids, control_cond,
+                          conditioning_scale, return_dict)
+        <- /root/reference/src/ctrlv/models/controlnet.py:226-351
+  UNetSpatioTemporalConditionModel.forward(sample, timestep, encoder_hidden_states,
+                          added_time_ids, down_block_additional_residuals,
+                          mid_block_additional_residuals, return_dict)
+        <- /root/reference/src/ctrlv/models/unet_spatio_temporal_condition.py:31-171
+
+Weights live in a flat dict keyed by the diffusers state-dict names and are
+repacked once into kernel layouts (bf16 K-major matrices, fp32 biases / norm affine).  Every
+contraction, norm and attention below is a call into libctrlv_b200.so — there is no PyTorch
+math on the path (torch provides device memory, views and streams only).
+
+Activations are channels-last: a reference tensor [B*T, C, h, w] is a [B*T*h*w, C] bf16 matrix.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+SVD_CONFIG = dict(
+    sample_size=None, in_channels=8, out_channels=4,
+    down_block_types=("CrossAttnDownBlockSpatioTemporal", "CrossAttnDownBlockSpatioTemporal",
+                      "CrossAttnDownBlockSpatioTemporal", "DownBlockSpatioTemporal"),
+    up_block_types=("UpBlockSpatioTemporal", "CrossAttnUpBlockSpatioTemporal",
+                    "CrossAttnUpBlockSpatioTemporal", "CrossAttnUpBlockSpatioTemporal"),
+    block_out_channels=(320, 640, 1280, 1280), addition_time_embed_dim=256,
+    projection_class_embeddings_input_dim=768, layers_per_block=2, cross_attention_dim=1024,
+    transformer_layers_per_block=1, num_attention_heads=(5, 10, 20, 20), num_frames=25,
+)
+
+
+def _tup(v, n):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter specification (names + shapes of the diffusers state dict)
+# ------------------------------------------------------------------------------------------------
+def _spec_linear(spec, name, i, o, bias=True):
+    spec[name + ".weight"] = (o, i)
+    if bias:
+        spec[name + ".bias"] = (o,)
+
+
+def _spec_norm(spec, name, c):
+    spec[name + ".weight"] = (c,)
+    spec[name + ".bias"] = (c,)
+
+
+def _spec_resblock(spec, pfx, cin, cout, temb):
+    s = pfx + ".spatial_res_block"
+    _spec_norm(spec, s + ".norm1", cin)
+    spec[s + ".conv1.weight"] = (cout, cin, 3, 3); spec[s + ".conv1.bias"] = (cout,)
+    _spec_linear(spec, s + ".time_emb_proj", temb, cout)
+    _spec_norm(spec, s + ".norm2", cout)
+    spec[s + ".conv2.weight"] = (cout, cout, 3, 3); spec[s + ".conv2.bias"] = (cout,)
+    if cin != cout:
+        spec[s + ".conv_shortcut.weight"] = (cout, cin, 1, 1); spec[s + ".conv_shortcut.bias"] = (cout,)
+    t = pfx + ".temporal_res_block"
+    _spec_norm(spec, t + ".norm1", cout)
+    spec[t + ".conv1.weight"] = (cout, cout, 3, 1, 1); spec[t + ".conv1.bias"] = (cout,)
+    _spec_linear(spec, t + ".time_emb_proj", temb, cout)
+    _spec_norm(spec, t + ".norm2", cout)
+    spec[t + ".conv2.weight"] = (cout, cout, 3, 1, 1); spec[t + ".conv2.bias"] = (cout,)
+    spec[pfx + ".time_mixer.mix_factor"] = (1,)
+
+
+def _spec_attn(spec, pfx, dim, kv_dim):
+    _spec_linear(spec, pfx + ".to_q", dim, dim, bias=False)
+    _spec_linear(spec, pfx + ".to_k", kv_dim, dim, bias=False)
+    _spec_linear(spec, pfx + ".to_v", kv_dim, dim, bias=False)
+    _spec_linear(spec, pfx + ".to_out.0", dim, dim)
+
+
+def _spec_ff(spec, pfx, dim):
+    _spec_linear(spec, pfx + ".net.0.proj", dim, 8 * dim)
+    _spec_linear(spec, pfx + ".net.2", 4 * dim, dim)
+
+
+def _spec_transformer(spec, pfx, c, xdim):
+    _spec_norm(spec, pfx + ".norm", c)
+    _spec_linear(spec, pfx + ".proj_in", c, c)
+    b = pfx + ".transformer_blocks.0"
+    _spec_norm(spec, b + ".norm1", c); _spec_attn(spec, b + ".attn1", c, c)
+    _spec_norm(spec, b + ".norm2", c); _spec_attn(spec, b + ".attn2", c, xdim)
+    _spec_norm(spec, b + ".norm3", c); _spec_ff(spec, b + ".ff", c)
+    t = pfx + ".temporal_transformer_blocks.0"
+    _spec_norm(spec, t + ".norm_in", c); _spec_ff(spec, t + ".ff_in", c)
+    _spec_norm(spec, t + ".norm1", c); _spec_attn(spec, t + ".attn1", c, c)
+    _spec_norm(spec, t + ".norm2", c); _spec_attn(spec, t + ".attn2", c, xdim)
+    _spec_norm(spec, t + ".norm3", c); _spec_ff(spec, t + ".ff", c)
+    _spec_linear(spec, pfx + ".time_pos_embed.linear_1", c, 4 * c)
+    _spec_linear(spec, pfx + ".time_pos_embed.linear_2", 4 * c, c)
+    spec[pfx + ".time_mixer.mix_factor"] = (1,)
+    _spec_linear(spec, pfx + ".proj_out", c, c)
+
+
+def param_spec(cfg: dict, controlnet: bool) -> "OrderedDict[str, tuple]":
+    """Names and shapes of the diffusers-format state dict of the UNet (or ControlNet)."""
+    spec: "OrderedDict[str, tuple]" = OrderedDict()
+    boc = tuple(cfg["block_out_channels"])
+    n = len(boc)
+    heads = _tup(cfg["num_attention_heads"], n)
+    xdim = _tup(cfg["cross_attention_dim"], n)
+    lpb = _tup(cfg["layers_per_block"], n)
+    temb = boc[0] * 4
+    spec["conv_in.weight"] = (boc[0], cfg["in_channels"], 3, 3); spec["conv_in.bias"] = (boc[0],)
+    _spec_linear(spec, "time_embedding.linear_1", boc[0], temb)
+    _spec_linear(spec, "time_embedding.linear_2", temb, temb)
+    _spec_linear(spec, "add_embedding.linear_1", cfg["projection_class_embeddings_input_dim"], temb)
+    _spec_linear(spec, "add_embedding.linear_2", temb, temb)
+    out_ch = boc[0]
+    for i, t in enumerate(cfg["down_block_types"]):
+        in_ch, out_ch = out_ch, boc[i]
+        for j in range(lpb[i]):
+            _spec_resblock(spec, f"down_blocks.{i}.resnets.{j}", in_ch if j == 0 else out_ch, out_ch, temb)
+        if t.startswith("CrossAttn"):
+            for j in range(lpb[i]):
+                _spec_transformer(spec, f"down_blocks.{i}.attentions.{j}", out_ch, xdim[i])
+        if i != n - 1:
+            spec[f"down_blocks.{i}.downsamplers.0.conv.weight"] = (out_ch, out_ch, 3, 3)
+            spec[f"down_blocks.{i}.downsamplers.0.conv.bias"] = (out_ch,)
+    _spec_resblock(spec, "mid_block.resnets.0", boc[-1], boc[-1], temb)
+    _spec_transformer(spec, "mid_block.attentions.0", boc[-1], xdim[-1])
+    _spec_resblock(spec, "mid_block.resnets.1", boc[-1], boc[-1], temb)
+    if controlnet:
+        spec["control_conv_in.weight"] = (boc[0], cfg["in_channels"] // 2, 3, 3)
+        spec["control_conv_in.bias"] = (boc[0],)
+        chans = [boc[0]]
+        for i, ch in enumerate(boc):
+            chans += [ch] * lpb[i]
+            if i != n - 1:
+                chans.append(ch)
+        for k, ch in enumerate(chans):
+            spec[f"controlnet_down_blocks.{k}.weight"] = (ch, ch, 1, 1)
+            spec[f"controlnet_down_blocks.{k}.bias"] = (ch,)
+        spec["controlnet_mid_block.weight"] = (boc[-1], boc[-1], 1, 1)
+        spec["controlnet_mid_block.bias"] = (boc[-1],)
+        return spec
+    rboc, rheads, rlpb, rxdim = boc[::-1], heads[::-1], lpb[::-1], xdim[::-1]
+    out_ch = rboc[0]
+    for i, t in enumerate(cfg["up_block_types"]):
+        prev, out_ch = out_ch, rboc[i]
+        in_ch = rboc[min(i + 1, n - 1)]
+        nl = rlpb[i] + 1
+        for j in range(nl):
+            skip = in_ch if j == nl - 1 else out_ch
+            rin = prev if j == 0 else out_ch
+            _spec_resblock(spec, f"up_blocks.{i}.resnets.{j}", rin + skip, out_ch, temb)
+        if t.startswith("CrossAttn"):
+            for j in range(nl):
+                _spec_transformer(spec, f"up_blocks.{i}.attentions.{j}", out_ch, rxdim[i])
+        if i != n - 1:
+            spec[f"up_blocks.{i}.upsamplers.0.conv.weight"] = (out_ch, out_ch, 3, 3)
+            spec[f"up_blocks.{i}.upsamplers.0.conv.bias"] = (out_ch,)
+    _spec_norm(spec, "conv_norm_out", boc[0])
+    spec["conv_out.weight"] = (cfg["out_channels"], boc[0], 3, 3); spec["conv_out.bias"] = (cfg["out_channels"],)
+    return spec
+
+
+def random_state_dict(cfg: dict, controlnet: bool, seed: int = 0, device="cuda",
+                      dtype=BF16, zero_conv_std: float = 0.02) -> Dict[str, torch.Tensor]:
+    """Random-init weights with PyTorch's default layer statistics (uniform(+-1/sqrt(fan_in)),
+    norm affine = (1, 0), mix_factor = 0.5), drawn directly on the device.  The ControlNet
+    zero-convs get N(0, zero_conv_std^2) instead of zeros so that the injection path carries
+    signal."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    spec = param_spec(cfg, controlnet)
+    for name, shape in spec.items():
+        if name.endswith("mix_factor"):
+            t = torch.full(shape, 0.5, device=device)
+        elif len(shape if name.endswith("weight") else spec[name[:-4] + "weight"]) == 1:  # norm affine
+            t = torch.ones(shape, device=device) if name.endswith("weight") else torch.zeros(shape, device=device)
+        elif name.startswith("controlnet_"):
+            t = torch.randn(shape, device=device, generator=g) * zero_conv_std
+        else:
+            wshape = shape if name.endswith("weight") else spec[name[:-4] + "weight"]
+            fan_in = 1
+            for d in wshape[1:]:
+                fan_in *= d
+            bound = 1.0 / math.sqrt(fan_in)
+            t = (torch.rand(shape, device=device, generator=g) * 2 - 1) * bound
+        sd[name] = t.to(dtype)
+    return sd
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing
+# ------------------------------------------------------------------------------------------------
+def _w(t):  # matrix operand
+    return t.detach().to(device="cuda", dtype=BF16).contiguous()
+
+
+def _f(t):  # fp32 vector
+    return t.detach().to(device="cuda", dtype=torch.float32).contiguous()
+
+
+def _conv9(w):  # [Cout, Cin, 3, 3] -> [Cout, 9*Cin], tap-major
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+def _conv_t3(w):  # [Cout, Cin, 3, 1, 1] -> [Cout, 3*Cin]
+    return w[:, :, :, 0, 0].permute(0, 2, 1).reshape(w.shape[0], -1)
+
+
+def _interleave_geglu(w, b):
+    """GEGLU proj rows [0:inner] are values, [inner:2*inner] gates (diffusers `chunk(2, -1)`);
+    interleave them so a (value, gate) pair sits in adjacent GEMM columns."""
+    inner = w.shape[0] // 2
+    wi = torch.stack([w[:inner], w[inner:]], dim=1).reshape(w.shape[0], w.shape[1])
+    bi = torch.stack([b[:inner], b[inner:]], dim=1).reshape(-1)
+    return wi, bi
+
+
+class _Lin:
+    def __init__(self, sd, name, bias=True):
+        self.w = _w(sd[name + ".weight"].reshape(sd[name + ".weight"].shape[0], -1))
+        self.b = _f(sd[name + ".bias"]) if bias else None
+
+
+class _Norm:
+    def __init__(self, sd, name):
+        self.g = _f(sd[name + ".weight"])
+        self.b = _f(sd[name + ".bias"])
+
+
+class _ResBlock:
+    def __init__(self, sd, pfx, eps):
+        s, t = pfx + ".spatial_res_block", pfx + ".temporal_res_block"
+        self.eps = eps
+        self.norm1, self.norm2 = _Norm(sd, s + ".norm1"), _Norm(sd, s + ".norm2")
+        w1 = sd[s + ".conv1.weight"]
+        self.cin, self.cout = w1.shape[1], w1.shape[0]
+        self.conv1_w, self.conv1_b = _w(_conv9(w1.float())), _f(sd[s + ".conv1.bias"])
+        self.temb = _Lin(sd, s + ".time_emb_proj")
+        w2 = _conv9(sd[s + ".conv2.weight"].float())
+        b2 = sd[s + ".conv2.bias"].float()
+        self.has_shortcut = (s + ".conv_shortcut.weight") in sd
+        if self.has_shortcut:  # 1x1 shortcut rides in the K loop of conv2
+            ws = sd[s + ".conv_shortcut.weight"].float().reshape(self.cout, self.cin)
+            w2 = torch.cat([w2, ws.to(w2.device)], dim=1)
+            b2 = b2 + sd[s + ".conv_shortcut.bias"].float().to(b2.device)
+        self.conv2_w, self.conv2_b = _w(w2), _f(b2)
+        self.tnorm1, self.tnorm2 = _Norm(sd, t + ".norm1"), _Norm(sd, t + ".norm2")
+        self.tconv1_w, self.tconv1_b = _w(_conv_t3(sd[t + ".conv1.weight"].float())), _f(sd[t + ".conv1.bias"])
+        self.ttemb = _Lin(sd, t + ".time_emb_proj")
+        self.tconv2_w, self.tconv2_b = _w(_conv_t3(sd[t + ".conv2.weight"].float())), _f(sd[t + ".conv2.bias"])
+        self.alpha = float(torch.sigmoid(sd[pfx + ".time_mixer.mix_factor"].float()).item())
+
+    def __call__(self, x, emb, g, x1=None):
+        """x [M, C0] (| x1 [M, C1] skip connection) -> [M, Cout];  g = geometry (B, T, H, W)."""
+        B, T, H, W = g
+        F_, HW = B * T, H * W
+        a1 = ops.groupnorm(x, F_, HW, self.norm1.g, self.norm1.b, self.eps, True, src1=x1)
+        temb = ops.small_linear(emb, self.temb.w, self.temb.b, act_in=True)
+        h = ops.conv3x3(a1, F_, H, W, self.conv1_w, bias=self.conv1_b, rowbias=temb, rb_mode=1,
+                        rb_div=T * HW)
+        a2 = ops.groupnorm(h, F_, HW, self.norm2.g, self.norm2.b, self.eps, True)
+        if self.has_shortcut:
+            xs = ops.conv3x3(a2, F_, H, W, self.conv2_w, sc0=x, sc1=x1, bias=self.conv2_b)
+        else:
+            assert x1 is None
+            xs = ops.conv3x3(a2, F_, H, W, self.conv2_w, bias=self.conv2_b, res1=x)
+        # temporal resnet on [B, T, HW, C] (GroupNorm statistics across frames), then AlphaBlender:
+        #   out = a*xs + (1-a)*(xs + h_t) = xs + (1-a)*h_t
+        a3 = ops.groupnorm(xs, B, T * HW, self.tnorm1.g, self.tnorm1.b, self.eps, True)
+        ttemb = ops.small_linear(emb, self.ttemb.w, self.ttemb.b, act_in=True)
+        h2 = ops.conv_t3(a3, B, T, HW, self.tconv1_w, bias=self.tconv1_b, rowbias=ttemb, rb_mode=1,
+                         rb_div=T * HW)
+        a4 = ops.groupnorm(h2, B, T * HW, self.tnorm2.g, self.tnorm2.b, self.eps, True)
+        return ops.conv_t3(a4, B, T, HW, self.tconv2_w, bias=self.tconv2_b, s_acc=1.0 - self.alpha,
+                           res1=xs, s_res1=1.0)
+
+
+class _FF:
+    def __init__(self, sd, pfx):
+        w1, b1 = _interleave_geglu(sd[pfx + ".net.0.proj.weight"].float(), sd[pfx + ".net.0.proj.bias"].float())
+        self.w1, self.b1 = _w(w1), _f(b1)
+        self.w2, self.b2 = _w(sd[pfx + ".net.2.weight"]), _f(sd[pfx + ".net.2.bias"])
+
+    def up(self, n):
+        return ops.linear(n, self.w1, bias=self.b1, geglu=True)
+
+
+class _SelfAttn:
+    def __init__(self, sd, pfx):
+        self.wqkv = _w(torch.cat([sd[pfx + ".to_q.weight"], sd[pfx + ".to_k.weight"], sd[pfx + ".to_v.weight"]], 0))
+        self.out = _Lin(sd, pfx + ".to_out.0")
+
+
+class _CrossAttnL1:
+    """Cross-attention over a 1-token context: softmax over one key is exactly 1, so
+    attn2(x, ctx) = to_out(to_v(ctx)) — a per-sample vector."""
+
+    def __init__(self, sd, pfx):
+        self.wv = _w(sd[pfx + ".to_v.weight"])
+        self.out = _Lin(sd, pfx + ".to_out.0")
+
+    def vector(self, ehs):  # ehs [B, xdim] fp32 -> [B, C] fp32 (includes the to_out bias)
+        return ops.small_linear(ops.small_linear(ehs, self.wv), self.out.w, self.out.b)
+
+
+class _Transformer:
+    def __init__(self, sd, pfx, heads, time_context_order):
+        self.heads = heads
+        self.order = time_context_order
+        self.norm = _Norm(sd, pfx + ".norm")
+        self.proj_in, self.proj_out = _Lin(sd, pfx + ".proj_in"), _Lin(sd, pfx + ".proj_out")
+        b = pfx + ".transformer_blocks.0"
+        self.norm1, self.norm3 = _Norm(sd, b + ".norm1"), _Norm(sd, b + ".norm3")
+        self.attn1, self.attn2, self.ff = _SelfAttn(sd, b + ".attn1"), _CrossAttnL1(sd, b + ".attn2"), _FF(sd, b + ".ff")
+        t = pfx + ".temporal_transformer_blocks.0"
+        self.tnorm_in, self.tnorm1, self.tnorm3 = _Norm(sd, t + ".norm_in"), _Norm(sd, t + ".norm1"), _Norm(sd, t + ".norm3")
+        self.tff_in, self.tff = _FF(sd, t + ".ff_in"), _FF(sd, t + ".ff")
+        self.tattn1, self.tattn2 = _SelfAttn(sd, t + ".attn1"), _CrossAttnL1(sd, t + ".attn2")
+        self.pos1, self.pos2 = _Lin(sd, pfx + ".time_pos_embed.linear_1"), _Lin(sd, pfx + ".time_pos_embed.linear_2")
+        self.alpha = float(torch.sigmoid(sd[pfx + ".time_mixer.mix_factor"].float()).item())
+        self.C = self.proj_in.w.shape[0]
+        self._pos_cache: Dict[int, torch.Tensor] = {}
+
+    def pos_emb(self, T):
+        """time_pos_embed(time_proj(arange(T))): depends on weights and T only."""
+        if T not in self._pos_cache:
+            idx = torch.arange(T, device="cuda", dtype=torch.float32)
+            e = ops.sinusoid(idx, self.C, round_bf16=True)
+            self._pos_cache[T] = ops.small_linear(ops.small_linear(e, self.pos1.w, self.pos1.b, act_out=True),
+                                                  self.pos2.w, self.pos2.b)
+        return self._pos_cache[T]
+
+    def __call__(self, x, ehs, g):
+        """x [M, C] rows ordered (b, t, site); ehs [B, xdim] fp32 (1-token context per sample)."""
+        B, T, H, W = g
+        S, F_ = H * W, B * T
+        a = ops.groupnorm(x, F_, S, self.norm.g, self.norm.b, 1e-6, False)
+        h = ops.linear(a, self.proj_in.w, bias=self.proj_in.b)
+        # --- BasicTransformerBlock (spatial)
+        n = ops.layernorm(h, self.norm1.g, self.norm1.b)
+        qkv = ops.linear(n, self.attn1.wqkv)
+        att = ops.attn_spatial(qkv, F_, S, self.heads)
+        ctx = self.attn2.vector(ehs)
+        h = ops.linear(att, self.attn1.out.w, bias=self.attn1.out.b, rowbias=ctx, rb_mode=1, rb_div=T * S, res1=h)
+        n = ops.layernorm(h, self.norm3.g, self.norm3.b)
+        h = ops.linear(self.ff.up(n), self.ff.w2, bias=self.ff.b2, res1=h)
+        # --- TemporalBasicTransformerBlock on h + pos[t]; sequences are the T frames of a site
+        pos = self.pos_emb(T)
+        n = ops.layernorm(h, self.tnorm_in.g, self.tnorm_in.b, rowbias=pos, rb_div=S, rb_mod=T)
+        hm = ops.linear(self.tff_in.up(n), self.tff_in.w2, bias=self.tff_in.b2, res1=h,
+                        rowbias=pos, rb_mode=2, rb_div=S, rb_mod=T)
+        n = ops.layernorm(hm, self.tnorm1.g, self.tnorm1.b)
+        qkv = ops.linear(n, self.tattn1.wqkv)
+        att = ops.attn_temporal(qkv, B, T, S, self.heads)
+        ctx_t = self.tattn2.vector(ehs)
+        if self.order == "s_major":  # diffusers 0.27.2: context of row (b, s) is ctx[(b*S + s) % B]
+            kw = dict(rb_mode=3, rb_div=T * S, rb_mod=S, rb_B=B)
+        else:
+            kw = dict(rb_mode=1, rb_div=T * S)
+        hm = ops.linear(att, self.tattn1.out.w, bias=self.tattn1.out.b, rowbias=ctx_t, res1=hm, **kw)
+        n = ops.layernorm(hm, self.tnorm3.g, self.tnorm3.b)
+        # ff(n) + hm, then AlphaBlender: a*h + (1-a)*(ff + hm)
+        h = ops.linear(self.tff.up(n), self.tff.w2, bias=self.tff.b2, s_acc=1.0 - self.alpha,
+                       res1=hm, s_res1=1.0 - self.alpha, res2=h, s_res2=self.alpha)
+        return ops.linear(h, self.proj_out.w, bias=self.proj_out.b, res1=x)
+
+
+class _TimeEmbed:
+    def __init__(self, sd, cfg):
+        self.t1, self.t2 = _Lin(sd, "time_embedding.linear_1"), _Lin(sd, "time_embedding.linear_2")
+        self.a1, self.a2 = _Lin(sd, "add_embedding.linear_1"), _Lin(sd, "add_embedding.linear_2")
+        self.dim0 = cfg["block_out_channels"][0]
+        self.add_dim = cfg["addition_time_embed_dim"]
+
+    def __call__(self, timesteps, added_time_ids):  # [B] fp32, [B, 3] fp32 -> [B, 4*C0] fp32
+        Bn = timesteps.shape[0]
+        te = ops.sinusoid(timesteps, self.dim0, round_bf16=True)
+        emb = ops.small_linear(ops.small_linear(te, self.t1.w, self.t1.b, act_out=True), self.t2.w, self.t2.b)
+        ae = ops.sinusoid(added_time_ids.reshape(-1), self.add_dim, round_bf16=True).reshape(Bn, -1)
+        # emb = time_embedding(t_emb) + add_embedding(time_embeds)   (controlnet.py:277-283)
+        return ops.small_linear(ops.small_linear(ae, self.a1.w, self.a1.b, act_out=True), self.a2.w, self.a2.b,
+                                out=emb, accumulate=True)
+
+
+class _Output(SimpleNamespace):
+    pass
+
+
+class _PackedModel(torch.nn.Module):
+    """Common part: config, flat diffusers-format state dict, packing, embeddings, encoder."""
+
+    is_controlnet = False
+
+    def __init__(self, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 time_context_order: str = "s_major", seed: int = 0, **overrides):
+        super().__init__()
+        cfg = dict(SVD_CONFIG)
+        if self.is_controlnet:
+            cfg.pop("out_channels"); cfg.pop("up_block_types")
+        cfg.update(overrides)
+        boc = cfg["block_out_channels"]
+        if len(boc) != len(cfg["down_block_types"]):  # controlnet.py:80-83
+            raise ValueError(
+                f"Must provide the same number of `block_out_channels` as `down_block_types`. "
+                f"`block_out_channels`: {boc}. `down_block_types`: {cfg['down_block_types']}.")
+        if not isinstance(cfg["num_attention_heads"], int) and len(cfg["num_attention_heads"]) != len(boc):
+            raise ValueError("Must provide the same number of `num_attention_heads` as `down_block_types`.")
+        for c in boc:
+            if c % 64 != 0:
+                raise ValueError(f"block_out_channels must be multiples of 64 for the sm_100a kernels, got {boc}")
+        self.cfg = cfg
+        self.config = SimpleNamespace(**cfg)
+        self.time_context_order = time_context_order
+        self.dtype = BF16
+        self._sd: Dict[str, torch.Tensor] = {}
+        if state_dict is None:
+            state_dict = random_state_dict(cfg, self.is_controlnet, seed=seed)
+        self.load_state_dict(state_dict)
+        # `add_embedding.linear_1.in_features` is read by ctrlv.utils.util:161
+        self.add_embedding = SimpleNamespace(linear_1=SimpleNamespace(
+            in_features=cfg["projection_class_embeddings_input_dim"]))
+
+    # ---- state dict with diffusers key names -------------------------------------------------
+    def state_dict(self, *a, **k):
+        return OrderedDict(self._sd)
+
+    def load_state_dict(self, sd, strict: bool = True):
+        spec = param_spec(self.cfg, self.is_controlnet)
+        missing = [k for k in spec if k not in sd]
+        unexpected = [k for k in sd if k not in spec]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing[:5]} unexpected {unexpected[:5]}")
+        for k, shape in spec.items():
+            if k in sd:
+                if tuple(sd[k].shape) != tuple(shape):
+                    raise RuntimeError(f"size mismatch for {k}: {tuple(sd[k].shape)} vs {shape}")
+                self._sd[k] = sd[k].detach().to("cuda")
+        self._pack()
+        return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
+
+    def to(self, *a, **k):  # weights are device-resident bf16 by construction
+        return self
+
+    def eval(self):
+        return self
+
+    @property
+    def device(self):
+        return torch.device("cuda", torch.cuda.current_device())
+
+    # ---- packing ------------------------------------------------------------------------------
+    def _pack_conv_in(self):
+        sd, cfg = self._sd, self.cfg
+        c0 = cfg["block_out_channels"][0]
+        cin = cfg["in_channels"]
+        w = torch.zeros(c0, 3, 3, 64, device="cuda", dtype=torch.float32)
+        w[..., :cin] = sd["conv_in.weight"].float().permute(0, 2, 3, 1)
+        b = sd["conv_in.bias"].float()
+        if self.is_controlnet:  # conv_in(sample) + control_conv_in(cond) == one conv on [sample | cond]
+            cc = sd["control_conv_in.weight"].shape[1]
+            w[..., cin:cin + cc] = sd["control_conv_in.weight"].float().permute(0, 2, 3, 1)
+            b = b + sd["control_conv_in.bias"].float()
+        self.conv_in_w, self.conv_in_b = _w(w.reshape(c0, -1)), _f(b)
+
+    def _pack(self):
+        sd, cfg = self._sd, self.cfg
+        boc = tuple(cfg["block_out_channels"])
+        n = len(boc)
+        heads = _tup(cfg["num_attention_heads"], n)
+        lpb = _tup(cfg["layers_per_block"], n)
+        if _tup(cfg["transformer_layers_per_block"], n) != (1,) * n:
+            raise NotImplementedError("transformer_layers_per_block != 1 is not supported")
+        order = self.time_context_order
+        self._pack_conv_in()
+        self.embed = _TimeEmbed(sd, cfg)
+        self.down = []
+        for i, t in enumerate(cfg["down_block_types"]):
+            attn = t.startswith("CrossAttn")
+            eps = 1e-6 if attn else 1e-5
+            res = [_ResBlock(sd, f"down_blocks.{i}.resnets.{j}", eps) for j in range(lpb[i])]
+            att = [_Transformer(sd, f"down_blocks.{i}.attentions.{j}", heads[i], order) for j in range(lpb[i])] if attn else None
+            ds = _Lin(sd, f"down_blocks.{i}.downsamplers.0.conv") if i != n - 1 else None
+            if ds is not None:
+                ds.w = _w(_conv9(sd[f"down_blocks.{i}.downsamplers.0.conv.weight"].float()))
+            self.down.append((res, att, ds))
+        self.mid = (_ResBlock(sd, "mid_block.resnets.0", 1e-5),
+                    _Transformer(sd, "mid_block.attentions.0", heads[-1], order),
+                    _ResBlock(sd, "mid_block.resnets.1", 1e-5))
+
+    # ---- shared forward pieces -----------------------------------------------------------------
+    @staticmethod
+    def _check_inputs(sample, timestep, encoder_hidden_states, added_time_ids):
+        if not torch.is_tensor(timestep):
+            # the reference dropped diffusers' float/int branch and calls `timesteps.shape`
+            # (controlnet.py:262-264) -> AttributeError there; be explicit here
+            raise TypeError("`timestep` must be a torch.Tensor (0-d or [batch])")
+        if sample.dim() != 5:
+            raise ValueError(f"`sample` must be [batch, frames, channels, height, width], got {tuple(sample.shape)}")
+        if encoder_hidden_states.dim() != 3 or encoder_hidden_states.shape[1] != 1:
+            raise NotImplementedError(
+                "encoder_hidden_states must be [batch, 1, cross_attention_dim]: the sm_100a path implements "
+                "the 1-token image-embedding context of the Box2Video pipeline")
+        h, w = sample.shape[-2:]
+        if h % 8 != 0 or w % 8 != 0:
+            raise ValueError(f"latent height and width have to be divisible by 8 but are {h} and {w}.")
+
+    def _embed(self, sample, timestep, added_time_ids):
+        Bn = sample.shape[0]
+        ts = timestep
+        if ts.dim() == 0:
+            ts = ts[None]
+        ts = ts.to(device="cuda", dtype=torch.float32).expand(Bn).contiguous()
+        ids = added_time_ids.to(device="cuda", dtype=torch.float32).contiguous()
+        return self.embed(ts, ids)  # [B, 4*C0] fp32
+
+    def _encode(self, x, emb, ehs, g):
+        """conv_in output -> (mid input, skip list, geometry list)."""
+        B, T, H, W = g
+        skips, geoms = [x], [g]
+        for res, att, ds in self.down:
+            for j, r in enumerate(res):
+                x = r(x, emb, g)
+                if att is not None:
+                    x = att[j](x, ehs, g)
+                skips.append(x); geoms.append(g)
+            if ds is not None:
+                x = ops.conv3x3(x, B * T, g[2], g[3], ds.w, stride=2, bias=ds.b)
+                g = (B, T, g[2] // 2, g[3] // 2)
+                skips.append(x); geoms.append(g)
+        return x, skips, geoms, g
+
+    def _mid(self, x, emb, ehs, g):
+        r0, a0, r1 = self.mid
+        return r1(a0(r0(x, emb, g), ehs, g), emb, g)
+
+
+def _to_rows(t: torch.Tensor, C: int) -> torch.Tensor:
+    """Reference-layout tensor [F, C, h, w] -> channels-last rows [F*h*w, C] bf16 (zero-copy when the
+    tensor is already a channels-last view produced by this package)."""
+    F_, Cc, h, w = t.shape
+    assert Cc == C
+    p = t.permute(0, 2, 3, 1)
+    if t.dtype == BF16 and p.is_contiguous():
+        return p.reshape(F_ * h * w, C)
+    return p.to(BF16).contiguous().reshape(F_ * h * w, C)
+
+
+def _from_rows(r: torch.Tensor, F_: int, h: int, w: int) -> torch.Tensor:
+    """rows [F*h*w, C] -> logical [F, C, h, w] view (channels-last strides, zero-copy)."""
+    return r.view(F_, h, w, r.shape[1]).permute(0, 3, 1, 2)
+
+
+class ControlNetModel(_PackedModel):
+    """Drop-in for ctrlv.models.ControlNetModel (controlnet.py:20-351) on sm_100a kernels."""
+
+    is_controlnet = True
+
+    def _pack(self):
+        super()._pack()
+        sd = self._sd
+        k = 0
+        self.zero_convs = []
+        while f"controlnet_down_blocks.{k}.weight" in sd:
+            self.zero_convs.append(_Lin(sd, f"controlnet_down_blocks.{k}"))
+            k += 1
+        self.zero_mid = _Lin(sd, "controlnet_mid_block")
+
+    @classmethod
+    def from_unet(cls, unet: "UNetSpatioTemporalConditionModel", load_weights_from_unet: bool = True):
+        c = unet.cfg  # controlnet.py:197-224
+        over = {k: c[k] for k in c if k not in ("out_channels", "up_block_types")}
+        ctrl = cls(time_context_order=unet.time_context_order, **over)
+        if load_weights_from_unet:
+            sd = ctrl.state_dict()
+            usd = unet.state_dict()
+            for k in sd:
+                if k in usd:
+                    sd[k] = usd[k].clone()
+            ctrl.load_state_dict(sd)
+        return ctrl
+
+    def forward_rows(self, inp64, emb, ehs, g, conditioning_scale: float = 1.0):
+        """inp64: [M, 64] padded channels-last input [sample(8) | control_cond(4) | 0]."""
+        B, T, H, W = g
+        x = ops.conv3x3(inp64, B * T, H, W, self.conv_in_w, bias=self.conv_in_b)
+        x, skips, geoms, gm = self._encode(x, emb, ehs, g)
+        x = self._mid(x, emb, ehs, gm)
+        res = [ops.linear(s, z.w, bias=z.b, s_acc=float(conditioning_scale)) for s, z in zip(skips, self.zero_convs)]
+        mid = ops.linear(x, self.zero_mid.w, bias=self.zero_mid.b, s_acc=float(conditioning_scale))
+        return res, mid, geoms, gm
+
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states, added_time_ids, control_cond=None,
+                conditioning_scale: float = 1.0, return_dict: bool = True, controlnet_cond=None):
+        if control_cond is None:
+            control_cond = controlnet_cond  # the docstring name in controlnet.py:249
+        self._check_inputs(sample, timestep, encoder_hidden_states, added_time_ids)
+        if control_cond is None:
+            raise ValueError("`control_cond` is required (controlnet.py:289 flattens it unconditionally)")
+        B, T, Cin, H, W = sample.shape
+        if Cin != self.cfg["in_channels"] or control_cond.shape[2] != self.cfg["in_channels"] // 2:
+            raise ValueError(f"expected sample with {self.cfg['in_channels']} and control_cond with "
+                             f"{self.cfg['in_channels'] // 2} channels")
+        out_dtype = sample.dtype
+        inp = torch.zeros((B * T * H * W, 64), device="cuda", dtype=BF16)
+        ops.nchw_to_nhwc(_as_f32_or_bf16(sample).reshape(B * T, Cin, H, W), inp, 0)
+        ops.nchw_to_nhwc(_as_f32_or_bf16(control_cond).reshape(B * T, Cin // 2, H, W), inp, Cin)
+        emb = self._embed(sample, timestep, added_time_ids)
+        ehs = encoder_hidden_states.to(device="cuda", dtype=torch.float32).reshape(B, -1).contiguous()
+        res, mid, geoms, gm = self.forward_rows(inp, emb, ehs, (B, T, H, W), conditioning_scale)
+        down = [_from_rows(r, B * T, gg[2], gg[3]) for r, gg in zip(res, geoms)]
+        midt = _from_rows(mid, B * T, gm[2], gm[3])
+        if out_dtype != BF16:
+            down = [d.to(out_dtype) for d in down]
+            midt = midt.to(out_dtype)
+        if not return_dict:
+            return (down, midt)
+        return _Output(down_block_res_samples=down, mid_block_res_sample=midt)
+
+    __call__ = forward
+
+
+def _as_f32_or_bf16(t: torch.Tensor) -> torch.Tensor:
+    t = t.to("cuda")
+    if t.dtype not in (torch.float32, BF16):
+        t = t.float()
+    return t.contiguous()
+
+
+class UNetSpatioTemporalConditionModel(_PackedModel):
+    """Drop-in for ctrlv.models.UNetSpatioTemporalConditionModel
+    (unet_spatio_temporal_condition.py:13-171) on sm_100a kernels."""
+
+    is_controlnet = False
+
+    def _pack(self):
+        super()._pack()
+        sd, cfg = self._sd, self.cfg
+        boc = tuple(cfg["block_out_channels"])
+        n = len(boc)
+        rheads = _tup(cfg["num_attention_heads"], n)[::-1]
+        rlpb = _tup(cfg["layers_per_block"], n)[::-1]
+        order = self.time_context_order
+        self.up = []
+        for i, t in enumerate(cfg["up_block_types"]):
+            attn = t.startswith("CrossAttn")
+            nl = rlpb[i] + 1
+            res = [_ResBlock(sd, f"up_blocks.{i}.resnets.{j}", 1e-6) for j in range(nl)]
+            att = [_Transformer(sd, f"up_blocks.{i}.attentions.{j}", rheads[i], order) for j in range(nl)] if attn else None
+            us = None
+            if i != n - 1:
+                us = _Lin(sd, f"up_blocks.{i}.upsamplers.0.conv")
+                us.w = _w(_conv9(sd[f"up_blocks.{i}.upsamplers.0.conv.weight"].float()))
+            self.up.append((res, att, us))
+        self.norm_out = _Norm(sd, "conv_norm_out")
+        oc = cfg["out_channels"]
+        assert oc <= 32
+        w = torch.zeros(32, 9 * boc[0], device="cuda", dtype=torch.float32)
+        w[:oc] = _conv9(sd["conv_out.weight"].float())
+        b = torch.zeros(32, device="cuda", dtype=torch.float32)
+        b[:oc] = sd["conv_out.bias"].float()
+        self.conv_out_w, self.conv_out_b = _w(w), _f(b)
+
+    def forward_rows(self, inp64, emb, ehs, g, down_res=None, mid_res=None, out_f32=None):
+        """inp64 [M, 64] -> noise prediction rows [M, out_channels] fp32."""
+        B, T, H, W = g
+        x = ops.conv3x3(inp64, B * T, H, W, self.conv_in_w, bias=self.conv_in_b)
+        x, skips, geoms, gm = self._encode(x, emb, ehs, g)
+        if down_res is not None:  # unet_spatio_temporal_condition.py:119-127
+            skips = [ops.axpby(s, r) for s, r in zip(skips, down_res)]
+        x = self._mid(x, emb, ehs, gm)
+        if mid_res is not None:  # :136-137
+            x = ops.axpby(x, mid_res)
+        g = gm
+        for res, att, us in self.up:
+            for j, r in enumerate(res):
+                skip = skips.pop()
+                x = r(x, emb, g, x1=skip)
+                if att is not None:
+                    x = att[j](x, ehs, g)
+            if us is not None:
+                x = ops.upsample2x(x, B * T, g[2], g[3])
+                g = (B, T, g[2] * 2, g[3] * 2)
+                x = ops.conv3x3(x, B * T, g[2], g[3], us.w, bias=us.b)
+        a = ops.groupnorm(x, B * T, g[2] * g[3], self.norm_out.g, self.norm_out.b, 1e-5, True)
+        oc = self.cfg["out_channels"]
+        if out_f32 is None:
+            out_f32 = torch.empty((x.shape[0], oc), device="cuda", dtype=torch.float32)
+        ops.conv3x3(a, B * T, g[2], g[3], self.conv_out_w, bias=self.conv_out_b, out_f32=out_f32, n_store=oc)
+        return out_f32
+
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states, added_time_ids,
+                down_block_additional_residuals=None, mid_block_additional_residuals=None,
+                return_dict: bool = True):
+        self._check_inputs(sample, timestep, encoder_hidden_states, added_time_ids)
+        B, T, Cin, H, W = sample.shape
+        if Cin != self.cfg["in_channels"]:
+            raise ValueError(f"expected sample with {self.cfg['in_channels']} channels, got {Cin}")
+        is_controlnet = mid_block_additional_residuals is not None and down_block_additional_residuals is not None
+        out_dtype = sample.dtype
+        inp = torch.zeros((B * T * H * W, 64), device="cuda", dtype=BF16)
+        ops.nchw_to_nhwc(_as_f32_or_bf16(sample).reshape(B * T, Cin, H, W), inp, 0)
+        emb = self._embed(sample, timestep, added_time_ids)
+        ehs = encoder_hidden_states.to(device="cuda", dtype=torch.float32).reshape(B, -1).contiguous()
+        down = mid = None
+        if is_controlnet:
+            down = [_to_rows(r, r.shape[1]) for r in down_block_additional_residuals]
+            mid = _to_rows(mid_block_additional_residuals, mid_block_additional_residuals.shape[1])
+        rows = self.forward_rows(inp, emb, ehs, (B, T, H, W), down, mid)
+        oc = self.cfg["out_channels"]
+        out = ops.nhwc_to_nchw(rows, B * T, oc, H, W, dtype=torch.float32).reshape(B, T, oc, H, W)
+        if out_dtype != torch.float32:
+            out = out.to(out_dtype)
+        if not return_dict:
+            return (out,)
+        return _Output(sample=out)
+
+    __call__ = forward

@@ -195,16 +195,19 @@ def attn_temporal(qkv: torch.Tensor, B: int, T: int, S: int, heads: int, scale: 
 
 
 def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
-                 act_in: bool = False, act_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y = act_out(act_in(x) @ w^T + b) for M <= 64 rows; x, y fp32, w bf16."""
+                 act_in: bool = False, act_out: bool = False, out: Optional[torch.Tensor] = None,
+                 accumulate: bool = False) -> torch.Tensor:
+    """y (+)= act_out(act_in(x) @ w^T + b) for M <= 64 rows; x, y fp32, w bf16."""
     _req(x, torch.float32, "x"); _req(w, BF16, "w")
     M, K = x.shape
     N = w.shape[0]
     assert x.is_contiguous() and w.is_contiguous() and w.shape[1] == K
     if out is None:
+        assert not accumulate
         out = torch.empty((M, N), dtype=torch.float32, device="cuda")
     check(lib().ctrlv_small_linear(x.data_ptr(), M, K, w.data_ptr(), _p(bias), N, 1 if act_in else 0,
-                                   1 if act_out else 0, out.data_ptr(), _stream()), "ctrlv_small_linear")
+                                   1 if act_out else 0, 1 if accumulate else 0, out.data_ptr(), _stream()),
+          "ctrlv_small_linear")
     return out
 
 
@@ -218,8 +221,9 @@ def sinusoid(t: torch.Tensor, dim: int, round_bf16: bool = True) -> torch.Tensor
 
 
 def prep_input(latents: torch.Tensor, image_latents: Optional[torch.Tensor], control_cond: Optional[torch.Tensor],
-               cfg: bool, sigma: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _req(latents, torch.float32, "latents")
+               cfg: bool, sigma_dev: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sigma_dev: fp32 CUDA tensor, element 0 = sigma of this step."""
+    _req(latents, torch.float32, "latents"); _req(sigma_dev, torch.float32, "sigma_dev")
     B, T, c4, h, w = latents.shape
     assert c4 == 4 and latents.is_contiguous()
     nb = 2 * B if cfg else B
@@ -229,17 +233,19 @@ def prep_input(latents: torch.Tensor, image_latents: Optional[torch.Tensor], con
     if out is None:
         out = torch.empty((nb * T * h * w, 64), dtype=BF16, device="cuda")
     check(lib().ctrlv_prep_input(latents.data_ptr(), _p(image_latents), _p(control_cond), B, 1 if cfg else 0,
-                                 T, h, w, float(sigma), out.data_ptr(), _stream()), "ctrlv_prep_input")
+                                 T, h, w, sigma_dev.data_ptr(), out.data_ptr(), _stream()), "ctrlv_prep_input")
     return out
 
 
 def cfg_euler(latents: torch.Tensor, noise: torch.Tensor, cfg: bool, guidance: Optional[torch.Tensor],
-              sigma: float, sigma_next: float, round_bf16: bool = False) -> torch.Tensor:
+              sigma_dev: torch.Tensor, round_bf16: bool = False) -> torch.Tensor:
+    """sigma_dev: fp32 CUDA tensor [sigma, sigma_next]; latents updated in place."""
     _req(latents, torch.float32, "latents"); _req(noise, torch.float32, "noise")
+    _req(sigma_dev, torch.float32, "sigma_dev"); assert sigma_dev.numel() >= 2
     B, T, c4, h, w = latents.shape
     assert latents.is_contiguous() and noise.stride(1) == 1
     check(lib().ctrlv_cfg_euler(latents.data_ptr(), noise.data_ptr(), noise.stride(0), B, 1 if cfg else 0, T, h,
-                                w, _p(guidance), float(sigma), float(sigma_next), 1 if round_bf16 else 0,
+                                w, _p(guidance), sigma_dev.data_ptr(), 1 if round_bf16 else 0,
                                 _stream()), "ctrlv_cfg_euler")
     return latents
 

@@ -1,0 +1,263 @@
+"""Sampling side of the hot path: the Euler-EDM schedule, the fused CFG denoise step (one CUDA
+graph per shape) and a drop-in `StableVideoControlPipeline.__call__`.
+
+Reference:
+  /root/reference/src/ctrlv/pipelines/pipeline_video_control.py:105-360  (__call__)
+  loop body :298-343 — cat([latents]*2), scale_model_input, cat(image_latents), ControlNet, UNet,
+  CFG combine, scheduler.step.
+Scheduler arithmetic: diffusers==0.27.2 EulerDiscreteScheduler with the SVD config.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Callable, Dict, List, Optional, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .models import BF16, ControlNetModel, UNetSpatioTemporalConditionModel
+
+
+class EulerDiscreteScheduler:
+    """Karras-sigma, v-prediction, continuous-timestep Euler scheduler (SVD configuration).
+
+    Host-side schedule construction only (numpy); the per-step arithmetic
+    (`scale_model_input`, `step`) runs in the fused CUDA kernels of this package."""
+
+    order = 1
+
+    def __init__(self, sigma_min: float = 0.002, sigma_max: float = 700.0, rho: float = 7.0,
+                 num_train_timesteps: int = 1000, timestep_spacing: str = "leading"):
+        self.config = SimpleNamespace(sigma_min=sigma_min, sigma_max=sigma_max, rho=rho,
+                                      num_train_timesteps=num_train_timesteps,
+                                      prediction_type="v_prediction", timestep_type="continuous",
+                                      use_karras_sigmas=True, timestep_spacing=timestep_spacing,
+                                      steps_offset=1)
+        self.sigmas = None
+        self.timesteps = None
+        self._step_index = None
+        self.num_inference_steps = None
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        c = self.config
+        self.num_inference_steps = num_inference_steps
+        ramp = np.linspace(0, 1, num_inference_steps)
+        min_inv_rho = c.sigma_min ** (1 / c.rho)
+        max_inv_rho = c.sigma_max ** (1 / c.rho)
+        sigmas = (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** c.rho  # float64
+        sig32 = torch.from_numpy(sigmas).to(torch.float32)
+        self.timesteps = torch.tensor([0.25 * math.log(float(s)) for s in sig32], dtype=torch.float32)
+        self.sigmas = torch.cat([sig32, torch.zeros(1, dtype=torch.float32)])  # kept on the host
+        self._step_index = None
+        return self
+
+    @property
+    def init_noise_sigma(self) -> float:
+        m = float(self.sigmas.max())
+        if self.config.timestep_spacing in ("linspace", "trailing"):
+            return m
+        return (m ** 2 + 1) ** 0.5
+
+    def index_for_timestep(self, t) -> int:
+        t = float(t)
+        d = (self.timesteps - t).abs()
+        return int(torch.argmin(d).item())
+
+
+class DenoiseStep:
+    """One CFG Euler-EDM iteration of ControlNet + UNet on a fixed shape, replayed from a CUDA
+    graph.  State: `latents` fp32 [B, T, 4, h, w] updated in place on the device."""
+
+    def __init__(self, unet: UNetSpatioTemporalConditionModel, controlnet: Optional[ControlNetModel],
+                 batch: int, num_frames: int, h: int, w: int, cfg: bool = True,
+                 conditioning_scale: float = 1.0, use_graph: bool = True):
+        self.unet, self.controlnet = unet, controlnet
+        self.B, self.T, self.h, self.w, self.cfg = batch, num_frames, h, w, cfg
+        self.nb = 2 * batch if cfg else batch
+        self.scale = conditioning_scale
+        self.use_graph = use_graph
+        dev = "cuda"
+        xdim = unet.cfg["cross_attention_dim"]
+        xdim = xdim if isinstance(xdim, int) else xdim[0]
+        self.latents = torch.zeros((batch, num_frames, 4, h, w), device=dev, dtype=torch.float32)
+        self.image_latents = torch.zeros((self.nb, num_frames, 4, h, w), device=dev, dtype=torch.float32)
+        self.cond_em = torch.zeros((self.nb, num_frames, 4, h, w), device=dev, dtype=torch.float32)
+        self.ehs = torch.zeros((self.nb, xdim), device=dev, dtype=torch.float32)
+        self.added_time_ids = torch.zeros((self.nb, 3), device=dev, dtype=torch.float32)
+        self.guidance = torch.ones((num_frames,), device=dev, dtype=torch.float32)
+        # per-step scalars [sigma, sigma_next, t x nb], refreshed by one small H2D copy per step
+        self.step_params = torch.zeros((2 + self.nb,), device=dev, dtype=torch.float32)
+        self.noise = torch.zeros((self.nb * num_frames * h * w, unet.cfg["out_channels"]), device=dev,
+                                 dtype=torch.float32)
+        self.inp = torch.zeros((self.nb * num_frames * h * w, 64), device=dev, dtype=BF16)
+        self._graph = None
+        self._host_params = None
+        self.launches_per_step = None
+
+    # -- the work of one step (kernel launches only) ------------------------------------------------
+    def _body(self):
+        g = (self.nb, self.T, self.h, self.w)
+        sig = self.step_params[0:2]
+        ts = self.step_params[2:]
+        ops.prep_input(self.latents, self.image_latents, self.cond_em if self.controlnet is not None else None,
+                       self.cfg, sig, out=self.inp)
+        down = mid = None
+        if self.controlnet is not None:
+            emb_c = self.controlnet.embed(ts, self.added_time_ids)
+            down, mid, _, _ = self.controlnet.forward_rows(self.inp, emb_c, self.ehs, g, self.scale)
+        emb_u = self.unet.embed(ts, self.added_time_ids)
+        self.unet.forward_rows(self.inp, emb_u, self.ehs, g, down, mid, out_f32=self.noise)
+        ops.cfg_euler(self.latents, self.noise, self.cfg, self.guidance, sig)
+
+    def set_schedule(self, sigmas: torch.Tensor, timesteps: torch.Tensor):
+        n = timesteps.numel()
+        hp = torch.empty((n, 2 + self.nb), dtype=torch.float32).pin_memory()
+        hp[:, 0] = sigmas[:n]
+        hp[:, 1] = sigmas[1:n + 1]
+        hp[:, 2:] = timesteps[:, None]
+        self._host_params = hp
+
+    def capture(self):
+        """Warm up eagerly (first-use attribute setup, embedding caches), then capture."""
+        if self._host_params is None:
+            raise RuntimeError("set_schedule() first")
+        keep = self.latents.clone()
+        self.step_params.copy_(self._host_params[0], non_blocking=True)
+        self._body()
+        torch.cuda.synchronize()
+        if self.use_graph:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                self._body()
+            self._graph = gr
+        self.latents.copy_(keep)
+        torch.cuda.synchronize()
+
+    def step(self, i: int):
+        self.step_params.copy_(self._host_params[i], non_blocking=True)
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._body()
+
+
+class StableVideoDiffusionPipelineOutput(SimpleNamespace):
+    pass
+
+
+class StableVideoControlPipeline:
+    """Drop-in for ctrlv.pipelines.StableVideoControlPipeline (pipeline_video_control.py:25-360).
+
+    The denoising loop (:298-343) runs on the sm_100a kernels.  The encoders around it — CLIP image
+    embedding (:220), VAE image/condition encode (:235, :84) and the temporal VAE decode (:346) —
+    are the "next" rows of SURVEY.md §8(f) and are NOT built yet: pass `image_embeddings=` and
+    `image_latents=` (and 4-channel `cond_images` latents, :86-88) and use `output_type="latent"`;
+    asking for pixel-space encode/decode raises."""
+
+    def __init__(self, vae=None, image_encoder=None, unet: UNetSpatioTemporalConditionModel = None,
+                 controlnet: ControlNetModel = None, scheduler: EulerDiscreteScheduler = None,
+                 feature_extractor=None):
+        if unet is None:
+            raise ValueError("`unet` is required")
+        self.vae, self.image_encoder, self.feature_extractor = vae, image_encoder, feature_extractor
+        self.unet, self.controlnet = unet, controlnet
+        self.scheduler = scheduler if scheduler is not None else EulerDiscreteScheduler()
+        self.vae_scale_factor = 8
+        self._steps: Dict[tuple, DenoiseStep] = {}
+        self._guidance_scale = 1.0
+
+    @property
+    def do_classifier_free_guidance(self):
+        g = self._guidance_scale
+        return (g > 1) if isinstance(g, (int, float)) else bool(g.max() > 1)
+
+    def check_inputs(self, image, cond_images, height, width):  # pipeline_video_control.py:51-68
+        if not isinstance(cond_images, torch.Tensor):
+            raise ValueError("`cond_images` has to be of type `torch.FloatTensor` but is " f"{type(cond_images)}")
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+
+    def _encode_vae_condition(self, cond_image, num_videos_per_prompt, do_cfg):  # :71-101
+        if cond_image.shape[2] == 3:
+            raise NotImplementedError("3-channel cond_images need the VAE encoder (SURVEY.md §8 f-1); "
+                                      "pass 4-channel bbox-frame latents")
+        assert cond_image.shape[2] == 4, "The input tensor should have 3 or 4 channels. 3 for frames and 4 for latents."
+        cond_em = cond_image.to("cuda", torch.float32).repeat(num_videos_per_prompt, 1, 1, 1, 1)
+        if do_cfg:
+            cond_em = torch.cat([torch.zeros_like(cond_em), cond_em])
+        return cond_em
+
+    @torch.no_grad()
+    def __call__(self, image=None, cond_images: torch.Tensor = None, height: int = 576, width: int = 1024,
+                 num_frames: Optional[int] = None, num_inference_steps: int = 25,
+                 min_guidance_scale: float = 1.0, max_guidance_scale: float = 3.0,
+                 control_condition_scale: float = 1.0, fps: int = 7, motion_bucket_id: int = 127,
+                 noise_aug_strength: float = 0.02, decode_chunk_size: Optional[int] = None,
+                 num_videos_per_prompt: Optional[int] = 1, generator=None,
+                 latents: Optional[torch.Tensor] = None, output_type: Optional[str] = "pil",
+                 callback_on_step_end: Optional[Callable] = None,
+                 callback_on_step_end_tensor_inputs: List[str] = ["latents"], return_dict: bool = True,
+                 image_embeddings: Optional[torch.Tensor] = None,
+                 image_latents: Optional[torch.Tensor] = None, use_graph: bool = True):
+        num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
+        self.check_inputs(image, cond_images, height, width)
+        if image_embeddings is None or image_latents is None:
+            raise NotImplementedError("CLIP / VAE image encoding is not part of this build (SURVEY.md §8 f-1, f-3): "
+                                      "pass image_embeddings=[B,1,D] and image_latents=[B,4,h,w]")
+        if output_type != "latent":
+            raise NotImplementedError("temporal VAE decode is not part of this build (SURVEY.md §8 f-1): "
+                                      "use output_type='latent'")
+        batch_size = image_embeddings.shape[0]
+        nvp = num_videos_per_prompt
+        self._guidance_scale = max_guidance_scale  # :217 — CFG on iff > 1
+        do_cfg = self.do_classifier_free_guidance
+        h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
+        B = batch_size * nvp
+        # :220 uncond image embedding = zeros; :235-245 uncond image latents = zeros
+        emb = image_embeddings.to("cuda", torch.float32).reshape(batch_size, -1).repeat_interleave(nvp, 0)
+        il = image_latents.to("cuda", torch.float32).repeat_interleave(nvp, 0)
+        if do_cfg:
+            emb = torch.cat([torch.zeros_like(emb), emb])
+            il = torch.cat([torch.zeros_like(il), il])
+        il = il.unsqueeze(1).repeat(1, num_frames, 1, 1, 1)
+        fps = fps - 1  # :224
+        ids = torch.tensor([[fps, motion_bucket_id, noise_aug_strength]], dtype=torch.float32).repeat(B, 1)
+        if do_cfg:
+            ids = torch.cat([ids, ids])
+        self.scheduler.set_timesteps(num_inference_steps)
+        timesteps = self.scheduler.timesteps
+        shape = (B, num_frames, 4, h, w)
+        if latents is None:
+            latents = torch.randn(shape, generator=generator, dtype=torch.float32,
+                                  device=generator.device if generator is not None else "cpu")
+        latents = latents.to("cuda", torch.float32) * self.scheduler.init_noise_sigma
+        cond_em = self._encode_vae_condition(cond_images, nvp, do_cfg)
+        guidance = torch.linspace(min_guidance_scale, max_guidance_scale, num_frames)  # :287
+
+        key = (B, num_frames, h, w, do_cfg, float(control_condition_scale), num_inference_steps, use_graph)
+        st = self._steps.get(key)
+        if st is None:
+            st = DenoiseStep(self.unet, self.controlnet, B, num_frames, h, w, do_cfg,
+                             control_condition_scale, use_graph)
+            st.set_schedule(self.scheduler.sigmas, timesteps)
+            st.capture()
+            self._steps[key] = st
+        st.latents.copy_(latents)
+        st.image_latents.copy_(il)
+        st.cond_em.copy_(cond_em)
+        st.ehs.copy_(emb)
+        st.added_time_ids.copy_(ids.to("cuda"))
+        st.guidance.copy_(guidance.to("cuda"))
+        for i, t in enumerate(timesteps):
+            st.step(i)
+            if callback_on_step_end is not None:
+                kw = {k: st.latents for k in callback_on_step_end_tensor_inputs if k == "latents"}
+                out = callback_on_step_end(self, i, t, kw)
+                if out and "latents" in out:
+                    st.latents.copy_(out["latents"])
+        frames = st.latents.clone()
+        if not return_dict:
+            return frames
+        return StableVideoDiffusionPipelineOutput(frames=frames)

@@ -156,9 +156,11 @@ int ctrlv_attn_temporal(const void* qkv, int32_t B, int32_t T, int32_t S, int32_
 
 /* Small-M dense layers on CUDA cores (embedding MLPs, time_emb_proj, 1-token cross-attention
  * value path): y[M][N] = act_in(x)[M][K] * W[N][K]^T + b, M <= 32; x, y fp32; W bf16.
- * act_in: 0 none, 1 SiLU.  act_out: 0 none, 1 SiLU. */
+ * act_in: 0 none, 1 SiLU.  act_out: 0 none, 1 SiLU.  accumulate: 1 adds the result to y
+ * (emb = time_embedding(...) + add_embedding(...), controlnet.py:277-283). */
 int ctrlv_small_linear(const float* x, int32_t M, int32_t K, const void* W, const float* bias,
-                       int32_t N, int32_t act_in, int32_t act_out, float* y, void* stream);
+                       int32_t N, int32_t act_in, int32_t act_out, int32_t accumulate, float* y,
+                       void* stream);
 
 /* diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): out[n][dim] =
  * [cos(t*f_k) | sin(t*f_k)], f_k = exp(-ln(10000) k / (dim/2)); t fp32 [n]. `round_bf16`
@@ -168,17 +170,19 @@ int ctrlv_sinusoid(const float* t, int32_t n, int32_t dim, int32_t round_bf16, f
 
 /* Loop-body glue of pipeline_video_control.py:300-304: builds the channels-last, 64-channel
  * padded model input  [2B or B][T][h][w][64] = [latents/sqrt(sigma^2+1) | image_latents |
- * control_cond | 0...]  from NCHW fp32 latents [B][T][4][h][w] and NCHW bf16/fp32 conditioning. */
+ * control_cond | 0...]  from NCHW fp32 latents [B][T][4][h][w] and NCHW fp32 conditioning.  sigma is read from device
+ * memory so that one captured CUDA graph serves every step of the schedule. */
 int ctrlv_prep_input(const float* latents, const float* image_latents, const float* control_cond,
-                     int32_t B, int32_t cfg, int32_t T, int32_t h, int32_t w, float sigma,
-                     void* out, void* stream);
+                     int32_t B, int32_t cfg, int32_t T, int32_t h, int32_t w,
+                     const float* sigma_dev /* device: [sigma] */, void* out, void* stream);
 
 /* CFG combine + EulerDiscreteScheduler.step (v-prediction), pipeline_video_control.py:327-332:
  * latents (fp32 NCHW [B][T][4][h][w]) updated in place from the model output
  * noise [2B or B][T*h*w][ld_noise] fp32 channels-last (first 4 columns). guidance: [T] fp32. */
 int ctrlv_cfg_euler(float* latents, const float* noise, int32_t ld_noise, int32_t B, int32_t cfg,
-                    int32_t T, int32_t h, int32_t w, const float* guidance, float sigma,
-                    float sigma_next, int32_t round_bf16, void* stream);
+                    int32_t T, int32_t h, int32_t w, const float* guidance,
+                    const float* sigma_dev /* device: [sigma, sigma_next] */, int32_t round_bf16,
+                    void* stream);
 
 /* Elementwise / layout helpers. */
 int ctrlv_upsample2x(const void* src, int32_t frames, int32_t H, int32_t Wd, int32_t C, void* out,

@@ -91,7 +91,8 @@ def t_glue():
     lat = torch.randn(B, T, 4, h, w, device=dev) * 10
     img = torch.randn(2 * B, T, 4, h, w, device=dev); ctl = torch.randn(2 * B, T, 4, h, w, device=dev)
     sigma = 3.7
-    out = ops.prep_input(lat, img, ctl, True, sigma)
+    sd = torch.tensor([sigma, 2.9], device=dev)
+    out = ops.prep_input(lat, img, ctl, True, sd)
     ref = torch.zeros(2 * B, T, h, w, 64, device=dev)
     ref[..., 0:4] = (torch.cat([lat, lat]) / (sigma ** 2 + 1) ** 0.5).permute(0, 1, 3, 4, 2)
     ref[..., 4:8] = img.permute(0, 1, 3, 4, 2); ref[..., 8:12] = ctl.permute(0, 1, 3, 4, 2)
@@ -99,7 +100,7 @@ def t_glue():
     noise = torch.randn(2 * B * T * h * w, 4, device=dev)
     g = torch.linspace(1, 3, T, device=dev)
     lat2 = lat.clone()
-    ops.cfg_euler(lat2, noise, True, g, sigma, 2.9)
+    ops.cfg_euler(lat2, noise, True, g, sd)
     n5 = noise.view(2 * B, T, h, w, 4).permute(0, 1, 4, 2, 3)
     nu, nc = n5[:B], n5[B:]
     v = nu + g.view(1, T, 1, 1, 1) * (nc - nu)
