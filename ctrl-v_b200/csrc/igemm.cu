@@ -11,8 +11,9 @@
 // * tcgen05.mma (cta_group::1, M=128, N=BN, K=16) issued by one thread, fp32 accumulators in
 //   TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the main loop of
 //   tile i+1.  Persistent CTAs (one per SM), static round-robin tile schedule.
-// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue
-//   (each owns the TMEM lane quarter warp_id % 4; one accumulator row per thread).
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..17 = epilogue
+//   (each owns the TMEM lane quarter warp_id % 4, one accumulator row per thread; the four warps
+//   of a quarter split the 32-column chunks so global-load latency of residuals is overlapped).
 #include "common.cuh"
 #include "../../include/ctrlv_b200.h"
 
@@ -21,7 +22,8 @@ namespace ctrlv {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 12;  // 3 per TMEM lane quarter; chunk c of a tile goes to group c % 3
+constexpr int kThreads = 64 + kEpiWarps * 32;
 
 struct IgemmSeg {
   int map, c0, nchunk, dx, dy, dz;
@@ -45,39 +47,51 @@ __device__ __forceinline__ int rowbias_index(const ctrlv_epilogue& ep, int m) {
   return (a * ep.rb_mod + m % ep.rb_mod) % ep.rb_B;
 }
 
+// residual rows of one chunk, fetched BEFORE the TMEM load so their latency overlaps it
+template <int NV>
+struct ResPrefetch {
+  uint4 r1[NV / 8], r2[NV / 8];
+  bool full;
+  __device__ __forceinline__ void issue(const ctrlv_epilogue& ep, long long m, int o0, int n_store, bool live) {
+    full = (o0 + NV <= n_store);
+    if (live && full) {
+      if (ep.res1) {
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res1) + (size_t)m * ep.ld_res1 + o0);
+#pragma unroll
+        for (int j = 0; j < NV / 8; ++j) r1[j] = __ldg(rp + j);
+      }
+      if (ep.res2) {
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res2) + (size_t)m * ep.ld_res2 + o0);
+#pragma unroll
+        for (int j = 0; j < NV / 8; ++j) r2[j] = __ldg(rp + j);
+      }
+    }
+  }
+};
+
+__device__ __forceinline__ void add_bf16x8(float* v, const uint4& u, float s) {
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] += s * f.x; v[1] += s * f.y;
+  f = unpack_bf16x2(u.y); v[2] += s * f.x; v[3] += s * f.y;
+  f = unpack_bf16x2(u.z); v[4] += s * f.x; v[5] += s * f.y;
+  f = unpack_bf16x2(u.w); v[6] += s * f.x; v[7] += s * f.y;
+}
+
 // scale, add residual streams, convert and store NV consecutive outputs of row m starting at
 // output column o0 (all loops compile-time so v[] stays in registers)
 template <int NV>
 __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, long long m, int o0,
-                                          int n_store) {
+                                          int n_store, const ResPrefetch<NV>& pf) {
 #pragma unroll
   for (int j = 0; j < NV; ++j) v[j] *= ep.s_acc;
-  if (o0 + NV <= n_store) {
+  if (pf.full) {
     if (ep.res1) {
-      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res1) +
-                                                       (size_t)m * ep.ld_res1 + o0);
 #pragma unroll
-      for (int j = 0; j < NV; j += 8) {
-        const uint4 u = __ldg(rp + (j >> 3));
-        float2 f;
-        f = unpack_bf16x2(u.x); v[j] += ep.s_res1 * f.x; v[j + 1] += ep.s_res1 * f.y;
-        f = unpack_bf16x2(u.y); v[j + 2] += ep.s_res1 * f.x; v[j + 3] += ep.s_res1 * f.y;
-        f = unpack_bf16x2(u.z); v[j + 4] += ep.s_res1 * f.x; v[j + 5] += ep.s_res1 * f.y;
-        f = unpack_bf16x2(u.w); v[j + 6] += ep.s_res1 * f.x; v[j + 7] += ep.s_res1 * f.y;
-      }
+      for (int j = 0; j < NV / 8; ++j) add_bf16x8(v + 8 * j, pf.r1[j], ep.s_res1);
     }
     if (ep.res2) {
-      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res2) +
-                                                       (size_t)m * ep.ld_res2 + o0);
 #pragma unroll
-      for (int j = 0; j < NV; j += 8) {
-        const uint4 u = __ldg(rp + (j >> 3));
-        float2 f;
-        f = unpack_bf16x2(u.x); v[j] += ep.s_res2 * f.x; v[j + 1] += ep.s_res2 * f.y;
-        f = unpack_bf16x2(u.y); v[j + 2] += ep.s_res2 * f.x; v[j + 3] += ep.s_res2 * f.y;
-        f = unpack_bf16x2(u.z); v[j + 4] += ep.s_res2 * f.x; v[j + 5] += ep.s_res2 * f.y;
-        f = unpack_bf16x2(u.w); v[j + 6] += ep.s_res2 * f.x; v[j + 7] += ep.s_res2 * f.y;
-      }
+      for (int j = 0; j < NV / 8; ++j) add_bf16x8(v + 8 * j, pf.r2[j], ep.s_res2);
     }
     if (ep.out) {
       uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)m * ep.ld_out + o0);
@@ -114,6 +128,41 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
   }
 }
 
+// one 32-column accumulator chunk of one row: prefetch residuals, TMEM load, bias, (GEGLU), store
+template <bool GEGLU>
+__device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t taddr, long long m, int n0,
+                                         int n_store, bool live, const float* rb) {
+  constexpr int NV = GEGLU ? 16 : 32;
+  ResPrefetch<NV> pf;
+  pf.issue(ep, m, GEGLU ? (n0 >> 1) : n0, n_store, live);
+  uint32_t raw[32];
+  tmem_ld32(taddr, raw);
+  tmem_ld_wait();
+  if (!live) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+  if (ep.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (rb) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(rb + n0 + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (GEGLU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * gelu_erf_f(v[2 * j + 1]);
+  }
+  ep_finish<NV>(v, ep, m, GEGLU ? (n0 >> 1) : n0, n_store, pf);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -137,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -221,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   } else {
     // ================================ epilogue ====================================
     const int q = warp & 3;  // TMEM lane quarter owned by this warp
+    const int sub = (warp - 2) >> 2;  // which of the 4 chunk groups this warp serves
     const int r = q * 32 + lane;
     const ctrlv_epilogue& ep = p.ep;
     const int n_out_total = ep.geglu ? p.N / 2 : p.N;
@@ -250,37 +300,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         rb = ep.rowbias + (size_t)rowbias_index(ep, (int)m) * ep.ld_rowbias;
 
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
-      for (int c = 0; c < p.BN / 32; ++c) {
+      for (int c = sub; c < p.BN / 32; c += kEpiWarps / 4) {
         __syncwarp();
-        uint32_t raw[32];
-        tmem_ld32(t_row + (uint32_t)(c * 32), raw);
-        tmem_ld_wait();
         const int n0 = nt * p.BN + c * 32;  // first GEMM column of this chunk
-        if (!valid || n0 >= p.N) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (rb) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(rb + n0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (ep.geglu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * gelu_erf_f(v[2 * j + 1]);
-          ep_finish<16>(v, ep, m, n0 >> 1, n_store);
-        } else {
-          ep_finish<32>(v, ep, m, n0, n_store);
-        }
+        const bool live = valid && n0 < p.N;
+        if (ep.geglu) ep_chunk<true>(ep, t_row + (uint32_t)(c * 32), m, n0, n_store, live, rb);
+        else ep_chunk<false>(ep, t_row + (uint32_t)(c * 32), m, n0, n_store, live, rb);
       }
       tc_fence_before();
       __syncwarp();
@@ -342,14 +367,20 @@ static void choose_box(int X, int Y, int Z, int* bx, int* by, int* bz) {
   *bx = bbx; *by = bby; *bz = bbz;
 }
 
-static int choose_bn(int N) {
-  if (N % 256 == 0) return 256;
-  if (N % 160 == 0) return 160;
-  if (N % 128 == 0) return 128;
-  if (N % 192 == 0) return 192;
-  if (N % 96 == 0) return 96;
-  if (N % 64 == 0) return 64;
-  return 0;
+// n-tile: among the tile widths that divide N pick the one with the lowest modelled time
+// (waves x per-tile MMA time; narrow tiles are shared-memory bound, so they cost at least 96)
+static int choose_bn(int N, long long tiles_m, int num_sms) {
+  const int cands[] = {256, 160, 128, 192, 96, 64};
+  int best = 0;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    if (N % bn != 0) continue;
+    const long long tiles = tiles_m * (N / bn);
+    const long long waves = (tiles + num_sms - 1) / num_sms;
+    const double cost = (double)waves * (bn < 96 ? 96 : bn) + 1e-3 * (256 - bn);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
 }
 
 static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
@@ -371,7 +402,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   p.tiles_y = (d->Y + p.by - 1) / p.by;
   p.tiles_z = (d->Z + p.bz - 1) / p.bz;
   p.N = d->N;
-  p.BN = d->bn > 0 ? d->bn : choose_bn(d->N);
+  p.BN = d->bn > 0 ? d->bn : choose_bn(d->N, (long long)p.tiles_x * p.tiles_y * p.tiles_z, g_num_sms);
   if (p.BN == 0) {
     // ragged N: largest 32-multiple tile, TMA zero-fills the weight rows past N
     p.BN = d->N >= 256 ? 256 : ((d->N + 31) / 32) * 32;

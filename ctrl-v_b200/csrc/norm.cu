@@ -16,19 +16,17 @@ constexpr int kMaxSplit = 256;
 // ------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict__ src1,
                                 int C1, int rows_per_unit, int rows_per_split, int nsplit,
-                                float* __restrict__ partial) {
-  __shared__ float bins[kGroups * 2];
+                                int nwork, float* __restrict__ partial) {
+  extern __shared__ float gn_smem[];  // [nwork][8] thread sums, then [vpr*4][2] channel-pair sums
   const int C = C0 + C1;
   const int vpr = C >> 3;
   const int cg = C / kGroups;
   const int unit = blockIdx.x / nsplit;
   const int split = blockIdx.x % nsplit;
   const int tid = threadIdx.x;
-  for (int i = tid; i < kGroups * 2; i += blockDim.x) bins[i] = 0.f;
-  __syncthreads();
   const int vec = tid % vpr;
-  const int rpar = blockDim.x / vpr;
-  const int rsub = tid / vpr;
+  const int rpar = nwork / vpr;
+  const int rsub = tid < nwork ? tid / vpr : rows_per_unit;  // padding threads do no rows
   const int c = vec << 3;
   const bf16* base;
   int ld;
@@ -38,6 +36,7 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ src0, int C0, const bf1
   if (r_end > rows_per_unit) r_end = rows_per_unit;
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   const size_t row0 = (size_t)unit * rows_per_unit;
+#pragma unroll 4
   for (int r = r_begin + rsub; r < r_end; r += rpar) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (row0 + r) * ld));
     float2 f;
@@ -46,15 +45,36 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ src0, int C0, const bf1
     f = unpack_bf16x2(u.z); s[2] += f.x + f.y; q[2] += f.x * f.x + f.y * f.y;
     f = unpack_bf16x2(u.w); s[3] += f.x + f.y; q[3] += f.x * f.x + f.y * f.y;
   }
-#pragma unroll
-  for (int pidx = 0; pidx < 4; ++pidx) {
-    const int g = (c + 2 * pidx) / cg;
-    atomicAdd(&bins[g * 2], s[pidx]);
-    atomicAdd(&bins[g * 2 + 1], q[pidx]);
+  // deterministic block reduction (no atomics): thread sums -> channel-pair sums -> group sums
+  if (tid < nwork) {
+    float* t = gn_smem + (size_t)tid * 8;
+    t[0] = s[0]; t[1] = s[1]; t[2] = s[2]; t[3] = s[3];
+    t[4] = q[0]; t[5] = q[1]; t[6] = q[2]; t[7] = q[3];
   }
   __syncthreads();
-  for (int i = tid; i < kGroups * 2; i += blockDim.x)
-    partial[((size_t)unit * nsplit + split) * (kGroups * 2) + i] = bins[i];
+  const int npair = vpr * 4;
+  float* pair = gn_smem + (size_t)nwork * 8;  // [npair][2]
+  for (int pp = tid; pp < npair; pp += blockDim.x) {
+    const int v = pp >> 2, pi = pp & 3;
+    float ps = 0.f, pq = 0.f;
+    for (int rs = 0; rs < rpar; ++rs) {
+      const float* t = gn_smem + (size_t)(rs * vpr + v) * 8;
+      ps += t[pi];
+      pq += t[4 + pi];
+    }
+    pair[pp * 2] = ps; pair[pp * 2 + 1] = pq;
+  }
+  __syncthreads();
+  if (tid < kGroups) {
+    const int ppg = cg >> 1;  // channel pairs per group
+    float gs = 0.f, gq = 0.f;
+    for (int i = 0; i < ppg; ++i) {
+      gs += pair[(tid * ppg + i) * 2];
+      gq += pair[(tid * ppg + i) * 2 + 1];
+    }
+    float* o = partial + ((size_t)unit * nsplit + split) * (kGroups * 2) + tid * 2;
+    o[0] = gs; o[1] = gq;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -63,7 +83,7 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ src0, int C0, const bf1
 // ------------------------------------------------------------------------------------------
 __global__ void gn_apply_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict__ src1,
                                 int C1, int rows_per_unit, int blocks_per_unit, int nsplit,
-                                const float* __restrict__ partial, const float* __restrict__ gamma,
+                                int nwork, const float* __restrict__ partial, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu,
                                 bf16* __restrict__ out) {
   __shared__ float mean_s[kGroups], rstd_s[kGroups];
@@ -73,24 +93,37 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ src0, int C0, const bf1
   const int unit = blockIdx.x / blocks_per_unit;
   const int blk = blockIdx.x % blocks_per_unit;
   const int tid = threadIdx.x;
-  for (int gi = tid; gi < kGroups; gi += blockDim.x) {
-    // fixed-order (deterministic) reduction of the split partials; fp64 only for this tiny sum
+  // deterministic reduction of the split partials: 8 lanes per group, each sums its strided
+  // share in a fixed order (fp64), then a fixed xor tree; works for any block size >= 32
+  for (int base_g = 0; base_g < kGroups; base_g += blockDim.x / 8) {
+    const int gi = base_g + tid / 8;
+    const int sl = tid & 7;
     double s = 0.0, q = 0.0;
-    const float* pp = partial + (size_t)unit * nsplit * (kGroups * 2) + gi * 2;
-    for (int i = 0; i < nsplit; ++i) {
-      s += (double)pp[(size_t)i * kGroups * 2];
-      q += (double)pp[(size_t)i * kGroups * 2 + 1];
+    if (gi < kGroups && tid / 8 < (int)blockDim.x / 8) {
+      const float* pp = partial + (size_t)unit * nsplit * (kGroups * 2) + gi * 2;
+      for (int i = sl; i < nsplit; i += 8) {
+        s += (double)pp[(size_t)i * kGroups * 2];
+        q += (double)pp[(size_t)i * kGroups * 2 + 1];
+      }
     }
-    const double cnt = (double)rows_per_unit * cg;
-    const double mean = s / cnt;
-    double var = q / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    mean_s[gi] = (float)mean;
-    rstd_s[gi] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (gi < kGroups && sl == 0 && tid / 8 < (int)blockDim.x / 8) {
+      const double cnt = (double)rows_per_unit * cg;
+      const double mean = s / cnt;
+      double var = q / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mean_s[gi] = (float)mean;
+      rstd_s[gi] = (float)(1.0 / sqrt(var + (double)eps));
+    }
   }
   __syncthreads();
+  if (tid >= nwork) return;
   const int vec = tid % vpr;
-  const int rpar = blockDim.x / vpr;
+  const int rpar = nwork / vpr;
   const int rsub = tid / vpr;
   const int c = vec << 3;
   const bf16* base;
@@ -110,6 +143,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ src0, int C0, const bf1
   int r_end = r_begin + rows_per_blk;
   if (r_end > rows_per_unit) r_end = rows_per_unit;
   const size_t row0 = (size_t)unit * rows_per_unit;
+#pragma unroll 4
   for (int r = r_begin + rsub; r < r_end; r += rpar) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (row0 + r) * ld));
     float v[8];
@@ -131,25 +165,27 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ src0, int C0, const bf1
 }
 
 // ------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, row held in registers (C <= 2048), two-pass statistics.
+// LayerNorm: a row is owned by LPR lanes (8/16/32) holding VPL 16-byte vectors each, so that a
+// 320-channel row (40 vectors) keeps every lane busy; two-pass statistics in registers.
 // ------------------------------------------------------------------------------------------
-constexpr int kLnMaxIter = 8;
-
-__global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, int M, int C,
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, long long ldx, int M, int C,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float eps, const float* __restrict__ rowbias, int ld_rowbias,
                                  int rb_div, int rb_mod, bf16* __restrict__ out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = gtid / LPR;
+  const int sl = threadIdx.x % LPR;  // sub-lane inside the row group
+  const bool active = row < M;
   const int vpr = C >> 3;
-  const bf16* xr = x + (size_t)warp * ldx;
-  const float* rb = rowbias ? rowbias + (size_t)((warp / rb_div) % rb_mod) * ld_rowbias : nullptr;
-  float v[kLnMaxIter][8];
+  const int rowc = active ? row : 0;
+  const bf16* xr = x + (size_t)rowc * ldx;
+  const float* rb = rowbias ? rowbias + (size_t)((rowc / rb_div) % rb_mod) * ld_rowbias : nullptr;
+  float v[VPL][8];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxIter; ++i) {
-    const int vec = lane + 32 * i;
+  for (int i = 0; i < VPL; ++i) {
+    const int vec = sl + LPR * i;
     if (vec < vpr) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + vec * 8));
       float2 f;
@@ -167,11 +203,13 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, int 
       for (int j = 0; j < 8; ++j) sum += v[i][j];
     }
   }
-  const float mean = warp_sum(sum) / (float)C;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxIter; ++i) {
-    const int vec = lane + 32 * i;
+  for (int i = 0; i < VPL; ++i) {
+    const int vec = sl + LPR * i;
     if (vec < vpr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -180,11 +218,14 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, int 
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
-  bf16* orow = out + (size_t)warp * C;
 #pragma unroll
-  for (int i = 0; i < kLnMaxIter; ++i) {
-    const int vec = lane + 32 * i;
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+  if (!active) return;
+  bf16* orow = out + (size_t)row * C;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vec = sl + LPR * i;
     if (vec < vpr) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8));
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8 + 4));
@@ -226,7 +267,8 @@ extern "C" int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, i
   int rpar = 512 / vpr;
   if (rpar < 1) rpar = 1;
   if (rpar > rows_per_unit) rpar = rows_per_unit;
-  const int nthreads = vpr * rpar;
+  const int nwork = vpr * rpar;
+  const int nthreads = (nwork + 31) / 32 * 32;
   // split each unit so that the grid has a few hundred blocks
   int nsplit = (592 + n_units - 1) / n_units;
   const int max_by_rows = (rows_per_unit + rpar - 1) / rpar;
@@ -236,13 +278,14 @@ extern "C" int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, i
   int rows_per_split = (rows_per_unit + nsplit - 1) / nsplit;
   nsplit = (rows_per_unit + rows_per_split - 1) / rows_per_split;
   float* partial = reinterpret_cast<float*>(workspace);
-  gn_stats_kernel<<<n_units * nsplit, nthreads, 0, stream>>>(
+  const size_t st_smem = ((size_t)nwork * 8 + (size_t)vpr * 8) * sizeof(float);
+  gn_stats_kernel<<<n_units * nsplit, nthreads, st_smem, stream>>>(
       reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1, rows_per_unit,
-      rows_per_split, nsplit, partial);
+      rows_per_split, nsplit, nwork, partial);
   CTRLV_CUDA(cudaGetLastError());
   gn_apply_kernel<<<n_units * nsplit, nthreads, 0, stream>>>(
       reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1, rows_per_unit,
-      nsplit, nsplit, partial, gamma, beta, eps, silu, reinterpret_cast<bf16*>(out));
+      nsplit, nsplit, nwork, partial, gamma, beta, eps, silu, reinterpret_cast<bf16*>(out));
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }
@@ -253,14 +296,30 @@ extern "C" int ctrlv_layernorm(const void* x, int64_t ldx, int32_t M, int32_t C,
                                void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTRLV_CHECK_ARG(x && out && gamma && beta, "layernorm: null pointer");
-  CTRLV_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * kLnMaxIter, "layernorm: C=%d unsupported", C);
+  CTRLV_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * 8, "layernorm: C=%d unsupported", C);
   CTRLV_CHECK_ARG(ldx % 8 == 0, "layernorm: ldx %% 8");
   if (rowbias) CTRLV_CHECK_ARG(rb_div > 0 && rb_mod > 0 && ld_rowbias % 4 == 0, "layernorm: bad rowbias args");
-  const int warps_per_block = 8;
-  const int blocks = (M + warps_per_block - 1) / warps_per_block;
-  layernorm_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(
-      reinterpret_cast<const bf16*>(x), ldx, M, C, gamma, beta, eps, rowbias, ld_rowbias, rb_div,
-      rb_mod, reinterpret_cast<bf16*>(out));
+  const int vpr = C / 8;
+  // lanes per row / vectors per lane: keep all lanes busy for C = 320 (8x5), 640 (16x5), 1280 (32x5)
+  int lpr = 32, vpl = 8;
+  if (vpr <= 8) { lpr = 8; vpl = 1; }
+  else if (vpr <= 16) { lpr = 8; vpl = 2; }
+  else if (vpr <= 40) { lpr = 8; vpl = 5; }
+  else if (vpr <= 80) { lpr = 16; vpl = 5; }
+  else if (vpr <= 160) { lpr = 32; vpl = 5; }
+  const int threads = 256;
+  const long long total = (long long)M * lpr;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+#define CTRLV_LN(L, V)                                                                            \
+  layernorm_kernel<L, V><<<blocks, threads, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, M, C, \
+      gamma, beta, eps, rowbias, ld_rowbias, rb_div, rb_mod, reinterpret_cast<bf16*>(out))
+  if (lpr == 8 && vpl == 1) CTRLV_LN(8, 1);
+  else if (lpr == 8 && vpl == 2) CTRLV_LN(8, 2);
+  else if (lpr == 8 && vpl == 5) CTRLV_LN(8, 5);
+  else if (lpr == 16) CTRLV_LN(16, 5);
+  else if (vpl == 5) CTRLV_LN(32, 5);
+  else CTRLV_LN(32, 8);
+#undef CTRLV_LN
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }

@@ -262,12 +262,14 @@ class _ResBlock:
         self.tconv2_w, self.tconv2_b = _w(_conv_t3(sd[t + ".conv2.weight"].float())), _f(sd[t + ".conv2.bias"])
         self.alpha = float(torch.sigmoid(sd[pfx + ".time_mixer.mix_factor"].float()).item())
 
-    def __call__(self, x, emb, g, x1=None):
-        """x [M, C0] (| x1 [M, C1] skip connection) -> [M, Cout];  g = geometry (B, T, H, W)."""
+    def __call__(self, x, aux, g, x1=None):
+        """x [M, C0] (| x1 [M, C1] skip connection) -> [M, Cout];  g = geometry (B, T, H, W);
+        aux.temb holds every block's time_emb_proj(silu(emb)) (one batched launch per forward)."""
         B, T, H, W = g
         F_, HW = B * T, H * W
         a1 = ops.groupnorm(x, F_, HW, self.norm1.g, self.norm1.b, self.eps, True, src1=x1)
-        temb = ops.small_linear(emb, self.temb.w, self.temb.b, act_in=True)
+        temb = aux.temb[:, self.temb_off:self.temb_off + self.cout]
+        ttemb = aux.temb[:, self.ttemb_off:self.ttemb_off + self.cout]
         h = ops.conv3x3(a1, F_, H, W, self.conv1_w, bias=self.conv1_b, rowbias=temb, rb_mode=1,
                         rb_div=T * HW)
         a2 = ops.groupnorm(h, F_, HW, self.norm2.g, self.norm2.b, self.eps, True)
@@ -279,7 +281,6 @@ class _ResBlock:
         # temporal resnet on [B, T, HW, C] (GroupNorm statistics across frames), then AlphaBlender:
         #   out = a*xs + (1-a)*(xs + h_t) = xs + (1-a)*h_t
         a3 = ops.groupnorm(xs, B, T * HW, self.tnorm1.g, self.tnorm1.b, self.eps, True)
-        ttemb = ops.small_linear(emb, self.ttemb.w, self.ttemb.b, act_in=True)
         h2 = ops.conv_t3(a3, B, T, HW, self.tconv1_w, bias=self.tconv1_b, rowbias=ttemb, rb_mode=1,
                          rb_div=T * HW)
         a4 = ops.groupnorm(h2, B, T * HW, self.tnorm2.g, self.tnorm2.b, self.eps, True)
@@ -308,11 +309,11 @@ class _CrossAttnL1:
     attn2(x, ctx) = to_out(to_v(ctx)) — a per-sample vector."""
 
     def __init__(self, sd, pfx):
-        self.wv = _w(sd[pfx + ".to_v.weight"])
-        self.out = _Lin(sd, pfx + ".to_out.0")
-
-    def vector(self, ehs):  # ehs [B, xdim] fp32 -> [B, C] fp32 (includes the to_out bias)
-        return ops.small_linear(ops.small_linear(ehs, self.wv), self.out.w, self.out.b)
+        # to_out(to_v(ctx)) = (W_out W_v) ctx + b_out: fold the two projections (fp32 product)
+        self.w = sd[pfx + ".to_out.0.weight"].float() @ sd[pfx + ".to_v.weight"].float()  # [C, xdim]
+        self.b = sd[pfx + ".to_out.0.bias"].float()
+        self.C = self.w.shape[0]
+        self.off = None  # column offset inside the model-wide batched context table
 
 
 class _Transformer:
@@ -342,8 +343,9 @@ class _Transformer:
                                                   self.pos2.w, self.pos2.b)
         return self._pos_cache[T]
 
-    def __call__(self, x, ehs, g):
-        """x [M, C] rows ordered (b, t, site); ehs [B, xdim] fp32 (1-token context per sample)."""
+    def __call__(self, x, aux, g):
+        """x [M, C] rows ordered (b, t, site); aux.ctx holds every block's 1-token cross-attention
+        vector to_out(to_v(ehs[b])) (one batched launch per forward)."""
         B, T, H, W = g
         S, F_ = H * W, B * T
         a = ops.groupnorm(x, F_, S, self.norm.g, self.norm.b, 1e-6, False)
@@ -352,7 +354,7 @@ class _Transformer:
         n = ops.layernorm(h, self.norm1.g, self.norm1.b)
         qkv = ops.linear(n, self.attn1.wqkv)
         att = ops.attn_spatial(qkv, F_, S, self.heads)
-        ctx = self.attn2.vector(ehs)
+        ctx = aux.ctx[:, self.attn2.off:self.attn2.off + self.C]
         h = ops.linear(att, self.attn1.out.w, bias=self.attn1.out.b, rowbias=ctx, rb_mode=1, rb_div=T * S, res1=h)
         n = ops.layernorm(h, self.norm3.g, self.norm3.b)
         h = ops.linear(self.ff.up(n), self.ff.w2, bias=self.ff.b2, res1=h)
@@ -364,7 +366,7 @@ class _Transformer:
         n = ops.layernorm(hm, self.tnorm1.g, self.tnorm1.b)
         qkv = ops.linear(n, self.tattn1.wqkv)
         att = ops.attn_temporal(qkv, B, T, S, self.heads)
-        ctx_t = self.tattn2.vector(ehs)
+        ctx_t = aux.ctx[:, self.tattn2.off:self.tattn2.off + self.C]
         if self.order == "s_major":  # diffusers 0.27.2: context of row (b, s) is ctx[(b*S + s) % B]
             kw = dict(rb_mode=3, rb_div=T * S, rb_mod=S, rb_B=B)
         else:
@@ -525,15 +527,37 @@ class _PackedModel(torch.nn.Module):
         ids = added_time_ids.to(device="cuda", dtype=torch.float32).contiguous()
         return self.embed(ts, ids)  # [B, 4*C0] fp32
 
-    def _encode(self, x, emb, ehs, g):
+    def _aux(self, emb, ehs):
+        """All per-sample vectors of one forward in two batched launches:
+        temb[b] = every time_emb_proj(silu(emb[b])); ctx[b] = every to_out(to_v(ehs[b]))."""
+        return SimpleNamespace(temb=ops.small_linear(emb, self.temb_w, self.temb_b, act_in=True),
+                               ctx=ops.small_linear(ehs, self.ctx_w, self.ctx_b))
+
+    def _finish_pack(self, resblocks, transformers):
+        tw, tb, off = [], [], 0
+        for r in resblocks:
+            for lin, name in ((r.temb, "temb_off"), (r.ttemb, "ttemb_off")):
+                setattr(r, name, off)
+                tw.append(lin.w); tb.append(lin.b); off += lin.w.shape[0]
+            r.temb = r.ttemb = None
+        self.temb_w, self.temb_b = torch.cat(tw).contiguous(), torch.cat(tb).contiguous()
+        cw, cb, off = [], [], 0
+        for t in transformers:
+            for ca in (t.attn2, t.tattn2):
+                ca.off = off
+                cw.append(ca.w); cb.append(ca.b); off += ca.C
+                ca.w = ca.b = None
+        self.ctx_w, self.ctx_b = _w(torch.cat(cw)), _f(torch.cat(cb))
+
+    def _encode(self, x, aux, g):
         """conv_in output -> (mid input, skip list, geometry list)."""
         B, T, H, W = g
         skips, geoms = [x], [g]
         for res, att, ds in self.down:
             for j, r in enumerate(res):
-                x = r(x, emb, g)
+                x = r(x, aux, g)
                 if att is not None:
-                    x = att[j](x, ehs, g)
+                    x = att[j](x, aux, g)
                 skips.append(x); geoms.append(g)
             if ds is not None:
                 x = ops.conv3x3(x, B * T, g[2], g[3], ds.w, stride=2, bias=ds.b)
@@ -541,9 +565,18 @@ class _PackedModel(torch.nn.Module):
                 skips.append(x); geoms.append(g)
         return x, skips, geoms, g
 
-    def _mid(self, x, emb, ehs, g):
+    def _mid(self, x, aux, g):
         r0, a0, r1 = self.mid
-        return r1(a0(r0(x, emb, g), ehs, g), emb, g)
+        return r1(a0(r0(x, aux, g), aux, g), aux, g)
+
+    def _all_blocks(self):
+        res, att = [], []
+        for r, a, _ in self.down:
+            res += r
+            att += a or []
+        res += [self.mid[0], self.mid[2]]
+        att.append(self.mid[1])
+        return res, att
 
 
 def _to_rows(t: torch.Tensor, C: int) -> torch.Tensor:
@@ -576,6 +609,7 @@ class ControlNetModel(_PackedModel):
             self.zero_convs.append(_Lin(sd, f"controlnet_down_blocks.{k}"))
             k += 1
         self.zero_mid = _Lin(sd, "controlnet_mid_block")
+        self._finish_pack(*self._all_blocks())
 
     @classmethod
     def from_unet(cls, unet: "UNetSpatioTemporalConditionModel", load_weights_from_unet: bool = True):
@@ -594,9 +628,10 @@ class ControlNetModel(_PackedModel):
     def forward_rows(self, inp64, emb, ehs, g, conditioning_scale: float = 1.0):
         """inp64: [M, 64] padded channels-last input [sample(8) | control_cond(4) | 0]."""
         B, T, H, W = g
+        aux = self._aux(emb, ehs)
         x = ops.conv3x3(inp64, B * T, H, W, self.conv_in_w, bias=self.conv_in_b)
-        x, skips, geoms, gm = self._encode(x, emb, ehs, g)
-        x = self._mid(x, emb, ehs, gm)
+        x, skips, geoms, gm = self._encode(x, aux, g)
+        x = self._mid(x, aux, gm)
         res = [ops.linear(s, z.w, bias=z.b, s_acc=float(conditioning_scale)) for s, z in zip(skips, self.zero_convs)]
         mid = ops.linear(x, self.zero_mid.w, bias=self.zero_mid.b, s_acc=float(conditioning_scale))
         return res, mid, geoms, gm
@@ -672,24 +707,30 @@ class UNetSpatioTemporalConditionModel(_PackedModel):
         b = torch.zeros(32, device="cuda", dtype=torch.float32)
         b[:oc] = sd["conv_out.bias"].float()
         self.conv_out_w, self.conv_out_b = _w(w), _f(b)
+        res, att = self._all_blocks()
+        for r, a, _ in self.up:
+            res += r
+            att += a or []
+        self._finish_pack(res, att)
 
     def forward_rows(self, inp64, emb, ehs, g, down_res=None, mid_res=None, out_f32=None):
         """inp64 [M, 64] -> noise prediction rows [M, out_channels] fp32."""
         B, T, H, W = g
+        aux = self._aux(emb, ehs)
         x = ops.conv3x3(inp64, B * T, H, W, self.conv_in_w, bias=self.conv_in_b)
-        x, skips, geoms, gm = self._encode(x, emb, ehs, g)
+        x, skips, geoms, gm = self._encode(x, aux, g)
         if down_res is not None:  # unet_spatio_temporal_condition.py:119-127
             skips = [ops.axpby(s, r) for s, r in zip(skips, down_res)]
-        x = self._mid(x, emb, ehs, gm)
+        x = self._mid(x, aux, gm)
         if mid_res is not None:  # :136-137
             x = ops.axpby(x, mid_res)
         g = gm
         for res, att, us in self.up:
             for j, r in enumerate(res):
                 skip = skips.pop()
-                x = r(x, emb, g, x1=skip)
+                x = r(x, aux, g, x1=skip)
                 if att is not None:
-                    x = att[j](x, ehs, g)
+                    x = att[j](x, aux, g)
             if us is not None:
                 x = ops.upsample2x(x, B * T, g[2], g[3])
                 g = (B, T, g[2] * 2, g[3] * 2)

@@ -19,6 +19,35 @@ def lib():
     return _lib.load()
 
 
+# Optional per-call timing (eager mode only; developer tool): set ops.PROFILE = {} to collect
+# {(op, shape-key): [calls, ms, flops]} with CUDA events around every call.
+PROFILE = None
+_prof_pending = []
+
+
+def _prof(op, key, flops=0.0):
+    if PROFILE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _prof_pending.append((op, key, flops, e0, e1))
+    return e1
+
+
+def _prof_end(tok):
+    if tok is not None:
+        tok.record()
+
+
+def profile_flush():
+    torch.cuda.synchronize()
+    for op, key, flops, e0, e1 in _prof_pending:
+        r = PROFILE.setdefault((op, key), [0, 0.0, 0.0])
+        r[0] += 1; r[1] += e0.elapsed_time(e1); r[2] += flops
+    _prof_pending.clear()
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -76,8 +105,10 @@ def linear(a: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
     assert w.shape[1] == K and w.is_contiguous() and a.stride(1) == 1
     kw = _alloc_out(M, N, kw.get("geglu", False), kw)
     ep = make_ep(**kw)
+    tok = _prof("linear", (M, K, N, bool(kw.get("geglu")), kw.get("res1") is not None, kw.get("res2") is not None), 2.0 * M * K * N)
     check(lib().ctrlv_linear(a.data_ptr(), a.stride(0), M, K, w.data_ptr(), N, C.byref(ep), _stream()),
           "ctrlv_linear")
+    _prof_end(tok)
     return kw["out"] if kw.get("out") is not None else kw["out_f32"]
 
 
@@ -100,8 +131,10 @@ def conv3x3(x: torch.Tensor, frames: int, H: int, W: int, w: torch.Tensor, strid
     Mo = frames * (H // stride) * (W // stride)
     kw = _alloc_out(Mo, N, kw.get("geglu", False), kw)
     ep = make_ep(**kw)
+    tok = _prof("conv3x3", (frames, H, W, stride, C0 + C1, SC0 + SC1, N), 2.0 * Mo * w.shape[1] * N)
     check(lib().ctrlv_conv3x3(x.data_ptr(), C0, _p(src1), C1, frames, H, W, stride, _p(sc0), SC0,
                               _p(sc1), SC1, w.data_ptr(), N, C.byref(ep), _stream()), "ctrlv_conv3x3")
+    _prof_end(tok)
     return kw["out"] if kw.get("out") is not None else kw["out_f32"]
 
 
@@ -114,8 +147,10 @@ def conv_t3(x: torch.Tensor, B: int, T: int, HW: int, w: torch.Tensor, **kw) -> 
     assert w.shape[1] == 3 * Cc and x.shape[0] == B * T * HW
     kw = _alloc_out(B * T * HW, N, kw.get("geglu", False), kw)
     ep = make_ep(**kw)
+    tok = _prof("conv_t3", (B, T, HW, Cc, N), 2.0 * B * T * HW * 3 * Cc * N)
     check(lib().ctrlv_conv_t3(x.data_ptr(), Cc, B, T, HW, w.data_ptr(), N, C.byref(ep), _stream()),
           "ctrlv_conv_t3")
+    _prof_end(tok)
     return kw["out"] if kw.get("out") is not None else kw["out_f32"]
 
 
@@ -148,9 +183,11 @@ def groupnorm(x: torch.Tensor, n_units: int, rows_per_unit: int, gamma: torch.Te
         out = torch.empty((x.shape[0], C0 + C1), dtype=BF16, device="cuda")
     if ws is None:
         ws = _gn_workspace(n_units)
+    tok = _prof("groupnorm", (n_units, rows_per_unit, C0 + C1))
     check(lib().ctrlv_groupnorm(x.data_ptr(), C0, _p(src1), C1, n_units, rows_per_unit, gamma.data_ptr(),
                                 beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), ws.data_ptr(),
                                 _stream()), "ctrlv_groupnorm")
+    _prof_end(tok)
     return out
 
 
@@ -164,9 +201,11 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         out = torch.empty((M, Cc), dtype=BF16, device="cuda")
     if rowbias is not None:
         _req(rowbias, torch.float32, "rowbias")
+    tok = _prof("layernorm", (M, Cc))
     check(lib().ctrlv_layernorm(x.data_ptr(), x.stride(0), M, Cc, gamma.data_ptr(), beta.data_ptr(), eps,
                                 _p(rowbias), rowbias.stride(0) if rowbias is not None else 0, rb_div,
                                 rb_mod, out.data_ptr(), _stream()), "ctrlv_layernorm")
+    _prof_end(tok)
     return out
 
 
@@ -177,8 +216,10 @@ def attn_spatial(qkv: torch.Tensor, frames: int, S: int, heads: int, scale: Opti
     assert qkv.is_contiguous() and qkv.shape == (frames * S, 3 * Cc), (qkv.shape, frames, S, heads)
     if out is None:
         out = torch.empty((frames * S, Cc), dtype=BF16, device="cuda")
+    tok = _prof("attn_spatial", (frames, S, heads), 4.0 * frames * heads * S * S * 64)
     check(lib().ctrlv_attn_spatial(qkv.data_ptr(), frames, S, heads, scale if scale is not None else 0.125,
                                    out.data_ptr(), _stream()), "ctrlv_attn_spatial")
+    _prof_end(tok)
     return out
 
 
@@ -189,8 +230,10 @@ def attn_temporal(qkv: torch.Tensor, B: int, T: int, S: int, heads: int, scale: 
     assert qkv.is_contiguous() and qkv.shape == (B * T * S, 3 * Cc)
     if out is None:
         out = torch.empty((B * T * S, Cc), dtype=BF16, device="cuda")
+    tok = _prof("attn_temporal", (B, T, S, heads), 4.0 * B * S * heads * T * T * 64)
     check(lib().ctrlv_attn_temporal(qkv.data_ptr(), B, T, S, heads, scale if scale is not None else 0.125,
                                     out.data_ptr(), _stream()), "ctrlv_attn_temporal")
+    _prof_end(tok)
     return out
 
 
