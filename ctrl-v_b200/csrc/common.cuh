@@ -93,6 +93,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// named barrier over `nthreads` threads that also AND-reduces a predicate
+__device__ __forceinline__ bool bar_red_and(int id, int nthreads, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %3, 0;\n\t"
+      "bar.red.and.pred p, %1, %2, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(r)
+      : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
+      : "memory");
+  return r != 0;
+}
+
 // ----------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------
@@ -281,19 +295,32 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(h);
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-// exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with erf from Abramowitz-Stegun 7.1.26
-// (|error| <= 1.5e-7, far below bf16 resolution): 1 rcp + 1 ex2 + 8 FMA instead of libm erff.
-__device__ __forceinline__ float gelu_erf_f(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// h * gelu_erf(g) with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below bf16
+// resolution).  gelu(g) = 0.5 (g + |g| erf(|g|/sqrt2)); the exponential is taken as exp2 of
+// -(z*sqrt(log2 e))^2 so the whole thing is 2 MUFU + 10 FP32 ops.
+__device__ __forceinline__ float geglu_f(float h, float g) {
+  const float ax = fabsf(g);
+  const float zs = ax * 0.8493218002880191f;               // |g|/sqrt2 * sqrt(log2 e)
+  const float t = rcp_approx(fmaf(0.2727374808792225f, zs, 1.0f));  // 1 / (1 + 0.3275911 z)
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(t, p, 1.421413741f);
   p = fmaf(t, p, -0.284496736f);
   p = fmaf(t, p, 0.254829592f);
   p *= t;
-  const float e = 1.0f - p * __expf(-z * z);
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  const float r = fmaf(-p, ex2_approx(-zs * zs), 1.0f);     // erf(|g|/sqrt2)
+  return (0.5f * h) * fmaf(ax, r, g);
 }
+__device__ __forceinline__ float gelu_erf_f(float x) { return geglu_f(1.0f, x); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

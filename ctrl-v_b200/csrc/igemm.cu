@@ -131,7 +131,7 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
 // one 32-column accumulator chunk of one row: prefetch residuals, TMEM load, bias, (GEGLU), store
 template <bool GEGLU>
 __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t taddr, long long m, int n0,
-                                         int n_store, bool live, const float* rb) {
+                                         int n_store, bool live, const float* sb, const float* rb) {
   constexpr int NV = GEGLU ? 16 : 32;
   ResPrefetch<NV> pf;
   pf.issue(ep, m, GEGLU ? (n0 >> 1) : n0, n_store, live);
@@ -142,10 +142,10 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-  if (ep.bias) {
+  {  // bias (+ tile-uniform rowbias) staged in shared memory by the epilogue warps
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+      const float4 b = *reinterpret_cast<const float4*>(sb + j);
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
@@ -158,7 +158,7 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
   }
   if (GEGLU) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * gelu_erf_f(v[2 * j + 1]);
+    for (int j = 0; j < 16; ++j) v[j] = geglu_f(v[2 * j], v[2 * j + 1]);
   }
   ep_finish<NV>(v, ep, m, GEGLU ? (n0 >> 1) : n0, n_store, pf);
 }
@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float bias_s[2][2][256];  // [tile parity][bias | bias + rowbias row 0][col]
 
   // 1024-byte aligned tile ring
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -292,20 +293,45 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+
+      // Stage this n-tile's bias in shared memory (overlaps the wait for the accumulator).  If every
+      // valid row of the tile uses the same rowbias row, that row is folded in as well.
+      int my_ridx = 0, ridx0 = 0;
+      if (ep.rb_mode != 0) {
+        const long long m0 = ((long long)(tz * p.bz) * p.Y + ty * p.by) * p.X + tx * p.bx;
+        ridx0 = rowbias_index(ep, (int)m0);
+        my_ridx = valid ? rowbias_index(ep, (int)m) : ridx0;
+      }
+      {
+        const int et = (int)threadIdx.x - 64;
+        if (et < p.BN) {
+          const int n = nt * p.BN + et;
+          float b = 0.f, b2 = 0.f;
+          if (n < p.N) {
+            if (ep.bias) b = __ldg(ep.bias + n);
+            b2 = b;
+            if (ep.rb_mode != 0) b2 += __ldg(ep.rowbias + (size_t)ridx0 * ep.ld_rowbias + n);
+          }
+          bias_s[as][0][et] = b;
+          bias_s[as][1][et] = b2;
+        }
+      }
+      const bool uniform = bar_red_and(1, kEpiWarps * 32, my_ridx == ridx0);
+      const float* sbias = uniform ? bias_s[as][1] : bias_s[as][0];
+      const float* rb = nullptr;
+      if (ep.rb_mode != 0 && valid && !uniform)
+        rb = ep.rowbias + (size_t)my_ridx * ep.ld_rowbias;
+
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-
-      const float* rb = nullptr;
-      if (ep.rb_mode != 0 && valid)
-        rb = ep.rowbias + (size_t)rowbias_index(ep, (int)m) * ep.ld_rowbias;
 
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
       for (int c = sub; c < p.BN / 32; c += kEpiWarps / 4) {
         __syncwarp();
         const int n0 = nt * p.BN + c * 32;  // first GEMM column of this chunk
         const bool live = valid && n0 < p.N;
-        if (ep.geglu) ep_chunk<true>(ep, t_row + (uint32_t)(c * 32), m, n0, n_store, live, rb);
-        else ep_chunk<false>(ep, t_row + (uint32_t)(c * 32), m, n0, n_store, live, rb);
+        if (ep.geglu) ep_chunk<true>(ep, t_row + (uint32_t)(c * 32), m, n0, n_store, live, sbias + c * 32, rb);
+        else ep_chunk<false>(ep, t_row + (uint32_t)(c * 32), m, n0, n_store, live, sbias + c * 32, rb);
       }
       tc_fence_before();
       __syncwarp();

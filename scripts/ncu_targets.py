@@ -1,0 +1,23 @@
+"""A few isolated kernel launches for `ncu --set full` captures."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ctrlv_b200 import ops
+BF = torch.bfloat16; dev = "cuda"
+which = sys.argv[1] if len(sys.argv) > 1 else "geglu"
+torch.manual_seed(0)
+def lin(M, K, N, **kw):
+    a = torch.randn(M, K, device=dev).to(BF); w = (torch.randn(N, K, device=dev) / K ** 0.5).to(BF)
+    b = torch.randn(N, device=dev)
+    if kw.pop("res", False):
+        kw["res1"] = torch.randn(M, N, device=dev).to(BF)
+    for _ in range(3): ops.linear(a, w, bias=b, **kw)
+    torch.cuda.synchronize()
+if which == "geglu": lin(71680, 320, 2560, geglu=True)
+elif which == "res320": lin(71680, 320, 320, res=True)
+elif which == "ffdown": lin(71680, 1280, 320, res=True)
+elif which == "attn":
+    qkv = torch.randn(28 * 2560, 960, device=dev).to(BF)
+    for _ in range(3): ops.attn_spatial(qkv, 28, 2560, 5)
+    torch.cuda.synchronize()
+print("ok")
