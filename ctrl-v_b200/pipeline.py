@@ -142,6 +142,29 @@ class DenoiseStep:
         else:
             self._body()
 
+    # -- host-buffer entry point (what a reference-side caller holding host tensors would use) -----
+    HOST_INPUTS = ("latents", "image_latents", "cond_em", "ehs", "added_time_ids", "guidance")
+
+    def make_host_buffers(self) -> Dict[str, torch.Tensor]:
+        """Pinned host mirrors of every per-step input plus the output latents."""
+        hb = {k: torch.empty(getattr(self, k).shape, dtype=torch.float32).pin_memory() for k in self.HOST_INPUTS}
+        hb["latents_out"] = torch.empty(self.latents.shape, dtype=torch.float32).pin_memory()
+        return hb
+
+    def step_host(self, i: int, hb: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """One denoise step with HOST inputs/outputs: H2D of the step's inputs, the step, D2H of the
+        updated latents, stream sync.  Returns hb["latents_out"]."""
+        for k in self.HOST_INPUTS:
+            getattr(self, k).copy_(hb[k], non_blocking=True)
+        self.step(i)
+        hb["latents_out"].copy_(self.latents, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return hb["latents_out"]
+
+    def host_bytes_per_step(self):
+        h2d = sum(getattr(self, k).numel() * 4 for k in self.HOST_INPUTS) + self.step_params.numel() * 4
+        return h2d, self.latents.numel() * 4
+
 
 class StableVideoDiffusionPipelineOutput(SimpleNamespace):
     pass

@@ -1,0 +1,265 @@
+"""GPU parity of every sm_100a kernel, called through the C ABI (ctypes), against the oracle's
+ops (torch fp32 on the same bf16-rounded inputs).  Tolerances: the kernels accumulate in fp32 and
+round once to bf16 on store (relative 2^-9 per element => rel-L2 ~ 1.7e-3); fp32 outputs 1e-5."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+TOL_BF16 = 4e-3   # rel-L2 for bf16-stored outputs
+TOL_F32 = 2e-5
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ctrlv_b200 import _lib, ops as o
+    assert _lib.load().ctrlv_device_check() == 0, _lib.load().ctrlv_last_error()
+    torch.manual_seed(0)
+    return o
+
+
+@pytest.mark.parametrize("M,K,N,flags", [
+    (128, 64, 64, {}),
+    (1, 64, 32, {}),                                # single row, narrowest tile
+    (1000, 320, 320, dict(bias=True)),              # ragged M
+    (4096, 320, 960, {}),
+    (4096, 1280, 1280, dict(bias=True, res1=True)),
+    (1120, 1280, 10240, dict(bias=True, geglu=True)),
+    (2048, 320, 2560, dict(bias=True, geglu=True, rowbias=2)),
+    (2048, 640, 640, dict(bias=True, rowbias=2, res1=True, res2=True, s_acc=0.4)),
+    (2 * 3 * 50, 128, 128, dict(bias=True, rowbias=3, res1=True)),   # time_context quirk indexing
+    (71680, 320, 320, dict(bias=True, res1=True)),  # BASELINE config-2 level-0 shape
+])
+def test_linear(ops, M, K, N, flags):
+    dev = "cuda"
+    a = torch.randn(M, K, device=dev).to(BF)
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).to(BF)
+    ref = a.float() @ w.float().t()
+    kw = {}
+    if flags.get("bias"):
+        b = torch.randn(N, device=dev); kw["bias"] = b; ref = ref + b
+    mode = flags.get("rowbias", 0)
+    if mode == 2:
+        R = 4; rb = torch.randn(R, N, device=dev); div = max(M // 8, 1)
+        kw.update(rowbias=rb, rb_mode=2, rb_div=div, rb_mod=R)
+        ref = ref + rb[(torch.arange(M, device=dev) // div) % R]
+    elif mode == 3:
+        B, T, S = 2, 3, M // 6
+        rb = torch.randn(B, N, device=dev)
+        kw.update(rowbias=rb, rb_mode=3, rb_div=T * S, rb_mod=S, rb_B=B)
+        m = torch.arange(M, device=dev)
+        ref = ref + rb[((m // (T * S)) * S + m % S) % B]
+    if flags.get("geglu"):
+        kw["geglu"] = True
+        ref = ref[:, 0::2] * F.gelu(ref[:, 1::2])
+    s_acc = flags.get("s_acc", 1.0)
+    ref = ref * s_acc; kw["s_acc"] = s_acc
+    if flags.get("res1"):
+        r1 = torch.randn(M, ref.shape[1], device=dev).to(BF); kw.update(res1=r1, s_res1=0.7); ref = ref + 0.7 * r1.float()
+    if flags.get("res2"):
+        r2 = torch.randn(M, ref.shape[1], device=dev).to(BF); kw.update(res2=r2, s_res2=0.3); ref = ref + 0.3 * r2.float()
+    out = ops.linear(a, w, **kw)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape and not torch.isnan(out).any()
+    assert rel(out, ref) < TOL_BF16
+
+
+def test_linear_fp32_output_and_padded_columns(ops):
+    a = torch.randn(300, 128, device="cuda").to(BF)
+    w = torch.zeros(32, 128, device="cuda"); w[:4] = torch.randn(4, 128, device="cuda") / 11
+    b = torch.zeros(32, device="cuda"); b[:4] = torch.randn(4, device="cuda")
+    out = torch.full((300, 4), 7.0, device="cuda")
+    ops.linear(a, w.to(BF), bias=b, out_f32=out, n_store=4)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.to(BF).float().t()[:, :4] + b[:4]
+    assert rel(out, ref) < TOL_F32
+
+
+def _pack9(w):
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+@pytest.mark.parametrize("frames,H,W,Cin,Cout,stride,shortcut", [
+    (2, 16, 16, 64, 64, 1, False),
+    (3, 40, 64, 64, 128, 1, False),
+    (4, 10, 16, 128, 128, 1, False),    # box packs several frames per tile
+    (5, 5, 8, 128, 64, 1, False),       # 120-row tiles
+    (2, 16, 16, 64, 128, 1, True),      # fused 1x1 conv_shortcut in the K loop
+    (2, 16, 16, 64, 64, 2, False),      # Downsample2D
+    (3, 40, 64, 128, 128, 2, False),
+    (1, 8, 8, 64, 64, 1, False),
+])
+def test_conv3x3(ops, frames, H, W, Cin, Cout, stride, shortcut):
+    dev = "cuda"
+    x = torch.randn(frames, Cin, H, W, device=dev).to(BF)
+    w = (torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5).to(BF)
+    b = torch.randn(Cout, device=dev)
+    ref = F.conv2d(x.float(), w.float(), b, stride=stride, padding=1)
+    xl = x.permute(0, 2, 3, 1).reshape(-1, Cin).contiguous()
+    wp = _pack9(w)
+    kw = dict(bias=b)
+    if shortcut:
+        ws = (torch.randn(Cout, Cin, device=dev) / Cin ** 0.5).to(BF)
+        x2 = torch.randn(frames, Cin, H, W, device=dev).to(BF)
+        ref = ref + F.conv2d(x2.float(), ws.float()[:, :, None, None])
+        wp = torch.cat([wp, ws], dim=1).contiguous()
+        kw["sc0"] = x2.permute(0, 2, 3, 1).reshape(-1, Cin).contiguous()
+    out = ops.conv3x3(xl, frames, H, W, wp, stride=stride, **kw)
+    torch.cuda.synchronize()
+    assert rel(out, ref.permute(0, 2, 3, 1).reshape(-1, Cout)) < TOL_BF16
+
+
+def test_conv3x3_two_sources_is_channel_concat(ops):
+    dev = "cuda"
+    f, H, W, C0, C1, Co = 2, 8, 16, 64, 128, 64
+    x0 = torch.randn(f, C0, H, W, device=dev).to(BF); x1 = torch.randn(f, C1, H, W, device=dev).to(BF)
+    w = (torch.randn(Co, C0 + C1, 3, 3, device=dev) / 40).to(BF)
+    ref = F.conv2d(torch.cat([x0, x1], 1).float(), w.float(), padding=1)
+    rows = lambda t: t.permute(0, 2, 3, 1).reshape(-1, t.shape[1]).contiguous()
+    out = ops.conv3x3(rows(x0), f, H, W, _pack9(w), src1=rows(x1))
+    torch.cuda.synchronize()
+    assert rel(out, rows(ref)) < TOL_BF16
+
+
+@pytest.mark.parametrize("B,T,HW,C,Co", [(2, 14, 160, 128, 128), (2, 14, 40, 64, 64), (1, 5, 256, 64, 128), (2, 1, 64, 64, 64)])
+def test_conv_t3(ops, B, T, HW, C, Co):
+    dev = "cuda"
+    x = torch.randn(B, C, T, HW, 1, device=dev).to(BF)
+    w = (torch.randn(Co, C, 3, 1, 1, device=dev) / (3 * C) ** 0.5).to(BF)
+    b = torch.randn(Co, device=dev)
+    ref = F.conv3d(x.float(), w.float(), b, padding=(1, 0, 0))[..., 0].permute(0, 2, 3, 1).reshape(-1, Co)
+    xl = x[..., 0].permute(0, 2, 3, 1).reshape(-1, C).contiguous()
+    wp = w[:, :, :, 0, 0].permute(0, 2, 1).reshape(Co, 3 * C).contiguous()
+    out = ops.conv_t3(xl, B, T, HW, wp, bias=b)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("frames,S,heads,sc", [(2, 128, 1, 1.0), (3, 160, 2, 1.0), (2, 40, 4, 1.0), (2, 2560, 5, 1.0),
+                                               (1, 640, 2, 3.0), (1, 1, 1, 1.0), (2, 129, 1, 2.0)])
+def test_attn_spatial(ops, frames, S, heads, sc):
+    C = heads * 64
+    qkv = (torch.randn(frames * S, 3 * C, device="cuda") * sc).to(BF)
+    out = ops.attn_spatial(qkv, frames, S, heads)
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(frames, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(frames * S, C)
+    assert not torch.isnan(out).any() and rel(out, ref) < 5e-3
+
+
+@pytest.mark.parametrize("B,T,S,heads,sc", [(1, 14, 9, 1, 1.0), (2, 14, 160, 2, 1.0), (2, 25, 64, 2, 1.0),
+                                            (2, 4, 256, 1, 3.0), (1, 1, 40, 1, 1.0), (2, 14, 2560, 5, 1.0)])
+def test_attn_temporal(ops, B, T, S, heads, sc):
+    C = heads * 64
+    qkv = (torch.randn(B * T * S, 3 * C, device="cuda") * sc).to(BF)
+    out = ops.attn_temporal(qkv, B, T, S, heads)
+    torch.cuda.synchronize()
+    x = qkv.float().view(B, T, S, 3, heads, 64).permute(3, 0, 2, 4, 1, 5)
+    ref = F.scaled_dot_product_attention(x[0], x[1], x[2]).permute(0, 3, 1, 2, 4).reshape(B * T * S, C)
+    assert not torch.isnan(out).any() and rel(out, ref) < 5e-3
+
+
+@pytest.mark.parametrize("units,rows,C0,C1,silu,eps", [(4, 256, 64, 0, True, 1e-5), (28, 2560, 320, 0, True, 1e-6),
+                                                       (2, 8960, 640, 0, True, 1e-5), (6, 160, 1280, 640, True, 1e-6),
+                                                       (6, 40, 1280, 1280, False, 1e-6), (3, 640, 640, 320, True, 1e-5),
+                                                       (2, 4, 64, 0, True, 1e-5)])
+def test_groupnorm(ops, units, rows, C0, C1, silu, eps):
+    dev = "cuda"
+    C = C0 + C1
+    x0 = (torch.randn(units * rows, C0, device=dev) * 2 + 0.5).to(BF)
+    x1 = (torch.randn(units * rows, C1, device=dev) - 0.3).to(BF) if C1 else None
+    g = torch.randn(C, device=dev); b = torch.randn(C, device=dev)
+    out = ops.groupnorm(x0, units, rows, g, b, eps, silu, src1=x1)
+    out2 = ops.groupnorm(x0, units, rows, g, b, eps, silu, src1=x1)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)  # deterministic reduction
+    x = torch.cat([x0, x1], 1) if C1 else x0
+    ref = F.group_norm(x.float().view(units, rows, C).permute(0, 2, 1), 32, g, b, eps)
+    if silu:
+        ref = F.silu(ref)
+    assert rel(out, ref.permute(0, 2, 1).reshape(-1, C)) < TOL_BF16
+
+
+@pytest.mark.parametrize("M,C,rb", [(4096, 320, False), (1120, 1280, False), (14 * 2 * 24, 64, True), (14 * 40, 640, True), (77, 128, False)])
+def test_layernorm(ops, M, C, rb):
+    dev = "cuda"
+    x = (torch.randn(M, C, device=dev) * 1.5 + 0.2).to(BF)
+    g = torch.randn(C, device=dev); b = torch.randn(C, device=dev)
+    kw, xr = {}, x.float()
+    if rb:
+        T = 7; S = M // (2 * T)
+        pos = torch.randn(T, C, device=dev)
+        kw = dict(rowbias=pos, rb_div=S, rb_mod=T)
+        xr = xr + pos[(torch.arange(M, device=dev) // S) % T]
+    out = ops.layernorm(x, g, b, 1e-5, **kw)
+    torch.cuda.synchronize()
+    assert rel(out, F.layer_norm(xr, (C,), g, b, 1e-5)) < TOL_BF16
+
+
+def test_small_linear_and_sinusoid(ops):
+    dev = "cuda"
+    for M, K, N, ai, ao in [(2, 320, 1280, False, True), (2, 1280, 1280, True, False), (14, 320, 1280, False, True), (25, 1024, 320, False, False)]:
+        x = torch.randn(M, K, device=dev); w = (torch.randn(N, K, device=dev) / K ** 0.5).to(BF); b = torch.randn(N, device=dev)
+        ref = (F.silu(x) if ai else x) @ w.float().t() + b
+        ref = F.silu(ref) if ao else ref
+        out = ops.small_linear(x, w, b, ai, ao)
+        assert rel(out, ref) < TOL_F32
+        acc = out.clone()
+        ops.small_linear(x, w, b, ai, ao, out=acc, accumulate=True)
+        assert rel(acc, 2 * ref) < TOL_F32
+    t = torch.tensor([1.63777006, -1.55365205, 6.0, 127.0, 0.02], device=dev)
+    e = ops.sinusoid(t, 320, round_bf16=False)
+    # SURVEY.md A.8 known answer
+    assert torch.allclose(e[0, :3].cpu(), torch.tensor([-0.0669237, 0.0246392, 0.1109036]), atol=2e-6)
+    assert torch.allclose(e[0, 160:163].cpu(), torch.tensor([0.9977581, 0.9996964, 0.9938312]), atol=2e-6)
+    from oracle.svd_oracle import Timesteps
+    assert rel(e, Timesteps(320)(t)) < 1e-5
+
+
+def test_loop_glue(ops):
+    from oracle.sampling import EulerDiscreteSchedulerOracle
+    dev = "cuda"
+    B, T, h, w = 2, 3, 8, 16
+    lat = torch.randn(B, T, 4, h, w, device=dev) * 10
+    img = torch.randn(2 * B, T, 4, h, w, device=dev); ctl = torch.randn(2 * B, T, 4, h, w, device=dev)
+    sch = EulerDiscreteSchedulerOracle(); sch.set_timesteps(25)
+    i = 9
+    sd = sch.sigmas[i:i + 2].to(dev).contiguous()
+    out = ops.prep_input(lat, img, ctl, True, sd)
+    ref = torch.zeros(2 * B, T, h, w, 64, device=dev)
+    ref[..., 0:4] = (torch.cat([lat, lat]) / float((sch.sigmas[i] ** 2 + 1) ** 0.5)).permute(0, 1, 3, 4, 2)
+    ref[..., 4:8] = img.permute(0, 1, 3, 4, 2); ref[..., 8:12] = ctl.permute(0, 1, 3, 4, 2)
+    assert rel(out, ref.reshape(-1, 64)) < TOL_BF16 and float(out[:, 12:].abs().max()) == 0.0
+    noise = torch.randn(2 * B * T * h * w, 4, device=dev)
+    g = torch.linspace(1, 3, T, device=dev)
+    lat2 = lat.clone()
+    ops.cfg_euler(lat2, noise, True, g, sd)
+    n5 = noise.view(2 * B, T, h, w, 4).permute(0, 1, 4, 2, 3)
+    v = n5[:B] + g.view(1, T, 1, 1, 1) * (n5[B:] - n5[:B])
+    sch.step_index = i
+    want = sch.step(v, sch.timesteps[i], lat)   # the oracle's EulerDiscreteScheduler.step
+    assert rel(lat2, want) < TOL_F32
+    x = torch.randn(3 * 4 * 6, 64, device=dev).to(BF)
+    up = ops.upsample2x(x, 3, 4, 6)
+    refu = F.interpolate(x.float().view(3, 4, 6, 64).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    assert torch.equal(up.float(), refu.permute(0, 2, 3, 1).reshape(-1, 64))
+    y = torch.randn(3 * 4 * 6, 64, device=dev).to(BF)
+    assert rel(ops.axpby(x, y, 0.3, 0.7), 0.3 * x.float() + 0.7 * y.float()) < TOL_BF16
+
+
+def test_errors_are_loud(ops):
+    from ctrlv_b200._lib import CtrlvError
+    a = torch.randn(64, 48, device="cuda").to(BF)   # K not a multiple of 64
+    w = torch.randn(64, 48, device="cuda").to(BF)
+    with pytest.raises(CtrlvError):
+        ops.linear(a, w)
+    with pytest.raises(ValueError):
+        ops.linear(a.float(), w)

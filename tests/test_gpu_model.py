@@ -1,0 +1,183 @@
+"""GPU parity of the drop-in models, the fused denoise step and the pipeline against the fp32
+oracle (north_star tolerance: per-step latent relative L2 <= 1e-2 in bf16)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def _build(order, over):
+    from ctrlv_b200 import models
+    from oracle import svd_oracle as O
+    torch.manual_seed(0)
+    ou = O.UNetSpatioTemporalConditionModel(time_context_order=order, **over)
+    oc = O.ControlNetModel(time_context_order=order, **over)
+    O.randomize_zero_convs(oc)
+    ou, oc = ou.to(dev).eval(), oc.to(dev).eval()
+    mu = models.UNetSpatioTemporalConditionModel(state_dict=ou.state_dict(), time_context_order=order, **over)
+    mc = models.ControlNetModel(state_dict=oc.state_dict(), time_context_order=order, **over)
+    return ou, oc, mu, mc
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from oracle import svd_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return _build("s_major", dict(O.TINY_CONFIG))
+
+
+def _inputs(T, h, w, sigma):
+    from oracle import svd_oracle as O
+    from oracle import sampling as S
+    inp = S.make_inputs(T=T, h=h, w=w, xdim=O.TINY_CONFIG["cross_attention_dim"], device=dev)
+    x = torch.cat([inp["latents"] * (sigma ** 2 + 1) ** 0.5] * 2) / (sigma ** 2 + 1) ** 0.5
+    return inp, torch.cat([x, inp["image_latents"]], dim=2)
+
+
+@pytest.mark.parametrize("T,h,w", [(4, 16, 16), (3, 8, 24)])
+def test_controlnet_and_unet_forward(tiny, T, h, w):
+    ou, oc, mu, mc = tiny
+    inp, x = _inputs(T, h, w, 15.59)
+    t = torch.tensor(0.6866)
+    with torch.no_grad():
+        od, om = oc(x, t, inp["image_embeddings"], inp["added_time_ids"], control_cond=inp["cond_em"],
+                    conditioning_scale=0.8, return_dict=False)
+        oy = ou(x, t, inp["image_embeddings"], inp["added_time_ids"], od, om, return_dict=False)[0]
+        oy0 = ou(x, t, inp["image_embeddings"], inp["added_time_ids"], return_dict=False)[0]
+    out = mc(x, timestep=t.to(dev), encoder_hidden_states=inp["image_embeddings"],
+             added_time_ids=inp["added_time_ids"], control_cond=inp["cond_em"], conditioning_scale=0.8)
+    md, mm = out.down_block_res_samples, out.mid_block_res_sample
+    assert len(md) == 12 and [tuple(a.shape) for a in md] == [tuple(b.shape) for b in od]
+    assert tuple(mm.shape) == tuple(om.shape)
+    my = mu(sample=x, timestep=t.to(dev), encoder_hidden_states=inp["image_embeddings"],
+            added_time_ids=inp["added_time_ids"], down_block_additional_residuals=md,
+            mid_block_additional_residuals=mm, return_dict=False)[0]
+    my0 = mu(x, torch.stack([t, t]).to(dev), inp["image_embeddings"], inp["added_time_ids"]).sample  # [B] timestep
+    torch.cuda.synchronize()
+    assert max(rel(a, b) for a, b in zip(md, od)) < 2.5e-2 and rel(mm, om) < 2.5e-2
+    assert rel(my, oy) < 2e-2 and rel(my0, oy0) < 2e-2
+    assert rel(oy, oy0) > 5e-2  # the ControlNet path carries signal in this test
+
+
+def test_residuals_in_reference_layout_are_accepted(tiny):
+    """The UNet accepts residuals as plain contiguous NCHW fp32 tensors (what a reference
+    ControlNet would hand over), not only this package's channels-last views."""
+    ou, oc, mu, mc = tiny
+    inp, x = _inputs(2, 8, 8, 3.0)
+    t = torch.tensor(0.27, device=dev)
+    md, mm = mc(x, t, inp["image_embeddings"], inp["added_time_ids"], control_cond=inp["cond_em"], return_dict=False)
+    a = mu(x, t, inp["image_embeddings"], inp["added_time_ids"], md, mm, return_dict=False)[0]
+    b = mu(x, t, inp["image_embeddings"], inp["added_time_ids"], [d.float().contiguous() for d in md],
+           mm.float().contiguous(), return_dict=False)[0]
+    assert torch.equal(a, b)
+
+
+def test_zero_init_controlnet_is_a_noop_and_from_unet(tiny):
+    from ctrlv_b200 import models
+    ou, oc, mu, mc = tiny
+    c0 = models.ControlNetModel.from_unet(mu)
+    sd = c0.state_dict()
+    for k in sd:
+        if k.startswith("controlnet_"):
+            sd[k] = torch.zeros_like(sd[k])
+    c0.load_state_dict(sd)
+    inp, x = _inputs(2, 8, 8, 3.0)
+    t = torch.tensor(0.27, device=dev)
+    d, m = c0(x, t, inp["image_embeddings"], inp["added_time_ids"], control_cond=inp["cond_em"], return_dict=False)
+    assert all(float(r.abs().max()) == 0.0 for r in d) and float(m.abs().max()) == 0.0
+    y0 = mu(x, t, inp["image_embeddings"], inp["added_time_ids"], return_dict=False)[0]
+    y1 = mu(x, t, inp["image_embeddings"], inp["added_time_ids"], d, m, return_dict=False)[0]
+    assert torch.equal(y0, y1)
+
+
+@pytest.mark.parametrize("order", ["s_major", "b_major"])
+def test_pipeline_loop_matches_oracle_loop(order):
+    from ctrlv_b200 import pipeline
+    from oracle import sampling as S
+    from oracle import svd_oracle as O
+    ou, oc, mu, mc = _build(order, dict(O.TINY_CONFIG))
+    T, h, w, steps = 4, 16, 16, 25  # the reference's default schedule (pipeline_video_control.py:112)
+    inp = S.make_inputs(T=T, h=h, w=w, xdim=O.TINY_CONFIG["cross_attention_dim"], device=dev)
+    trace, mtrace = [], []
+    with torch.no_grad():
+        S.sample_loop(ou, oc, inp, num_steps=steps, trace=trace)
+    pipe = pipeline.StableVideoControlPipeline(unet=mu, controlnet=mc)
+    res = {}
+    for use_graph in (False, True):
+        mtrace.clear()
+        out = pipe(cond_images=inp["cond_em_cond"], height=h * 8, width=w * 8, num_frames=T,
+                   num_inference_steps=steps, latents=inp["latents"].clone(), output_type="latent",
+                   image_embeddings=inp["image_embeds_cond"], image_latents=inp["image_latents_cond"],
+                   use_graph=use_graph,
+                   callback_on_step_end=lambda p, i, t, kw: mtrace.append(kw["latents"].clone()) or {})
+        torch.cuda.synchronize()
+        res[use_graph] = out.frames.clone()
+        # teacher-forced per-step error: restart each step from the oracle's state
+        st = next(s for k, s in pipe._steps.items() if k[-1] == use_graph)
+        sch = S.EulerDiscreteSchedulerOracle(); sch.set_timesteps(steps)
+        prevs = [inp["latents"] * sch.init_noise_sigma] + trace[:-1]
+        for i in range(steps):
+            st.latents.copy_(prevs[i]); st.step(i)
+            assert rel(st.latents, trace[i]) < 1e-2, (order, use_graph, i)
+    assert torch.equal(res[False], res[True])  # graph replay == eager launches, bit for bit
+
+
+def test_pipeline_errors():
+    from ctrlv_b200 import pipeline, models
+    from oracle import svd_oracle as O
+    mu = models.UNetSpatioTemporalConditionModel(**O.TINY_CONFIG)
+    pipe = pipeline.StableVideoControlPipeline(unet=mu, controlnet=None)
+    with pytest.raises(ValueError):
+        pipe(cond_images=None, height=64, width=64)
+    with pytest.raises(ValueError):
+        pipe(cond_images=torch.zeros(1, 2, 4, 8, 8), height=65, width=64)
+    with pytest.raises(NotImplementedError):
+        pipe(cond_images=torch.zeros(1, 2, 4, 8, 8), height=64, width=64, num_frames=2)
+
+
+@pytest.mark.parametrize("T,h,w", [(14, 40, 64)])
+def test_full_size_single_step(T, h, w):
+    """BASELINE config 1/2 shapes with the full SVD architecture: one CFG step, noise_pred and
+    teacher-forced latent error vs the fp32 oracle (run on the GPU in fp32)."""
+    from ctrlv_b200 import models, pipeline
+    from oracle import sampling as S
+    from oracle import svd_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = dict(models.SVD_CONFIG)
+    sd_u = models.random_state_dict(cfg, False, seed=0, dtype=torch.float32)
+    sd_c = models.random_state_dict(cfg, True, seed=1, dtype=torch.float32)
+    with torch.device("meta"):
+        ou = O.UNetSpatioTemporalConditionModel(); oc = O.ControlNetModel()
+    ou.load_state_dict(sd_u, assign=True); oc.load_state_dict(sd_c, assign=True)
+    mu = models.UNetSpatioTemporalConditionModel(state_dict=sd_u)
+    mc = models.ControlNetModel(state_dict=sd_c)
+    inp = S.make_inputs(T=T, h=h, w=w, device=dev)
+    sch = S.EulerDiscreteSchedulerOracle(); sch.set_timesteps(25)
+    st = pipeline.DenoiseStep(mu, mc, 1, T, h, w, cfg=True, use_graph=False)
+    st.set_schedule(sch.sigmas, sch.timesteps)
+    st.image_latents.copy_(inp["image_latents"]); st.cond_em.copy_(inp["cond_em"])
+    st.ehs.copy_(inp["image_embeddings"].reshape(2, -1)); st.added_time_ids.copy_(inp["added_time_ids"])
+    st.guidance.copy_(inp["guidance"])
+    gs = inp["guidance"].view(1, -1, 1, 1, 1)
+    for i in (0, 17):
+        sigma = sch.sigmas[i]
+        lat = inp["latents"] * float((sigma ** 2 + 1) ** 0.5)
+        sch.step_index = i
+        with torch.no_grad():
+            want, noise = S.denoise_step(ou, oc, sch, lat, sch.timesteps[i], inp["image_latents"],
+                                         inp["image_embeddings"], inp["added_time_ids"], inp["cond_em"], gs,
+                                         return_noise=True)
+        st.latents.copy_(lat)
+        st.step(i)
+        torch.cuda.synchronize()
+        got_noise = st.noise.view(2, T, h, w, 4).permute(0, 1, 4, 2, 3)
+        assert rel(got_noise, noise) < 2e-2, i          # model output (bf16 path vs fp32 oracle)
+        assert rel(st.latents, want) < 1e-2, i          # north_star: per-step latent rel L2 <= 1e-2

@@ -1,0 +1,127 @@
+"""CPU tests of the host-side logic and of the C-ABI library surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_param_spec_matches_oracle_state_dict():
+    from ctrlv_b200 import models
+    from oracle import svd_oracle as O
+    for over in ({}, O.TINY_CONFIG):
+        with torch.device("meta"):
+            u = O.UNetSpatioTemporalConditionModel(**over)
+            c = O.ControlNetModel(**over)
+        for mod, ctrl in ((u, False), (c, True)):
+            spec = models.param_spec({**models.SVD_CONFIG, **over}, ctrl)
+            sd = {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+            assert set(spec) == set(sd)
+            assert all(tuple(spec[k]) == sd[k] for k in sd)
+    import math
+    assert sum(math.prod(s) for s in models.param_spec(models.SVD_CONFIG, False).values()) == 1_524_623_082
+    assert sum(math.prod(s) for s in models.param_spec(models.SVD_CONFIG, True).values()) == 680_946_897
+
+
+def test_product_scheduler_equals_oracle_scheduler():
+    from ctrlv_b200.pipeline import EulerDiscreteScheduler
+    from oracle.sampling import EulerDiscreteSchedulerOracle
+    for n in (2, 25, 30, 50):
+        a = EulerDiscreteScheduler().set_timesteps(n)
+        b = EulerDiscreteSchedulerOracle()
+        b.set_timesteps(n)
+        assert torch.equal(a.sigmas, b.sigmas)
+        assert torch.allclose(a.timesteps, b.timesteps, rtol=0, atol=2e-7)
+        assert abs(a.init_noise_sigma - float(b.init_noise_sigma)) < 1e-3
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "ctrlv_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctrlv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ctrlv_b200 import _lib
+    names = _declared_functions()
+    assert len(names) >= 20
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    lib = _lib.load()  # builds in-tree if absent (nvcc cross-compiles without a GPU)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert b"sm_100a" in lib.ctrlv_version()
+    assert isinstance(lib.ctrlv_last_error(), bytes)
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors of the C structs: sizes must match what nvcc compiled (checked through a tiny
+    C program compiled with gcc against the same header)."""
+    import subprocess
+    import tempfile
+    from ctrlv_b200 import _lib
+    prog = r'''
+#include <stdio.h>
+#include "ctrlv_b200.h"
+int main(void){ printf("%zu %zu %zu %zu\n", sizeof(ctrlv_epilogue), sizeof(ctrlv_src), sizeof(ctrlv_seg), sizeof(ctrlv_igemm_desc)); return 0; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [ctypes.sizeof(_lib.Epilogue), ctypes.sizeof(_lib.Src), ctypes.sizeof(_lib.Seg),
+                     ctypes.sizeof(_lib.IgemmDesc)]
+
+
+def test_input_validation_mirrors_reference():
+    from ctrlv_b200 import models
+    chk = models._PackedModel._check_inputs
+    ok = torch.zeros(2, 3, 8, 16, 16)
+    ehs = torch.zeros(2, 1, 1024)
+    ids = torch.zeros(2, 3)
+    chk(ok, torch.tensor(1.0), ehs, ids)
+    with pytest.raises(TypeError):
+        chk(ok, 1.0, ehs, ids)  # controlnet.py:262-264: timestep must be a tensor
+    with pytest.raises(ValueError):
+        chk(torch.zeros(2, 3, 8, 12, 16), torch.tensor(1.0), ehs, ids)
+    with pytest.raises(NotImplementedError):
+        chk(ok, torch.tensor(1.0), torch.zeros(2, 4, 1024), ids)
+
+
+def test_pipeline_check_inputs():
+    from ctrlv_b200.pipeline import StableVideoControlPipeline
+    p = StableVideoControlPipeline.__new__(StableVideoControlPipeline)
+    with pytest.raises(ValueError):  # pipeline_video_control.py:61-65
+        p.check_inputs(None, None, 320, 512)
+    with pytest.raises(ValueError):  # :67-68
+        p.check_inputs(None, torch.zeros(1), 321, 512)
+    p.check_inputs(None, torch.zeros(1), 320, 512)
+
+
+def test_shard_clips():
+    from ctrlv_b200.parallel import shard_clips
+    for n in (1, 7, 8, 13):
+        for w in (1, 2, 4, 8):
+            parts = [shard_clips(n, w, r) for r in range(w)]
+            assert sum(parts, []) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    with pytest.raises(ValueError):
+        shard_clips(4, 2, 2)
+
+
+def test_geglu_interleave_and_conv_packing():
+    from ctrlv_b200 import models
+    w = torch.arange(8 * 3, dtype=torch.float32).reshape(8, 3)
+    b = torch.arange(8, dtype=torch.float32)
+    wi, bi = models._interleave_geglu(w, b)
+    assert torch.equal(wi[0::2], w[:4]) and torch.equal(wi[1::2], w[4:])
+    assert torch.equal(bi[0::2], b[:4]) and torch.equal(bi[1::2], b[4:])
+    cw = torch.randn(5, 7, 3, 3)
+    p = models._conv9(cw)
+    assert p.shape == (5, 63) and torch.equal(p[:, 7 * 4:7 * 5], cw[:, :, 1, 1])  # tap (1,1) = centre
+    tw = torch.randn(5, 7, 3, 1, 1)
+    assert torch.equal(models._conv_t3(tw)[:, 7:14], tw[:, :, 1, 0, 0])
