@@ -85,11 +85,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)  // suspend-time hint (ns): sleep in hardware instead of spinning
       : "memory");
 }
 

@@ -30,6 +30,11 @@ struct AttnParams {
   bf16* out;
 };
 
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -174,9 +179,20 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
         tmem_ld32(tS + lane_off + c * 32, raw);
         tmem_ld_wait();
         const uint32_t okm = chunk_mask(kv0, c);
+        if (okm == 0xffffffffu) {  // common case: every column valid, no per-element predicate
+          float m0 = fmaxf(__uint_as_float(raw[0]), __uint_as_float(raw[1]));
+          float m1 = fmaxf(__uint_as_float(raw[2]), __uint_as_float(raw[3]));
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if ((okm >> i) & 1u) m_blk = fmaxf(m_blk, __uint_as_float(raw[i]));
+          for (int i = 4; i < 32; i += 4) {
+            m0 = max3f(m0, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+            m1 = max3f(m1, __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+          }
+          m_blk = max3f(m_blk, m0, m1);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if ((okm >> i) & 1u) m_blk = fmaxf(m_blk, __uint_as_float(raw[i]));
+        }
       }
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = ex2f((m_run - m_new) * p.c);
@@ -206,14 +222,26 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
         tmem_ld_wait();
         uint32_t pk[16];
         const uint32_t okm = chunk_mask(kv0, c);
+        if (okm == 0xffffffffu) {
+          float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pv[2];
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2f(fmaf(__uint_as_float(raw[i]), p.c, -mc));
+            const float p1 = ex2f(fmaf(__uint_as_float(raw[i + 1]), p.c, -mc));
+            l0 += p0; l1 += p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          l_run += l0 + l1;
+        } else {
 #pragma unroll
-          for (int e = 0; e < 2; ++e)
-            pv[e] = ((okm >> (i + e)) & 1u) ? ex2f(__uint_as_float(raw[i + e]) * p.c - mc) : 0.f;
-          l_run += pv[0] + pv[1];
-          pk[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+          for (int i = 0; i < 32; i += 2) {
+            float pv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              pv[e] = ((okm >> (i + e)) & 1u) ? ex2f(__uint_as_float(raw[i + e]) * p.c - mc) : 0.f;
+            l_run += pv[0] + pv[1];
+            pk[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+          }
         }
         uint8_t* atom = prow + (c >> 1) * kTile;
 #pragma unroll

@@ -14,6 +14,8 @@
 // * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..17 = epilogue
 //   (each owns the TMEM lane quarter warp_id % 4, one accumulator row per thread; the four warps
 //   of a quarter split the 32-column chunks so global-load latency of residuals is overlapped).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/ctrlv_b200.h"
 
@@ -429,6 +431,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   p.tiles_z = (d->Z + p.bz - 1) / p.bz;
   p.N = d->N;
   p.BN = d->bn > 0 ? d->bn : choose_bn(d->N, (long long)p.tiles_x * p.tiles_y * p.tiles_z, g_num_sms);
+  if (const char* e = getenv("CTRLV_DEBUG_BN")) p.BN = atoi(e);  // developer override
   if (p.BN == 0) {
     // ragged N: largest 32-multiple tile, TMA zero-fills the weight rows past N
     p.BN = d->N >= 256 ? 256 : ((d->N + 31) / 32) * 32;
@@ -475,6 +478,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   p.stage_bytes = kBM * kBK * 2 + p.BN * kBK * 2;
   int stages = (g_max_smem - 2048) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (const char* e = getenv("CTRLV_DEBUG_STAGES")) stages = atoi(e);  // developer override
   CTRLV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for 2 stages");
   p.stages = stages;
   p.tmem_cols = 2 * p.BN <= 128 ? 128 : (2 * p.BN <= 256 ? 256 : 512);
