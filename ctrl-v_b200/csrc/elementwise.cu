@@ -36,7 +36,7 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int M, int K,
           float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float t = act_in ? silu_f(xv[j]) : xv[j];
+            const float t = act_in ? silu_acc_f(xv[j]) : xv[j];
             acc[mi] += t * w[j];
           }
         }
@@ -47,7 +47,7 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int M, int K,
       const float s = warp_sum(acc[mi]);
       if (lane == 0 && m0 + mi < M) {
         float t = s + (bias ? bias[n] : 0.f);
-        t = act_out ? silu_f(t) : t;
+        t = act_out ? silu_acc_f(t) : t;
         float* yp = y + (size_t)(m0 + mi) * N + n;
         *yp = accumulate ? *yp + t : t;
       }

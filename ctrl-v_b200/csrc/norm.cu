@@ -81,7 +81,7 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ src0, int C0, const bf1
 // GroupNorm apply (+SiLU): out[row][C0+C1] = act((x - mean) * rstd * gamma + beta)
 // grid = n_units * blocks_per_unit; a block stays inside one statistics unit.
 // ------------------------------------------------------------------------------------------
-__global__ void gn_apply_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict__ src1,
+__global__ void __launch_bounds__(512, 3) gn_apply_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict__ src1,
                                 int C1, int rows_per_unit, int blocks_per_unit, int nsplit,
                                 int nwork, const float* __restrict__ partial, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu,
@@ -143,7 +143,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ src0, int C0, const bf1
   int r_end = r_begin + rows_per_blk;
   if (r_end > rows_per_unit) r_end = rows_per_unit;
   const size_t row0 = (size_t)unit * rows_per_unit;
-#pragma unroll 4
+#pragma unroll 8
   for (int r = r_begin + rsub; r < r_end; r += rpar) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (row0 + r) * ld));
     float v[8];
@@ -227,15 +227,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
   for (int i = 0; i < VPL; ++i) {
     const int vec = sl + LPR * i;
     if (vec < vpr) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8 + 4));
       float o[8];
-      o[0] = (v[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[i][1] - mean) * rstd * g0.y + b0.y;
-      o[2] = (v[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[i][3] - mean) * rstd * g0.w + b0.w;
-      o[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
-      o[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
+      const float nm = -mean * rstd;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(v[i][j], rstd, nm);
+      if (gamma) {  // affine folded into the consumer's weights when gamma == nullptr
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8 + 4));
+        o[0] = o[0] * g0.x + b0.x; o[1] = o[1] * g0.y + b0.y; o[2] = o[2] * g0.z + b0.z; o[3] = o[3] * g0.w + b0.w;
+        o[4] = o[4] * g1.x + b1.x; o[5] = o[5] * g1.y + b1.y; o[6] = o[6] * g1.z + b1.z; o[7] = o[7] * g1.w + b1.w;
+      }
       uint4 u;
       u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
       u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
@@ -295,7 +298,7 @@ extern "C" int ctrlv_layernorm(const void* x, int64_t ldx, int32_t M, int32_t C,
                                int32_t ld_rowbias, int32_t rb_div, int32_t rb_mod, void* out,
                                void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CTRLV_CHECK_ARG(x && out && gamma && beta, "layernorm: null pointer");
+  CTRLV_CHECK_ARG(x && out && ((gamma == nullptr) == (beta == nullptr)), "layernorm: null pointer");
   CTRLV_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * 8, "layernorm: C=%d unsupported", C);
   CTRLV_CHECK_ARG(ldx % 8 == 0, "layernorm: ldx %% 8");
   if (rowbias) CTRLV_CHECK_ARG(rb_div > 0 && rb_mod > 0 && ld_rowbias % 4 == 0, "layernorm: bad rowbias args");

@@ -288,9 +288,23 @@ class _ResBlock:
                            res1=xs, s_res1=1.0)
 
 
+def _fold_ln(w, b, norm_w, norm_b):
+    """Linear(LayerNorm_affine(z)) = (W diag(gamma)) z + (b + W beta): fold the LayerNorm's affine
+    part into the Linear that consumes it, so the norm kernel only normalises."""
+    w = w.float()
+    g, be = norm_w.float().to(w.device), norm_b.float().to(w.device)
+    b2 = w @ be
+    if b is not None:
+        b2 = b2 + b.float().to(w.device)
+    return w * g[None, :], b2
+
+
 class _FF:
-    def __init__(self, sd, pfx):
-        w1, b1 = _interleave_geglu(sd[pfx + ".net.0.proj.weight"].float(), sd[pfx + ".net.0.proj.bias"].float())
+    def __init__(self, sd, pfx, norm=None):
+        w1, b1 = sd[pfx + ".net.0.proj.weight"].float(), sd[pfx + ".net.0.proj.bias"].float()
+        if norm is not None:
+            w1, b1 = _fold_ln(w1, b1, sd[norm + ".weight"], sd[norm + ".bias"])
+        w1, b1 = _interleave_geglu(w1, b1)
         self.w1, self.b1 = _w(w1), _f(b1)
         self.w2, self.b2 = _w(sd[pfx + ".net.2.weight"]), _f(sd[pfx + ".net.2.bias"])
 
@@ -299,8 +313,10 @@ class _FF:
 
 
 class _SelfAttn:
-    def __init__(self, sd, pfx):
-        self.wqkv = _w(torch.cat([sd[pfx + ".to_q.weight"], sd[pfx + ".to_k.weight"], sd[pfx + ".to_v.weight"]], 0))
+    def __init__(self, sd, pfx, norm):
+        w = torch.cat([sd[pfx + ".to_q.weight"], sd[pfx + ".to_k.weight"], sd[pfx + ".to_v.weight"]], 0)
+        w, b = _fold_ln(w, None, sd[norm + ".weight"], sd[norm + ".bias"])
+        self.wqkv, self.bqkv = _w(w), _f(b)
         self.out = _Lin(sd, pfx + ".to_out.0")
 
 
@@ -323,12 +339,12 @@ class _Transformer:
         self.norm = _Norm(sd, pfx + ".norm")
         self.proj_in, self.proj_out = _Lin(sd, pfx + ".proj_in"), _Lin(sd, pfx + ".proj_out")
         b = pfx + ".transformer_blocks.0"
-        self.norm1, self.norm3 = _Norm(sd, b + ".norm1"), _Norm(sd, b + ".norm3")
-        self.attn1, self.attn2, self.ff = _SelfAttn(sd, b + ".attn1"), _CrossAttnL1(sd, b + ".attn2"), _FF(sd, b + ".ff")
+        # every LayerNorm feeds a Linear: its affine part is folded into that Linear's weights
+        self.attn1 = _SelfAttn(sd, b + ".attn1", b + ".norm1")
+        self.attn2, self.ff = _CrossAttnL1(sd, b + ".attn2"), _FF(sd, b + ".ff", b + ".norm3")
         t = pfx + ".temporal_transformer_blocks.0"
-        self.tnorm_in, self.tnorm1, self.tnorm3 = _Norm(sd, t + ".norm_in"), _Norm(sd, t + ".norm1"), _Norm(sd, t + ".norm3")
-        self.tff_in, self.tff = _FF(sd, t + ".ff_in"), _FF(sd, t + ".ff")
-        self.tattn1, self.tattn2 = _SelfAttn(sd, t + ".attn1"), _CrossAttnL1(sd, t + ".attn2")
+        self.tff_in, self.tff = _FF(sd, t + ".ff_in", t + ".norm_in"), _FF(sd, t + ".ff", t + ".norm3")
+        self.tattn1, self.tattn2 = _SelfAttn(sd, t + ".attn1", t + ".norm1"), _CrossAttnL1(sd, t + ".attn2")
         self.pos1, self.pos2 = _Lin(sd, pfx + ".time_pos_embed.linear_1"), _Lin(sd, pfx + ".time_pos_embed.linear_2")
         self.alpha = float(torch.sigmoid(sd[pfx + ".time_mixer.mix_factor"].float()).item())
         self.C = self.proj_in.w.shape[0]
@@ -351,20 +367,20 @@ class _Transformer:
         a = ops.groupnorm(x, F_, S, self.norm.g, self.norm.b, 1e-6, False)
         h = ops.linear(a, self.proj_in.w, bias=self.proj_in.b)
         # --- BasicTransformerBlock (spatial)
-        n = ops.layernorm(h, self.norm1.g, self.norm1.b)
-        qkv = ops.linear(n, self.attn1.wqkv)
+        n = ops.layernorm(h)
+        qkv = ops.linear(n, self.attn1.wqkv, bias=self.attn1.bqkv)
         att = ops.attn_spatial(qkv, F_, S, self.heads)
         ctx = aux.ctx[:, self.attn2.off:self.attn2.off + self.C]
         h = ops.linear(att, self.attn1.out.w, bias=self.attn1.out.b, rowbias=ctx, rb_mode=1, rb_div=T * S, res1=h)
-        n = ops.layernorm(h, self.norm3.g, self.norm3.b)
+        n = ops.layernorm(h)
         h = ops.linear(self.ff.up(n), self.ff.w2, bias=self.ff.b2, res1=h)
         # --- TemporalBasicTransformerBlock on h + pos[t]; sequences are the T frames of a site
         pos = self.pos_emb(T)
-        n = ops.layernorm(h, self.tnorm_in.g, self.tnorm_in.b, rowbias=pos, rb_div=S, rb_mod=T)
+        n = ops.layernorm(h, rowbias=pos, rb_div=S, rb_mod=T)
         hm = ops.linear(self.tff_in.up(n), self.tff_in.w2, bias=self.tff_in.b2, res1=h,
                         rowbias=pos, rb_mode=2, rb_div=S, rb_mod=T)
-        n = ops.layernorm(hm, self.tnorm1.g, self.tnorm1.b)
-        qkv = ops.linear(n, self.tattn1.wqkv)
+        n = ops.layernorm(hm)
+        qkv = ops.linear(n, self.tattn1.wqkv, bias=self.tattn1.bqkv)
         att = ops.attn_temporal(qkv, B, T, S, self.heads)
         ctx_t = aux.ctx[:, self.tattn2.off:self.tattn2.off + self.C]
         if self.order == "s_major":  # diffusers 0.27.2: context of row (b, s) is ctx[(b*S + s) % B]
@@ -372,7 +388,7 @@ class _Transformer:
         else:
             kw = dict(rb_mode=1, rb_div=T * S)
         hm = ops.linear(att, self.tattn1.out.w, bias=self.tattn1.out.b, rowbias=ctx_t, res1=hm, **kw)
-        n = ops.layernorm(hm, self.tnorm3.g, self.tnorm3.b)
+        n = ops.layernorm(hm)
         # ff(n) + hm, then AlphaBlender: a*h + (1-a)*(ff + hm)
         h = ops.linear(self.tff.up(n), self.tff.w2, bias=self.tff.b2, s_acc=1.0 - self.alpha,
                        res1=hm, s_res1=1.0 - self.alpha, res2=h, s_res2=self.alpha)

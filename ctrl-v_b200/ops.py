@@ -191,10 +191,13 @@ def groupnorm(x: torch.Tensor, n_units: int, rows_per_unit: int, gamma: torch.Te
     return out
 
 
-def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
-              rowbias: Optional[torch.Tensor] = None, rb_div: int = 1, rb_mod: int = 1,
+def layernorm(x: torch.Tensor, gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None,
+              eps: float = 1e-5, rowbias: Optional[torch.Tensor] = None, rb_div: int = 1, rb_mod: int = 1,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _req(x, BF16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    """LayerNorm over rows; gamma/beta None = normalisation only (affine folded into the consumer)."""
+    _req(x, BF16, "x")
+    if gamma is not None:
+        _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
     M, Cc = x.shape
     assert x.stride(1) == 1
     if out is None:
@@ -202,7 +205,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     if rowbias is not None:
         _req(rowbias, torch.float32, "rowbias")
     tok = _prof("layernorm", (M, Cc))
-    check(lib().ctrlv_layernorm(x.data_ptr(), x.stride(0), M, Cc, gamma.data_ptr(), beta.data_ptr(), eps,
+    check(lib().ctrlv_layernorm(x.data_ptr(), x.stride(0), M, Cc, _p(gamma), _p(beta), eps,
                                 _p(rowbias), rowbias.stride(0) if rowbias is not None else 0, rb_div,
                                 rb_mod, out.data_ptr(), _stream()), "ctrlv_layernorm")
     _prof_end(tok)

@@ -138,7 +138,8 @@ int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, int32_t C1, 
 
 /* nn.LayerNorm(C, eps) over rows, with an optional fp32 row-bias added first
  * (x + rowbias[(m / rb_div) % rb_mod]): the frame-position embedding of
- * TransformerSpatioTemporalModel. */
+ * TransformerSpatioTemporalModel.  gamma == beta == NULL: plain normalisation (the affine part
+ * folded into the weights of the Linear that consumes the result). */
 int ctrlv_layernorm(const void* x, int64_t ldx, int32_t M, int32_t C, const float* gamma,
                     const float* beta, float eps, const float* rowbias, int32_t ld_rowbias,
                     int32_t rb_div, int32_t rb_mod, void* out, void* stream);

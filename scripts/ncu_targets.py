@@ -21,3 +21,10 @@ elif which == "attn":
     for _ in range(3): ops.attn_spatial(qkv, 28, 2560, 5)
     torch.cuda.synchronize()
 print("ok")
+if which == "norms":
+    x = torch.randn(71680, 320, device=dev).to(BF); g = torch.randn(320, device=dev); b = torch.randn(320, device=dev); o = torch.empty_like(x)
+    for _ in range(2):
+        ops.groupnorm(x, 28, 2560, g, b, 1e-5, True, out=o)
+        ops.groupnorm(x, 2, 35840, g, b, 1e-5, True, out=o)
+        ops.layernorm(x, g, b, out=o)
+    torch.cuda.synchronize()
