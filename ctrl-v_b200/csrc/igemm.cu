@@ -27,6 +27,10 @@ constexpr int kMaxStages = 8;
 constexpr int kEpiWarps = 12;  // 3 per TMEM lane quarter; chunk c of a tile goes to group c % 3
 constexpr int kThreads = 64 + kEpiWarps * 32;
 
+// developer trace: clock64 stamps of CTA 0 (8 slots per tile), read back with ctrlv_debug_trace_read
+__device__ long long g_trace[8 * 64];
+#define TRACE(it, k) do { if (p.trace && blockIdx.x == 0 && (it) < 64) g_trace[(it) * 8 + (k)] = clock64(); } while (0)
+
 struct IgemmSeg {
   int map, c0, nchunk, dx, dy, dz;
 };
@@ -39,6 +43,12 @@ struct IgemmParams {
   int X, Y, Z, bx, by, bz;
   int tiles_x, tiles_y, tiles_z, tiles_n, tiles_total;
   int BN, N, stages, a_bytes, stage_bytes, tmem_cols;
+  int cg;  // 1 or 2 CTAs per tile (tcgen05 cta_group)
+  int bres;       // 1: weight-stationary — the CTA's whole B tile (all K) stays resident in smem
+  int bres_off;   // byte offset of the resident B region (after the A ring)
+  int m_tiles;    // tiles_x * tiles_y * tiles_z
+  int trace;
+  int dbg;  // developer experiments: bit0 skip MMA issue, bit1 skip TMA loads
   ctrlv_epilogue ep;
 };
 
@@ -52,7 +62,7 @@ __device__ __forceinline__ int rowbias_index(const ctrlv_epilogue& ep, int m) {
 // residual rows of one chunk, fetched BEFORE the TMEM load so their latency overlaps it
 template <int NV>
 struct ResPrefetch {
-  uint4 r1[NV / 8], r2[NV / 8];
+  uint4 r1[NV / 8];  // res2 (only the AlphaBlender epilogue has one) is loaded late, in ep_finish
   bool full;
   __device__ __forceinline__ void issue(const ctrlv_epilogue& ep, long long m, int o0, int n_store, bool live) {
     full = (o0 + NV <= n_store);
@@ -61,11 +71,6 @@ struct ResPrefetch {
         const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res1) + (size_t)m * ep.ld_res1 + o0);
 #pragma unroll
         for (int j = 0; j < NV / 8; ++j) r1[j] = __ldg(rp + j);
-      }
-      if (ep.res2) {
-        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res2) + (size_t)m * ep.ld_res2 + o0);
-#pragma unroll
-        for (int j = 0; j < NV / 8; ++j) r2[j] = __ldg(rp + j);
       }
     }
   }
@@ -92,8 +97,9 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
       for (int j = 0; j < NV / 8; ++j) add_bf16x8(v + 8 * j, pf.r1[j], ep.s_res1);
     }
     if (ep.res2) {
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res2) + (size_t)m * ep.ld_res2 + o0);
 #pragma unroll
-      for (int j = 0; j < NV / 8; ++j) add_bf16x8(v + 8 * j, pf.r2[j], ep.s_res2);
+      for (int j = 0; j < NV / 8; ++j) add_bf16x8(v + 8 * j, __ldg(rp + j), ep.s_res2);
     }
     if (ep.out) {
       uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)m * ep.ld_out + o0);
@@ -133,10 +139,9 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
 // one 32-column accumulator chunk of one row: prefetch residuals, TMEM load, bias, (GEGLU), store
 template <bool GEGLU>
 __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t taddr, long long m, int n0,
-                                         int n_store, bool live, const float* sb, const float* rb) {
+                                         int n_store, bool live, const float* sb, const float* rb,
+                                         const ResPrefetch<GEGLU ? 16 : 32>& pf) {
   constexpr int NV = GEGLU ? 16 : 32;
-  ResPrefetch<NV> pf;
-  pf.issue(ep, m, GEGLU ? (n0 >> 1) : n0, n_store, live);
   uint32_t raw[32];
   tmem_ld32(taddr, raw);
   tmem_ld_wait();
@@ -165,12 +170,48 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
   ep_finish<NV>(v, ep, m, GEGLU ? (n0 >> 1) : n0, n_store, pf);
 }
 
+// All 32-column chunks of one accumulator row owned by this warp (c = sub, sub + G, sub + 2G, G = 3
+// chunk groups, at most 3 chunks for BN <= 256).  Residual rows are fetched one chunk AHEAD — the
+// first one before the accumulator is even ready — so their HBM latency overlaps the MMA wait and
+// the previous chunk's math instead of sitting on the critical path.
+template <bool GEGLU>
+__device__ __forceinline__ void ep_tile(const ctrlv_epilogue& ep, uint64_t* tfull, uint32_t tphase, uint32_t t_row,
+                                        long long m, int n_base, int N, int BN, int n_store, bool valid, int sub,
+                                        const float* sbias, const float* rb) {
+  constexpr int NV = GEGLU ? 16 : 32;
+  constexpr int G = kEpiWarps / 4;
+  const int nch = BN / 32;
+  const int c0 = sub, c1 = sub + G, c2 = sub + 2 * G;
+  ResPrefetch<NV> pa, pb;
+  auto o_of = [&](int c) { return GEGLU ? ((n_base + c * 32) >> 1) : (n_base + c * 32); };
+  auto live_of = [&](int c) { return valid && (n_base + c * 32) < N; };
+  if (c0 < nch) pa.issue(ep, m, o_of(c0), n_store, live_of(c0));
+  mbar_wait(tfull, tphase);
+  tc_fence_after();
+  if (c0 >= nch) return;
+  if (c1 < nch) pb.issue(ep, m, o_of(c1), n_store, live_of(c1));
+  __syncwarp();
+  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c0 * 32), m, n_base + c0 * 32, n_store, live_of(c0), sbias + c0 * 32, rb, pa);
+  if (c1 >= nch) return;
+  if (c2 < nch) pa.issue(ep, m, o_of(c2), n_store, live_of(c2));
+  __syncwarp();
+  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c1 * 32), m, n_base + c1 * 32, n_store, live_of(c1), sbias + c1 * 32, rb, pb);
+  if (c2 >= nch) return;
+  __syncwarp();
+  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c2 * 32), m, n_base + c2 * 32, n_store, live_of(c2), sbias + c2 * 32, rb, pa);
+}
+
+// CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) shares
+// one 256-row x BN tile: each CTA loads its own 128 A rows and HALF of the B tile, the leader issues
+// M=256 MMAs that read both halves — halves the shared-memory and L2 traffic of the B operand.
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[2][2][256];  // [tile parity][bias | bias + rowbias row 0][col]
 
@@ -187,35 +228,58 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    mbar_init(&bres_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiWarps);
+      mbar_init(&tempty_bar[s], kEpiWarps * CG);  // CG = 2: both CTAs' epilogue warps free the leader's buffer
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_base_smem, (uint32_t)p.tmem_cols);
+    if (CG == 1) tmem_alloc(&tmem_base_smem, (uint32_t)p.tmem_cols);
+    else tmem_alloc_cg2(&tmem_base_smem, (uint32_t)p.tmem_cols);
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;
 
-  const int nloc = (p.tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // work unit: (super-tile of CG consecutive m-tiles, n-tile); units are dealt round-robin to
+  // clusters; inside a pair CTA r owns m-tile CG*super + r
+  // Weight-stationary mode (small K): CTA c keeps n-tile c % tiles_n for its whole life and walks
+  // the m-tiles c / tiles_n, + grid / tiles_n, ...; concurrent CTAs still share A tiles through L2.
+  int unit0 = (int)blockIdx.x / CG;
+  int nunits = (int)gridDim.x / CG;
+  int nloc = (p.tiles_total - unit0 + nunits - 1) / nunits;
+  const int bres_nt = (int)blockIdx.x % p.tiles_n;
+  if (CG == 1 && p.bres) {
+    const int per_n = (int)gridDim.x / p.tiles_n;  // host makes the grid a multiple of tiles_n
+    const int first = (int)blockIdx.x / p.tiles_n;
+    nloc = first < p.m_tiles ? (p.m_tiles - first + per_n - 1) / per_n : 0;
+    unit0 = first * p.tiles_n + bres_nt;   // so that tile = unit0 + it * nunits decodes as usual
+    nunits = per_n * p.tiles_n;
+  }
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    {  // warp-uniform loop, one elected lane issues (see the MMA issuer below)
       int stage = 0;
       uint32_t phase = 0;
+      if (CG == 1 && p.bres && nloc > 0 && elect_one()) {  // the whole [BN x K] weight tile, once
+        mbar_expect_tx(&bres_bar, (uint32_t)(p.kblocks * p.BN * kBK * 2));
+        for (int kb = 0; kb < p.kblocks; ++kb)
+          tma_load_2d(smem + p.bres_off + (size_t)kb * p.BN * kBK * 2, &p.tmB, &bres_bar, kb * kBK, bres_nt * p.BN);
+      }
       for (int it = 0; it < nloc; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
+        const int tile = unit0 + it * nunits;
         const int nt = tile % p.tiles_n;
-        int mt = tile / p.tiles_n;
+        int mt = (tile / p.tiles_n) * CG + (int)crank;
         const int tx = mt % p.tiles_x;
         mt /= p.tiles_x;
         const int ty = mt % p.tiles_y;
-        const int tz = mt / p.tiles_y;
+        const int tz = mt / p.tiles_y;  // may run past tiles_z for the odd tail: TMA zero-fills
         const int x0 = tx * p.bx, y0 = ty * p.by, z0 = tz * p.bz;
         int kb = 0;
         for (int s = 0; s < p.nseg; ++s) {
@@ -224,10 +288,23 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
             uint8_t* sb = sa + kBM * kBK * 2;
-            mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + p.BN * kBK * 2));
-            tma_load_4d(sa, &p.tmA[sg.map], &full_bar[stage], sg.c0 + ch * kBK, x0 + sg.dx,
-                        y0 + sg.dy, z0 + sg.dz);
-            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * kBK, nt * p.BN);
+            if (elect_one()) {
+              if (CG == 2) {
+                // both CTAs credit the LEADER's full barrier; the leader expects the pair's bytes
+                const uint32_t lead_bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
+                if (crank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * (p.a_bytes + (p.BN / 2) * kBK * 2)));
+                tma_load_4d_cg2(sa, &p.tmA[sg.map], lead_bar, sg.c0 + ch * kBK, x0 + sg.dx, y0 + sg.dy, z0 + sg.dz);
+                tma_load_2d_cg2(sb, &p.tmB, lead_bar, kb * kBK, nt * p.BN + (int)crank * (p.BN / 2));
+              } else if (p.bres) {
+                mbar_expect_tx(&full_bar[stage], (uint32_t)p.a_bytes);
+                tma_load_4d(sa, &p.tmA[sg.map], &full_bar[stage], sg.c0 + ch * kBK, x0 + sg.dx, y0 + sg.dy, z0 + sg.dz);
+              } else {
+                mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + p.BN * kBK * 2));
+                tma_load_4d(sa, &p.tmA[sg.map], &full_bar[stage], sg.c0 + ch * kBK, x0 + sg.dx, y0 + sg.dy, z0 + sg.dz);
+                tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * kBK, nt * p.BN);
+              }
+            }
+            __syncwarp();
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -238,10 +315,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(kBM, p.BN, 0, 0);
+    if (crank == 0) {
+      // Warp-uniform loop: all lanes wait on the barriers, ONE elected lane issues.  (Issuing from a
+      // `lane == 0` branch makes ptxas wrap every UTCHMMA / UTCBAR in an ELECT..BRA.U.ANY waterfall
+      // loop, which costs more issue time than the MMAs themselves for narrow tiles.)
+      const uint32_t idesc = make_idesc(kBM * CG, p.BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
+      if (CG == 1 && p.bres && nloc > 0) mbar_wait(&bres_bar, 0);
       for (int it = 0; it < nloc; ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -252,22 +333,32 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = sa + kBM * kBK * 2;
+          const uint32_t sb = p.bres ? smem_u32(smem + p.bres_off + (size_t)kb * p.BN * kBK * 2) : sa + kBM * kBK * 2;
           const uint64_t da = make_sdesc(sa, 16, 1024);
           const uint64_t db = make_sdesc(sb, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 32 bytes (16 bf16) inside the 128B swizzle atom: +2 in the >>4 address field
-            umma_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                    (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance 32 bytes (16 bf16) inside the 128B swizzle atom: +2 in the >>4 address field
+              if (CG == 1)
+                umma_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+              else
+                umma_ss_cg2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            }
+            if (CG == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_cg2(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[as]);
+        if (elect_one()) {
+          if (CG == 1) umma_commit(&tfull_bar[as]);
+          else umma_commit_cg2(&tfull_bar[as]);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -278,10 +369,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const ctrlv_epilogue& ep = p.ep;
     const int n_out_total = ep.geglu ? p.N / 2 : p.N;
     const int n_store = ep.n_store > 0 ? ep.n_store : n_out_total;
+    const uint32_t tempty_lead0 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
+    const uint32_t tempty_lead1 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u;
     for (int it = 0; it < nloc; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
+      const int tile = unit0 + it * nunits;
       const int nt = tile % p.tiles_n;
-      int mt = tile / p.tiles_n;
+      int mt = (tile / p.tiles_n) * CG + (int)crank;
       const int tx = mt % p.tiles_x;
       mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
@@ -299,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       // Stage this n-tile's bias in shared memory (overlaps the wait for the accumulator).  If every
       // valid row of the tile uses the same rowbias row, that row is folded in as well.
       int my_ridx = 0, ridx0 = 0;
-      if (ep.rb_mode != 0) {
+      if (ep.rb_mode != 0 && tz * p.bz < p.Z) {  // (the odd tail tile of a CTA pair has no rows)
         const long long m0 = ((long long)(tz * p.bz) * p.Y + ty * p.by) * p.X + tx * p.bx;
         ridx0 = rowbias_index(ep, (int)m0);
         my_ridx = valid ? rowbias_index(ep, (int)m) : ridx0;
@@ -324,29 +417,28 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       if (ep.rb_mode != 0 && valid && !uniform)
         rb = ep.rowbias + (size_t)my_ridx * ep.ld_rowbias;
 
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
-      for (int c = sub; c < p.BN / 32; c += kEpiWarps / 4) {
-        __syncwarp();
-        const int n0 = nt * p.BN + c * 32;  // first GEMM column of this chunk
-        const bool live = valid && n0 < p.N;
-        if (ep.geglu) ep_chunk<true>(ep, t_row + (uint32_t)(c * 32), m, n0, n_store, live, sbias + c * 32, rb);
-        else ep_chunk<false>(ep, t_row + (uint32_t)(c * 32), m, n0, n_store, live, sbias + c * 32, rb);
-      }
+      if (ep.geglu)
+        ep_tile<true>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, rb);
+      else
+        ep_tile<false>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, rb);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(&tempty_bar[as]);
+        else mbar_arrive_cluster(as ? tempty_lead1 : tempty_lead0);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer may still read our smem / arrive on our barriers
   tc_fence_after();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (CG == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc_cg2(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -364,9 +456,10 @@ static int device_props() {
   CTRLV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CTRLV_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   cudaFuncAttributes fa;
-  CTRLV_CUDA(cudaFuncGetAttributes(&fa, igemm_kernel));
+  CTRLV_CUDA(cudaFuncGetAttributes(&fa, igemm_kernel<1>));
   smem -= (int)fa.sharedSizeBytes;  // static shared memory (barriers) counts against the limit
-  CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   g_max_smem = smem;
   g_num_sms = sms;
   return CTRLV_OK;
@@ -429,17 +522,6 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   p.tiles_x = (d->X + p.bx - 1) / p.bx;
   p.tiles_y = (d->Y + p.by - 1) / p.by;
   p.tiles_z = (d->Z + p.bz - 1) / p.bz;
-  p.N = d->N;
-  p.BN = d->bn > 0 ? d->bn : choose_bn(d->N, (long long)p.tiles_x * p.tiles_y * p.tiles_z, g_num_sms);
-  if (const char* e = getenv("CTRLV_DEBUG_BN")) p.BN = atoi(e);  // developer override
-  if (p.BN == 0) {
-    // ragged N: largest 32-multiple tile, TMA zero-fills the weight rows past N
-    p.BN = d->N >= 256 ? 256 : ((d->N + 31) / 32) * 32;
-  }
-  CTRLV_CHECK_ARG(p.BN % 32 == 0 && p.BN >= 32 && p.BN <= 256, "igemm: bad n-tile %d", p.BN);
-  p.tiles_n = (d->N + p.BN - 1) / p.BN;
-  p.tiles_total = p.tiles_x * p.tiles_y * p.tiles_z * p.tiles_n;
-
   int kblocks = 0;
   for (int s = 0; s < d->nseg; ++s) {
     const ctrlv_seg& sg = d->seg[s];
@@ -454,6 +536,46 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   CTRLV_CHECK_ARG(kblocks * 64 == d->K, "igemm: K=%d does not match segments (%d)", d->K, kblocks * 64);
   p.nseg = d->nseg;
   p.kblocks = kblocks;
+  const int kblocks_pre = kblocks;
+  p.N = d->N;
+  p.BN = d->bn > 0 ? d->bn : choose_bn(d->N, (long long)p.tiles_x * p.tiles_y * p.tiles_z, g_num_sms);
+  if (const char* e = getenv("CTRLV_DEBUG_BN")) p.BN = atoi(e);  // developer override
+  if (p.BN == 0) {
+    // ragged N: largest 32-multiple tile, TMA zero-fills the weight rows past N
+    p.BN = d->N >= 256 ? 256 : ((d->N + 31) / 32) * 32;
+  }
+  // weight-stationary candidates (short K, many m-tiles): the widest n-tile whose whole [BN x K]
+  // weight slab plus >= 5 A stages fits in shared memory
+  int bres_bn = 0;
+  {
+    const long long room_total = (long long)g_max_smem - 2048;
+    const long long m_tiles_pre = (long long)p.tiles_x * p.tiles_y * p.tiles_z;
+    // (measured neutral on B200 for this path's shapes — the short-K GEMMs are bound by the MMA
+    //  issue/epilogue chain, not by weight re-fetch — so it is opt-in: CTRLV_BRES=1)
+    bool want = kblocks <= 10 && m_tiles_pre >= 2LL * g_num_sms && d->bn == 0 && !getenv("CTRLV_DEBUG_BN");
+    {
+      const char* e = getenv("CTRLV_BRES");
+      want = want && e != nullptr && atoi(e) != 0;
+    }
+    if (want) {
+      const int cands[] = {256, 192, 160, 128, 96};
+      for (int bn : cands) {
+        if (d->N % bn != 0 || g_num_sms / (d->N / bn) < 1) continue;
+        if ((long long)kblocks * bn * kBK * 2 + 5LL * kBM * kBK * 2 <= room_total) { bres_bn = bn; break; }
+      }
+    }
+    if (bres_bn) p.BN = bres_bn;
+  }
+  CTRLV_CHECK_ARG(p.BN % 32 == 0 && p.BN >= 32 && p.BN <= 256, "igemm: bad n-tile %d", p.BN);
+  p.tiles_n = (d->N + p.BN - 1) / p.BN;
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_z;
+  // CTA pairs (cta_group::2) whenever there are at least two m-tiles and the n-tile splits in two
+  // CTA pairs (cta_group::2) pay off only for long K loops with plenty of tiles; short-K problems are
+  // epilogue / L2 bound and run better as independent CTAs (measured, profiles/r01_cg2_vs_cg1.txt)
+  p.cg = (tiles_m >= 2 && kblocks_pre >= 30 && p.BN % 32 == 0 && d->N % p.BN == 0) ? 2 : 1;
+  if (const char* e = getenv("CTRLV_DEBUG_CG")) p.cg = atoi(e);  // developer override
+  p.tiles_total = ((tiles_m + p.cg - 1) / p.cg) * p.tiles_n;
+
 
   for (int i = 0; i < d->nsrc; ++i) {
     const ctrlv_src& s = d->src[i];
@@ -470,13 +592,24 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   {
     uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
     uint64_t strides[1] = {(uint64_t)d->K * 2};
-    uint32_t box[2] = {64, (uint32_t)p.BN};
+    uint32_t box[2] = {64, (uint32_t)(p.BN / p.cg)};
     rc = encode_tmap_bf16(&p.tmB, d->W, 2, dims, strides, box, true);
     if (rc) return rc;
   }
   p.a_bytes = 64 * p.bx * p.by * p.bz * 2;
-  p.stage_bytes = kBM * kBK * 2 + p.BN * kBK * 2;
-  int stages = (g_max_smem - 2048) / p.stage_bytes;
+  p.stage_bytes = kBM * kBK * 2 + (p.BN / p.cg) * kBK * 2;
+  p.m_tiles = tiles_m;
+  p.trace = getenv("CTRLV_DEBUG_TRACE") ? 1 : 0;
+  if (const char* e = getenv("CTRLV_DEBUG_DBG")) p.dbg = atoi(e);
+  if (bres_bn && p.cg == 1) {
+    const long long room = (long long)g_max_smem - 2048 - (long long)kblocks * p.BN * kBK * 2;
+    p.bres = 1;
+    p.stage_bytes = kBM * kBK * 2;
+    int st = (int)(room / p.stage_bytes);
+    if (st > kMaxStages) st = kMaxStages;
+    p.bres_off = st * p.stage_bytes;
+  }
+  int stages = p.bres ? p.bres_off / p.stage_bytes : (g_max_smem - 2048) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (const char* e = getenv("CTRLV_DEBUG_STAGES")) stages = atoi(e);  // developer override
   CTRLV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for 2 stages");
@@ -500,16 +633,41 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
     if (p.ep.out_f32) CTRLV_CHECK_ARG(p.ep.ld_out_f32 % 4 == 0, "igemm: out_f32 ld %% 4");
   }
 
-  const int grid = p.tiles_total < g_num_sms ? p.tiles_total : g_num_sms;
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  igemm_kernel<<<grid, kThreads, smem, stream>>>(p);
-  CTRLV_CUDA(cudaGetLastError());
+  size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  if (p.bres) smem = (size_t)p.bres_off + (size_t)p.kblocks * p.BN * kBK * 2 + 1024;
+  if (p.cg == 1) {
+    int grid = p.tiles_total < g_num_sms ? p.tiles_total : g_num_sms;
+    if (p.bres) grid = (g_num_sms / p.tiles_n) * p.tiles_n;
+    igemm_kernel<1><<<grid, kThreads, smem, stream>>>(p);
+    CTRLV_CUDA(cudaGetLastError());
+  } else {
+    const int pairs = p.tiles_total < g_num_sms / 2 ? p.tiles_total : g_num_sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    CTRLV_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<2>, p));
+  }
   return CTRLV_OK;
 }
 
 }  // namespace ctrlv
 
 using namespace ctrlv;
+
+// developer hook (not part of the public header): copy the trace stamps of the last traced launch
+extern "C" int ctrlv_debug_trace_read(long long* out, int n) {
+  CTRLV_CUDA(cudaDeviceSynchronize());
+  CTRLV_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * (n < 8 * 64 ? n : 8 * 64)));
+  return CTRLV_OK;
+}
 
 extern "C" int ctrlv_igemm(const ctrlv_igemm_desc* desc, void* stream) {
   return igemm_launch(desc, reinterpret_cast<cudaStream_t>(stream));
