@@ -60,17 +60,57 @@ __device__ __forceinline__ int rowbias_index(const ctrlv_epilogue& ep, int m) {
 }
 
 // residual rows of one chunk, fetched BEFORE the TMEM load so their latency overlaps it
+// ---- epilogue data movement -------------------------------------------------------------------
+// A thread owns one accumulator ROW, so its natural global accesses are 32 scattered 16-byte pieces
+// per warp instruction — the LSU, not HBM, becomes the limit for short-K GEMMs.  Every bf16
+// residual read / output write is therefore transposed through a 2 KB warp-private smem tile so that
+// a warp instruction touches whole 64-byte row segments (CPR lanes per row): 4x fewer LSU
+// transactions, no cross-warp synchronisation.
+template <int NV>
+struct EpRows {  // per (tile, warp): the rows this lane touches in the transposed (coalesced) mapping
+  static constexpr int CPR = NV / 8;    // 16-byte pieces per row of one chunk
+  static constexpr int RPI = 32 / CPR;  // rows covered by one warp-wide 16-byte access
+  int mT[CPR];
+  bool vT[CPR];
+  __device__ __forceinline__ void init(long long m, bool valid) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < CPR; ++i) {
+      const int r = lane / CPR + RPI * i;
+      mT[i] = __shfl_sync(0xffffffffu, (int)m, r);
+      vT[i] = __shfl_sync(0xffffffffu, (int)valid, r) != 0;
+    }
+  }
+  // 16-byte slot of (row, piece) in the warp tile, XOR-swizzled so that both the row-owner access
+  // (lane = row) and the transposed access (CPR lanes per row) are bank-conflict free
+  static __device__ __forceinline__ int slot(int row, int piece) {
+    return row * CPR + (CPR == 4 ? (piece ^ ((row >> 1) & 3)) : (piece ^ ((row >> 2) & 1)));
+  }
+};
+
 template <int NV>
 struct ResPrefetch {
-  uint4 r1[NV / 8];  // res2 (only the AlphaBlender epilogue has one) is loaded late, in ep_finish
-  bool full;
-  __device__ __forceinline__ void issue(const ctrlv_epilogue& ep, long long m, int o0, int n_store, bool live) {
-    full = (o0 + NV <= n_store);
-    if (live && full) {
-      if (ep.res1) {
-        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res1) + (size_t)m * ep.ld_res1 + o0);
+  static constexpr int CPR = NV / 8;
+  uint4 r1[CPR];  // transposed mapping: piece (lane % CPR) of rows lane / CPR + RPI * i
+  float bv;       // lane j: bias[n0 + j] (+ the warp-uniform rowbias row), redistributed through smem
+  bool full;      // warp-uniform: the whole chunk lies inside the stored columns
+  __device__ __forceinline__ void issue(const ctrlv_epilogue& ep, const EpRows<NV>& rows, int o0, int n_store,
+                                        int n0, int N, const float* rb_uniform) {
+    const int lane = threadIdx.x & 31;
+    const int nl = n0 + lane;
+    bv = 0.f;
+    if (nl < N) {
+      if (ep.bias) bv = __ldg(ep.bias + nl);
+      if (rb_uniform) bv += __ldg(rb_uniform + nl);
+    }
+    full = (o0 + NV <= n_store) && (n0 < N);
+    if (full && ep.res1) {
 #pragma unroll
-        for (int j = 0; j < NV / 8; ++j) r1[j] = __ldg(rp + j);
+      for (int i = 0; i < CPR; ++i) {
+        r1[i] = make_uint4(0, 0, 0, 0);
+        if (rows.vT[i])
+          r1[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res1) +
+                                                       (size_t)rows.mT[i] * ep.ld_res1 + o0 + (lane % CPR) * 8));
       }
     }
   }
@@ -84,41 +124,66 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u, float s) {
   f = unpack_bf16x2(u.w); v[6] += s * f.x; v[7] += s * f.y;
 }
 
-// scale, add residual streams, convert and store NV consecutive outputs of row m starting at
-// output column o0 (all loops compile-time so v[] stays in registers)
+// scale, add residual streams, convert and store NV consecutive outputs of row m starting at output
+// column o0.  Executed by ALL lanes of the warp (the smem transposes are warp-collective).
 template <int NV>
-__device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, long long m, int o0,
-                                          int n_store, const ResPrefetch<NV>& pf) {
+__device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, long long m, bool valid, int o0,
+                                          int n_store, const ResPrefetch<NV>& pf, const EpRows<NV>& rows,
+                                          uint4* wst) {
+  constexpr int CPR = NV / 8;
+  constexpr int RPI = 32 / CPR;
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < NV; ++j) v[j] *= ep.s_acc;
   if (pf.full) {
     if (ep.res1) {
+      __syncwarp();
 #pragma unroll
-      for (int j = 0; j < NV / 8; ++j) add_bf16x8(v + 8 * j, pf.r1[j], ep.s_res1);
+      for (int i = 0; i < CPR; ++i) wst[EpRows<NV>::slot(lane / CPR + RPI * i, lane % CPR)] = pf.r1[i];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < CPR; ++j) add_bf16x8(v + 8 * j, wst[EpRows<NV>::slot(lane, j)], ep.s_res1);
     }
-    if (ep.res2) {
+    if (ep.res2 && valid) {
       const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res2) + (size_t)m * ep.ld_res2 + o0);
 #pragma unroll
-      for (int j = 0; j < NV / 8; ++j) add_bf16x8(v + 8 * j, __ldg(rp + j), ep.s_res2);
+      for (int j = 0; j < CPR; ++j) add_bf16x8(v + 8 * j, __ldg(rp + j), ep.s_res2);
     }
-    if (ep.out) {
-      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)m * ep.ld_out + o0);
+    if (ep.out && NV == 16) {
+      // GEGLU chunks yield only 32 B per row: the transpose does not pay (measured), store directly
+      if (valid) {
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)m * ep.ld_out + o0);
 #pragma unroll
-      for (int j = 0; j < NV; j += 8) {
+        for (int j = 0; j < CPR; ++j)
+          op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+      }
+    } else if (ep.out) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < CPR; ++j) {
         uint4 u;
-        u.x = pack_bf16x2(v[j], v[j + 1]);
-        u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        u.z = pack_bf16x2(v[j + 4], v[j + 5]);
-        u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        op[j >> 3] = u;
+        u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+        u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        wst[EpRows<NV>::slot(lane, j)] = u;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < CPR; ++i) {
+        const uint4 u = wst[EpRows<NV>::slot(lane / CPR + RPI * i, lane % CPR)];
+        if (rows.vT[i])
+          *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)rows.mT[i] * ep.ld_out + o0 +
+                                    (lane % CPR) * 8) = u;
       }
     }
-    if (ep.out_f32) {
+    if (ep.out_f32 && valid) {
       float4* op = reinterpret_cast<float4*>(ep.out_f32 + (size_t)m * ep.ld_out_f32 + o0);
 #pragma unroll
       for (int j = 0; j < NV; j += 4) op[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
-  } else {
+  } else if (valid) {
     // ragged tail of a padded-N problem (e.g. conv_out with 4 real channels): scalar, predicated
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -136,27 +201,29 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
   }
 }
 
-// one 32-column accumulator chunk of one row: prefetch residuals, TMEM load, bias, (GEGLU), store
+// one 32-column accumulator chunk of one row: TMEM load, bias, (GEGLU), residual, store
 template <bool GEGLU>
-__device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t taddr, long long m, int n0,
-                                         int n_store, bool live, const float* sb, const float* rb,
-                                         const ResPrefetch<GEGLU ? 16 : 32>& pf) {
+__device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t taddr, long long m, bool valid, int n0,
+                                         int n_store, float* sb, uint4* wst, const float* rb,
+                                         const ResPrefetch<GEGLU ? 16 : 32>& pf,
+                                         const EpRows<GEGLU ? 16 : 32>& rows) {
   constexpr int NV = GEGLU ? 16 : 32;
   uint32_t raw[32];
   tmem_ld32(taddr, raw);
+  // bias (+ warp-uniform rowbias): lane j fetched column j; broadcast through this warp's smem row
+  __syncwarp();  // previous chunk's readers are done with the row
+  sb[threadIdx.x & 31] = pf.bv;
+  __syncwarp();
   tmem_ld_wait();
-  if (!live) return;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-  {  // bias (+ tile-uniform rowbias) staged in shared memory by the epilogue warps
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(sb + j);
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-    }
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + j);
+    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
   }
-  if (rb) {
+  if (rb) {  // (nullptr for rows outside the problem)
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(rb + n0 + j));
@@ -167,7 +234,7 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = geglu_f(v[2 * j], v[2 * j + 1]);
   }
-  ep_finish<NV>(v, ep, m, GEGLU ? (n0 >> 1) : n0, n_store, pf);
+  ep_finish<NV>(v, ep, m, valid, GEGLU ? (n0 >> 1) : n0, n_store, pf, rows, wst);
 }
 
 // All 32-column chunks of one accumulator row owned by this warp (c = sub, sub + G, sub + 2G, G = 3
@@ -177,28 +244,29 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
 template <bool GEGLU>
 __device__ __forceinline__ void ep_tile(const ctrlv_epilogue& ep, uint64_t* tfull, uint32_t tphase, uint32_t t_row,
                                         long long m, int n_base, int N, int BN, int n_store, bool valid, int sub,
-                                        const float* sbias, const float* rb) {
+                                        float* sbias, uint4* wst, const float* rb, const float* rb_uniform) {
   constexpr int NV = GEGLU ? 16 : 32;
   constexpr int G = kEpiWarps / 4;
   const int nch = BN / 32;
   const int c0 = sub, c1 = sub + G, c2 = sub + 2 * G;
+  EpRows<NV> rows;
+  rows.init(m, valid);
   ResPrefetch<NV> pa, pb;
   auto o_of = [&](int c) { return GEGLU ? ((n_base + c * 32) >> 1) : (n_base + c * 32); };
-  auto live_of = [&](int c) { return valid && (n_base + c * 32) < N; };
-  if (c0 < nch) pa.issue(ep, m, o_of(c0), n_store, live_of(c0));
+  if (c0 < nch) pa.issue(ep, rows, o_of(c0), n_store, n_base + c0 * 32, N, rb_uniform);
   mbar_wait(tfull, tphase);
   tc_fence_after();
   if (c0 >= nch) return;
-  if (c1 < nch) pb.issue(ep, m, o_of(c1), n_store, live_of(c1));
+  if (c1 < nch) pb.issue(ep, rows, o_of(c1), n_store, n_base + c1 * 32, N, rb_uniform);
   __syncwarp();
-  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c0 * 32), m, n_base + c0 * 32, n_store, live_of(c0), sbias + c0 * 32, rb, pa);
+  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c0 * 32), m, valid, n_base + c0 * 32, n_store, sbias, wst, rb, pa, rows);
   if (c1 >= nch) return;
-  if (c2 < nch) pa.issue(ep, m, o_of(c2), n_store, live_of(c2));
+  if (c2 < nch) pa.issue(ep, rows, o_of(c2), n_store, n_base + c2 * 32, N, rb_uniform);
   __syncwarp();
-  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c1 * 32), m, n_base + c1 * 32, n_store, live_of(c1), sbias + c1 * 32, rb, pb);
+  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c1 * 32), m, valid, n_base + c1 * 32, n_store, sbias, wst, rb, pb, rows);
   if (c2 >= nch) return;
   __syncwarp();
-  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c2 * 32), m, n_base + c2 * 32, n_store, live_of(c2), sbias + c2 * 32, rb, pa);
+  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c2 * 32), m, valid, n_base + c2 * 32, n_store, sbias, wst, rb, pa, rows);
 }
 
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) shares
@@ -213,7 +281,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float bias_s[2][2][256];  // [tile parity][bias | bias + rowbias row 0][col]
+  __shared__ __align__(16) float wbias[kEpiWarps][32];   // per-warp broadcast row for the bias chunk
+  __shared__ __align__(16) uint4 wstage[kEpiWarps][128];  // per-warp 32 x 64 B transpose tile
 
   // 1024-byte aligned tile ring
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -389,39 +458,26 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
-      // Stage this n-tile's bias in shared memory (overlaps the wait for the accumulator).  If every
-      // valid row of the tile uses the same rowbias row, that row is folded in as well.
-      int my_ridx = 0, ridx0 = 0;
-      if (ep.rb_mode != 0 && tz * p.bz < p.Z) {  // (the odd tail tile of a CTA pair has no rows)
-        const long long m0 = ((long long)(tz * p.bz) * p.Y + ty * p.by) * p.X + tx * p.bx;
-        ridx0 = rowbias_index(ep, (int)m0);
-        my_ridx = valid ? rowbias_index(ep, (int)m) : ridx0;
-      }
-      {
-        const int et = (int)threadIdx.x - 64;
-        if (et < p.BN) {
-          const int n = nt * p.BN + et;
-          float b = 0.f, b2 = 0.f;
-          if (n < p.N) {
-            if (ep.bias) b = __ldg(ep.bias + n);
-            b2 = b;
-            if (ep.rb_mode != 0) b2 += __ldg(ep.rowbias + (size_t)ridx0 * ep.ld_rowbias + n);
-          }
-          bias_s[as][0][et] = b;
-          bias_s[as][1][et] = b2;
-        }
-      }
-      const bool uniform = bar_red_and(1, kEpiWarps * 32, my_ridx == ridx0);
-      const float* sbias = uniform ? bias_s[as][1] : bias_s[as][0];
+      // rowbias: if every valid row of this warp uses the same table row it is folded into the bias
+      // fetch (one value per lane); otherwise each thread reads its own row in ep_chunk
       const float* rb = nullptr;
-      if (ep.rb_mode != 0 && valid && !uniform)
-        rb = ep.rowbias + (size_t)my_ridx * ep.ld_rowbias;
-
+      const float* rb_uniform = nullptr;
+      if (ep.rb_mode != 0) {
+        const int my_ridx = valid ? rowbias_index(ep, (int)m) : -1;
+        int ref = my_ridx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ref = max(ref, __shfl_xor_sync(0xffffffffu, ref, o));
+        const bool uni = __all_sync(0xffffffffu, my_ridx < 0 || my_ridx == ref);
+        if (uni && ref >= 0) rb_uniform = ep.rowbias + (size_t)ref * ep.ld_rowbias;
+        else if (valid) rb = ep.rowbias + (size_t)my_ridx * ep.ld_rowbias;
+      }
+      float* sbias = wbias[warp - 2];
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
+      uint4* wst = wstage[warp - 2];
       if (ep.geglu)
-        ep_tile<true>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, rb);
+        ep_tile<true>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
       else
-        ep_tile<false>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, rb);
+        ep_tile<false>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
