@@ -625,10 +625,12 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   CTRLV_CHECK_ARG(p.BN % 32 == 0 && p.BN >= 32 && p.BN <= 256, "igemm: bad n-tile %d", p.BN);
   p.tiles_n = (d->N + p.BN - 1) / p.BN;
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_z;
-  // CTA pairs (cta_group::2) whenever there are at least two m-tiles and the n-tile splits in two
-  // CTA pairs (cta_group::2) pay off only for long K loops with plenty of tiles; short-K problems are
-  // epilogue / L2 bound and run better as independent CTAs (measured, profiles/r01_cg2_vs_cg1.txt)
-  p.cg = (tiles_m >= 2 && kblocks_pre >= 30 && p.BN % 32 == 0 && d->N % p.BN == 0) ? 2 : 1;
+  // CTA pairs (cta_group::2): a single CTA's 128 x 256 tile is shared-memory-bandwidth bound
+  // (TMA writes + MMA reads ~ 96 KB per k-block); a pair halves the B traffic and deepens the TMA
+  // ring.  Measured on this path's shapes (profiles/r01_cg2_vs_cg1.txt): +15-19 % on the 3x3 convs,
+  // a win for K >= 1280 and for wide-N K = 640, a loss for K = 320 and tiny M.
+  p.cg = (tiles_m >= 16 && p.BN % 32 == 0 && d->N % p.BN == 0 &&
+          (kblocks_pre >= 20 || (kblocks_pre >= 10 && d->N >= 2560))) ? 2 : 1;
   if (const char* e = getenv("CTRLV_DEBUG_CG")) p.cg = atoi(e);  // developer override
   p.tiles_total = ((tiles_m + p.cg - 1) / p.cg) * p.tiles_n;
 
