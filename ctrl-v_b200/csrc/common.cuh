@@ -395,6 +395,58 @@ __device__ __forceinline__ float geglu_f(float h, float g) {
   return (0.5f * h) * fmaf(ax, r, g);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return geglu_f(1.0f, x); }
+
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2: two fp32 lanes per instruction) -------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_splat(float x) { return f2_pack(x, x); }
+
+// two GEGLU outputs at once: (h0*gelu(g0), h1*gelu(g1)); same A&S 7.1.26 erf as geglu_f, polynomial
+// evaluated with packed fp32x2 instructions (half the FP32 issue slots), MUFU rcp/ex2 stay scalar
+__device__ __forceinline__ void geglu2_f(float h0, float g0, float h1, float g1, float& o0, float& o1) {
+  const uint64_t g = f2_pack(g0, g1);
+  const uint64_t ax = g & 0x7fffffff7fffffffull;
+  const uint64_t zs = f2_mul(ax, f2_splat(0.8493218002880191f));
+  const uint64_t nzs = f2_mul(ax, f2_splat(-0.8493218002880191f));
+  const uint64_t d = f2_fma(zs, f2_splat(0.2727374808792225f), f2_splat(1.0f));
+  float d0, d1;
+  f2_unpack(d, d0, d1);
+  const uint64_t t = f2_pack(rcp_approx(d0), rcp_approx(d1));
+  // q = -(a1 t + a2 t^2 + ... + a5 t^5)
+  uint64_t q = f2_fma(t, f2_splat(-1.061405429f), f2_splat(1.453152027f));
+  q = f2_fma(t, q, f2_splat(-1.421413741f));
+  q = f2_fma(t, q, f2_splat(0.284496736f));
+  q = f2_fma(t, q, f2_splat(-0.254829592f));
+  q = f2_mul(q, t);
+  float e0, e1;
+  f2_unpack(f2_mul(nzs, zs), e0, e1);
+  const uint64_t e = f2_pack(ex2_approx(e0), ex2_approx(e1));
+  const uint64_t r = f2_fma(q, e, f2_splat(1.0f));  // erf(|g|/sqrt2)
+  const uint64_t t2 = f2_fma(ax, r, g);            // g + |g| erf(.)
+  const uint64_t o = f2_mul(f2_mul(f2_pack(h0, h1), f2_splat(0.5f)), t2);
+  f2_unpack(o, o0, o1);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

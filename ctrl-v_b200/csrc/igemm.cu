@@ -232,7 +232,11 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
   }
   if (GEGLU) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = geglu_f(v[2 * j], v[2 * j + 1]);
+    for (int j = 0; j < 16; j += 2) {
+      float o0, o1;
+      geglu2_f(v[2 * j], v[2 * j + 1], v[2 * j + 2], v[2 * j + 3], o0, o1);
+      v[j] = o0; v[j + 1] = o1;
+    }
   }
   ep_finish<NV>(v, ep, m, valid, GEGLU ? (n0 >> 1) : n0, n_store, pf, rows, wst);
 }
