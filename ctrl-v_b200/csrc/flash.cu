@@ -20,7 +20,7 @@
 
 namespace ctrlv {
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 64 + 256;  // TMA warp, MMA warp, 8 softmax warps
 constexpr int kTile = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
 
 struct AttnParams {
@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   __shared__ __align__(8) uint64_t q_full, s_full, p_full, o_full;
   __shared__ __align__(8) uint64_t kv_full[3], kv_empty[3];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float xmax[2][2][128];  // [block parity][column half][row]: partial row max exchange
+  __shared__ float xsum[2][128];     // [column half][row]: partial row sums (end of the loop)
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
     tma_prefetch_desc(&p.tm);
     mbar_init(&q_full, 1);
     mbar_init(&s_full, 1);
-    mbar_init(&p_full, 4);
+    mbar_init(&p_full, 8);
     mbar_init(&o_full, 1);
     for (int i = 0; i < 3; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -144,12 +146,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
     }
   } else {
     // ============================ softmax / epilogue ==============================
+    // 8 warps: two per TMEM lane quarter.  Warp (q, half) owns key columns [64*half, 64*half+64) of
+    // its 32 query rows and output columns [32*half, 32*half+32); the two halves exchange their
+    // partial row max through shared memory (the partial row sums only meet at the end).
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    float o_acc[64];
+    float o_acc[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     const int rg = (MODE == 1) ? (r % p.G) : 0;
     // temporal mode: the T keys of this row's site sit at columns rg + t*G (block-diagonal mask)
@@ -165,16 +171,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
       const int nvalid = p.S - kv0 - c * 32;
       return nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
     };
-    uint8_t* prow = sP + r * 128;
+    uint8_t* prow = sP + half * kTile + r * 128;  // this warp's 64 key columns = one 128B-swizzle atom
 
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&s_full, (uint32_t)(j & 1));
       tc_fence_after();
       const int kv0 = j * 128;
-      // ---- pass 1: row max over the valid columns
+      // ---- pass 1: row max over this warp's valid columns
       float m_blk = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t raw[32];
         tmem_ld32(tS + lane_off + c * 32, raw);
         tmem_ld_wait();
@@ -194,29 +201,31 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
             if ((okm >> i) & 1u) m_blk = fmaxf(m_blk, __uint_as_float(raw[i]));
         }
       }
+      // exchange with the other half (double-buffered by block parity, one 256-thread barrier)
+      xmax[j & 1][half][r] = m_blk;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      m_blk = fmaxf(m_blk, xmax[j & 1][half ^ 1][r]);
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = ex2f((m_run - m_new) * p.c);
       // ---- fold the previous block's P V into the fp32 accumulator (also frees the P buffer)
       if (j > 0) {
         mbar_wait(&o_full, (uint32_t)((j - 1) & 1));
         tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld32(tO + lane_off + half * 32, raw);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(tO + lane_off + c * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(raw[i]);
-        }
+        for (int i = 0; i < 32; ++i) o_acc[i] += __uint_as_float(raw[i]);
       }
 #pragma unroll
-      for (int i = 0; i < 64; ++i) o_acc[i] *= alpha;
+      for (int i = 0; i < 32; ++i) o_acc[i] *= alpha;
       l_run *= alpha;
       m_run = m_new;
       const float mc = m_new * p.c;
       // ---- pass 2: P = exp2(s*c - m*c) as bf16 into swizzled smem
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t raw[32];
         tmem_ld32(tS + lane_off + c * 32, raw);
         tmem_ld_wait();
@@ -243,11 +252,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
             pk[i >> 1] = pack_bf16x2(pv[0], pv[1]);
           }
         }
-        uint8_t* atom = prow + (c >> 1) * kTile;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int ch = (c & 1) * 4 + i;
-          *reinterpret_cast<uint4*>(atom + ((ch ^ (r & 7)) << 4)) =
+          const int ch = cc * 4 + i;
+          *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) =
               make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
       }
@@ -256,18 +264,19 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full);
     }
-    // ---- last block's P V, normalise, store
+    // ---- last block's P V, combine the two partial row sums, normalise, store
     mbar_wait(&o_full, (uint32_t)((nkv - 1) & 1));
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t raw[32];
-      tmem_ld32(tO + lane_off + c * 32, raw);
+      tmem_ld32(tO + lane_off + half * 32, raw);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(raw[i]);
+      for (int i = 0; i < 32; ++i) o_acc[i] += __uint_as_float(raw[i]);
     }
-    const float inv = 1.0f / l_run;
+    xsum[half][r] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float inv = 1.0f / (l_run + xsum[half ^ 1][r]);
     long long orow;
     bool valid;
     if (MODE == 0) {
@@ -281,9 +290,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
       orow = ((long long)blockIdx.z * p.T + t) * p.S + s;
     }
     if (valid) {
-      uint4* op = reinterpret_cast<uint4*>(p.out + orow * p.C + head * 64);
+      uint4* op = reinterpret_cast<uint4*>(p.out + orow * p.C + head * 64 + half * 32);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         uint4 u;
         u.x = pack_bf16x2(o_acc[8 * i] * inv, o_acc[8 * i + 1] * inv);
         u.y = pack_bf16x2(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
