@@ -290,6 +290,8 @@ def run_b200(a):
     e2e_value = world * a.steps / (float(ms2.item()) / 1e3)
     h2d, d2h = st.host_bytes_per_step()
 
+    if world > 1:
+        dist.destroy_process_group()
     if rank != 0:
         return 0
     peaks, peak_src = {}, "fallback (B200_PROFILING.md)"

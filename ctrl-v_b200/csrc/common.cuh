@@ -93,6 +93,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// wait that backs off between probes: for waits that are long whenever another role is the
+// bottleneck (producer waiting for a free stage, MMA issuer waiting for a drained accumulator), so
+// the polling warp does not steal issue slots from the warps doing the work on its SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "memory");
+    if (done) break;
+    __nanosleep(128);
+  }
+}
+
 // named barrier over `nthreads` threads that also AND-reduces a predicate
 __device__ __forceinline__ bool bar_red_and(int id, int nthreads, bool pred) {
   uint32_t r;

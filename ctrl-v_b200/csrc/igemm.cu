@@ -24,8 +24,7 @@ namespace ctrlv {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
-constexpr int kEpiWarps = 12;  // 3 per TMEM lane quarter; chunk c of a tile goes to group c % 3
-constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kMaxEpiWarps = 16;  // epilogue warps: 12 (3 per TMEM lane quarter) or 16 (4 per quarter)
 
 // developer trace: clock64 stamps of CTA 0 (8 slots per tile), read back with ctrlv_debug_trace_read
 __device__ long long g_trace[8 * 64];
@@ -245,12 +244,12 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
 // chunk groups, at most 3 chunks for BN <= 256).  Residual rows are fetched one chunk AHEAD — the
 // first one before the accumulator is even ready — so their HBM latency overlaps the MMA wait and
 // the previous chunk's math instead of sitting on the critical path.
-template <bool GEGLU>
+template <bool GEGLU, int EW>
 __device__ __forceinline__ void ep_tile(const ctrlv_epilogue& ep, uint64_t* tfull, uint32_t tphase, uint32_t t_row,
                                         long long m, int n_base, int N, int BN, int n_store, bool valid, int sub,
                                         float* sbias, uint4* wst, const float* rb, const float* rb_uniform) {
   constexpr int NV = GEGLU ? 16 : 32;
-  constexpr int G = kEpiWarps / 4;
+  constexpr int G = EW / 4;
   const int nch = BN / 32;
   const int c0 = sub, c1 = sub + G, c2 = sub + 2 * G;
   EpRows<NV> rows;
@@ -276,8 +275,9 @@ __device__ __forceinline__ void ep_tile(const ctrlv_epilogue& ep, uint64_t* tful
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) shares
 // one 256-row x BN tile: each CTA loads its own 128 A rows and HALF of the B tile, the leader issues
 // M=256 MMAs that read both halves — halves the shared-memory and L2 traffic of the B operand.
-template <int CG>
-__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+template <int CG, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  constexpr int kEpiWarps = EW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float wbias[kEpiWarps][32];   // per-warp broadcast row for the bias chunk
-  __shared__ __align__(16) uint4 wstage[kEpiWarps][128];  // per-warp 32 x 64 B transpose tile
+  __shared__ __align__(16) float wbias[EW][32];   // per-warp broadcast row for the bias chunk
+  __shared__ __align__(16) uint4 wstage[EW][128];  // per-warp 32 x 64 B transpose tile
 
   // 1024-byte aligned tile ring
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         for (int s = 0; s < p.nseg; ++s) {
           const IgemmSeg sg = p.seg[s];
           for (int ch = 0; ch < sg.nchunk; ++ch, ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
             uint8_t* sb = sa + kBM * kBK * 2;
             if (elect_one()) {
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       for (int it = 0; it < nloc; ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        mbar_wait_relaxed(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
         for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -478,10 +478,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       float* sbias = wbias[warp - 2];
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
       uint4* wst = wstage[warp - 2];
-      if (ep.geglu)
-        ep_tile<true>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
+      if (EW == 16 || ep.geglu)  // the 16-warp instantiation is GEGLU-only (keeps it inside 96 registers)
+        ep_tile<true, EW>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
       else
-        ep_tile<false>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
+        ep_tile<false, EW>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -516,10 +516,10 @@ static int device_props() {
   CTRLV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CTRLV_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   cudaFuncAttributes fa;
-  CTRLV_CUDA(cudaFuncGetAttributes(&fa, igemm_kernel<1>));
-  smem -= (int)fa.sharedSizeBytes;  // static shared memory (barriers) counts against the limit
-  CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CTRLV_CUDA(cudaFuncGetAttributes(&fa, igemm_kernel<1, 12>));
+  smem -= (int)fa.sharedSizeBytes;  // static shared memory (barriers, epilogue tiles) counts against the limit
+  CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<1, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   g_max_smem = smem;
   g_num_sms = sms;
   return CTRLV_OK;
@@ -697,17 +697,20 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
 
   size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   if (p.bres) smem = (size_t)p.bres_off + (size_t)p.kblocks * p.BN * kBK * 2 + 1024;
+  // 16 epilogue warps for the GEGLU epilogue (erf math on 8 chunks of a 256-wide tile: 2 per warp)
+  int ew = 12;  // (16 warps measured no faster for the GEGLU epilogue: it is issue-bound, not latency-bound)
+  const int threads = 64 + ew * 32;
   if (p.cg == 1) {
     int grid = p.tiles_total < g_num_sms ? p.tiles_total : g_num_sms;
     if (p.bres) grid = (g_num_sms / p.tiles_n) * p.tiles_n;
-    igemm_kernel<1><<<grid, kThreads, smem, stream>>>(p);
+    igemm_kernel<1, 12><<<grid, threads, smem, stream>>>(p);
     CTRLV_CUDA(cudaGetLastError());
   } else {
     const int pairs = p.tiles_total < g_num_sms / 2 ? p.tiles_total : g_num_sms / 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr;
@@ -715,7 +718,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    CTRLV_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<2>, p));
+    CTRLV_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<2, 12>, p));
   }
   return CTRLV_OK;
 }

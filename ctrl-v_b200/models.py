@@ -729,12 +729,14 @@ class UNetSpatioTemporalConditionModel(_PackedModel):
             att += a or []
         self._finish_pack(res, att)
 
-    def forward_rows(self, inp64, emb, ehs, g, down_res=None, mid_res=None, out_f32=None):
+    def forward_rows(self, inp64, emb, ehs, g, down_res=None, mid_res=None, out_f32=None, join=None):
         """inp64 [M, 64] -> noise prediction rows [M, out_channels] fp32."""
         B, T, H, W = g
         aux = self._aux(emb, ehs)
         x = ops.conv3x3(inp64, B * T, H, W, self.conv_in_w, bias=self.conv_in_b)
         x, skips, geoms, gm = self._encode(x, aux, g)
+        if join is not None:
+            join()  # the residuals come from another stream (DenoiseStep two-stream mode)
         if down_res is not None:  # unet_spatio_temporal_condition.py:119-127
             skips = [ops.axpby(s, r) for s, r in zip(skips, down_res)]
         x = self._mid(x, aux, gm)

@@ -72,8 +72,10 @@ class DenoiseStep:
 
     def __init__(self, unet: UNetSpatioTemporalConditionModel, controlnet: Optional[ControlNetModel],
                  batch: int, num_frames: int, h: int, w: int, cfg: bool = True,
-                 conditioning_scale: float = 1.0, use_graph: bool = True):
+                 conditioning_scale: float = 1.0, use_graph: bool = True, two_streams: bool = True):
         self.unet, self.controlnet = unet, controlnet
+        self.two_streams = two_streams
+        self._side = torch.cuda.Stream() if two_streams else None
         self.B, self.T, self.h, self.w, self.cfg = batch, num_frames, h, w, cfg
         self.nb = 2 * batch if cfg else batch
         self.scale = conditioning_scale
@@ -104,11 +106,25 @@ class DenoiseStep:
         ops.prep_input(self.latents, self.image_latents, self.cond_em if self.controlnet is not None else None,
                        self.cfg, sig, out=self.inp)
         down = mid = None
+        join = None
         if self.controlnet is not None:
-            emb_c = self.controlnet.embed(ts, self.added_time_ids)
-            down, mid, _, _ = self.controlnet.forward_rows(self.inp, emb_c, self.ehs, g, self.scale)
+            if self.two_streams:
+                # the ControlNet and the UNet encoder both depend only on `inp` (they meet at
+                # unet_spatio_temporal_condition.py:119): run the ControlNet on a side stream so its
+                # kernels fill the tails / small grids of the UNet encoder's
+                main = torch.cuda.current_stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    emb_c = self.controlnet.embed(ts, self.added_time_ids)
+                    down, mid, _, _ = self.controlnet.forward_rows(self.inp, emb_c, self.ehs, g, self.scale)
+                    for t in list(down) + [mid]:
+                        t.record_stream(main)
+                join = lambda: main.wait_stream(self._side)
+            else:
+                emb_c = self.controlnet.embed(ts, self.added_time_ids)
+                down, mid, _, _ = self.controlnet.forward_rows(self.inp, emb_c, self.ehs, g, self.scale)
         emb_u = self.unet.embed(ts, self.added_time_ids)
-        self.unet.forward_rows(self.inp, emb_u, self.ehs, g, down, mid, out_f32=self.noise)
+        self.unet.forward_rows(self.inp, emb_u, self.ehs, g, down, mid, out_f32=self.noise, join=join)
         ops.cfg_euler(self.latents, self.noise, self.cfg, self.guidance, sig)
 
     def set_schedule(self, sigmas: torch.Tensor, timesteps: torch.Tensor):
