@@ -2,6 +2,7 @@
 // the driver entry point (no link-time dependency on libcuda).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -16,6 +17,15 @@ void set_last_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CTRLV_PDL");
+    v = (e != nullptr && atoi(e) != 0) ? 1 : 0;  // opt-in: measured neutral inside the captured step graph
+  }
+  return v != 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

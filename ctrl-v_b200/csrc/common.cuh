@@ -3,6 +3,8 @@
 // no CUTLASS/CuTe dependency.  Bit layouts of the UMMA descriptors are documented next to
 // the builders below.
 #pragma once
+#include <cstring>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -39,6 +41,30 @@ void set_last_error(const char* fmt, ...);
     }                                                                                      \
   } while (0)
 
+// Programmatic dependent launch: every kernel of this library is launched with the
+// programmatic-stream-serialization attribute (also inside captured CUDA graphs), calls
+// pdl_trigger() on entry so its successor may be scheduled while it drains, and pdl_wait() before
+// its first access to global memory (full completion + visibility of the predecessor).
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Host: encode a tiled, 128B-swizzled bf16 tensor map of rank `rank` (<=5).
 // dims[0] is the contiguous dimension; strides_bytes[i] is the stride of dims[i+1].
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
@@ -48,6 +74,8 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 // ----------------------------------------------------------------------------------------
 // small utilities
 // ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -13,6 +13,8 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int M, int K,
                                     const bf16* __restrict__ W, const float* __restrict__ bias,
                                     int N, int act_in, int act_out, int accumulate,
                                     float* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -58,6 +60,8 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int M, int K,
 // diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0)
 __global__ void sinusoid_kernel(const float* __restrict__ t, int n, int dim, int round_bf16,
                                 float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim >> 1;
   if (idx >= n * half) return;
@@ -79,6 +83,8 @@ __global__ void sinusoid_kernel(const float* __restrict__ t, int n, int dim, int
 __global__ void prep_input_kernel(const float* __restrict__ lat, const float* __restrict__ img,
                                   const float* __restrict__ ctl, int B, int nb, int T, int hw,
                                   const float* __restrict__ sigma_dev, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const float sg = __ldg(sigma_dev);
   const float inv_scale = rsqrtf(sg * sg + 1.0f);
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,6 +118,8 @@ __global__ void prep_input_kernel(const float* __restrict__ lat, const float* __
 __global__ void cfg_euler_kernel(float* __restrict__ lat, const float* __restrict__ noise, int ldn,
                                  int B, int cfg, int T, int hw, const float* __restrict__ guidance,
                                  const float* __restrict__ sigma_dev, int round_bf16) {
+  pdl_wait();
+  pdl_trigger();
   const float sigma = __ldg(sigma_dev), sigma_next = __ldg(sigma_dev + 1);
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * T * hw;
@@ -142,6 +150,8 @@ __global__ void cfg_euler_kernel(float* __restrict__ lat, const float* __restric
 
 __global__ void upsample2x_kernel(const uint4* __restrict__ src, int frames, int H, int W, int vpr,
                                   uint4* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)frames * 2 * H * 2 * W * vpr;
   if (idx >= total) return;
@@ -155,6 +165,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ src, int frames, int
 
 __global__ void axpby_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, float a,
                              float b, long long nvec, uint4* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nvec) return;
   const uint4 ux = __ldg(x + idx), uy = __ldg(y + idx);
@@ -171,6 +183,8 @@ __global__ void axpby_kernel(const uint4* __restrict__ x, const uint4* __restric
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, int frames, int C, int HW, int Cpad,
                                     int c_off, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)frames * HW * C;
   if (idx >= total) return;
@@ -185,6 +199,8 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, int frames, int C
 template <typename TI, typename TO>
 __global__ void nhwc_to_nchw_kernel(const TI* __restrict__ src, long long ld, int frames, int C,
                                     int HW, TO* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)frames * HW * C;
   if (idx >= total) return;
@@ -208,8 +224,8 @@ extern "C" int ctrlv_small_linear(const float* x, int32_t M, int32_t K, const vo
   CTRLV_CHECK_ARG(x && W && y, "small_linear: null pointer");
   CTRLV_CHECK_ARG(M > 0 && M <= 64 && K % 8 == 0 && N > 0, "small_linear: M=%d K=%d N=%d unsupported", M, K, N);
   const int wpb = 8;
-  small_linear_kernel<<<nblk(N, wpb), wpb * 32, 0, stream>>>(x, M, K, reinterpret_cast<const bf16*>(W),
-                                                            bias, N, act_in, act_out, accumulate, y);
+  CTRLV_CUDA(launch_pdl(small_linear_kernel, dim3(nblk(N, wpb)), dim3(wpb * 32), (size_t)(0), stream, x, M, K, reinterpret_cast<const bf16*>(W),
+                                                            bias, N, act_in, act_out, accumulate, y));
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }
@@ -218,7 +234,7 @@ extern "C" int ctrlv_sinusoid(const float* t, int32_t n, int32_t dim, int32_t ro
                               void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTRLV_CHECK_ARG(t && out && n > 0 && dim > 0 && dim % 2 == 0, "sinusoid: bad arguments");
-  sinusoid_kernel<<<nblk((long long)n * dim / 2, 128), 128, 0, stream>>>(t, n, dim, round_bf16, out);
+  CTRLV_CUDA(launch_pdl(sinusoid_kernel, dim3(nblk((long long)n * dim / 2, 128)), dim3(128), (size_t)(0), stream, t, n, dim, round_bf16, out));
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }
@@ -230,8 +246,8 @@ extern "C" int ctrlv_prep_input(const float* latents, const float* image_latents
   CTRLV_CHECK_ARG(latents && out && sigma_dev, "prep_input: null pointer");
   const int nb = cfg ? 2 * B : B;
   const long long total = (long long)nb * T * h * w;
-  prep_input_kernel<<<nblk(total, 256), 256, 0, stream>>>(latents, image_latents, control_cond, B, nb,
-                                                          T, h * w, sigma_dev, reinterpret_cast<bf16*>(out));
+  CTRLV_CUDA(launch_pdl(prep_input_kernel, dim3(nblk(total, 256)), dim3(256), (size_t)(0), stream, latents, image_latents, control_cond, B, nb,
+                                                          T, h * w, sigma_dev, reinterpret_cast<bf16*>(out)));
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }
@@ -242,8 +258,8 @@ extern "C" int ctrlv_cfg_euler(float* latents, const float* noise, int32_t ld_no
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTRLV_CHECK_ARG(latents && noise && sigma_dev && ld_noise >= 4, "cfg_euler: bad arguments");
   const long long total = (long long)B * T * h * w;
-  cfg_euler_kernel<<<nblk(total, 256), 256, 0, stream>>>(latents, noise, ld_noise, B, cfg, T, h * w,
-                                                         guidance, sigma_dev, round_bf16);
+  CTRLV_CUDA(launch_pdl(cfg_euler_kernel, dim3(nblk(total, 256)), dim3(256), (size_t)(0), stream, latents, noise, ld_noise, B, cfg, T, h * w,
+                                                         guidance, sigma_dev, round_bf16));
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }
@@ -253,8 +269,8 @@ extern "C" int ctrlv_upsample2x(const void* src, int32_t frames, int32_t H, int3
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTRLV_CHECK_ARG(src && out && C % 8 == 0, "upsample2x: bad arguments");
   const long long total = (long long)frames * 4 * H * Wd * (C / 8);
-  upsample2x_kernel<<<nblk(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), frames, H,
-                                                          Wd, C / 8, reinterpret_cast<uint4*>(out));
+  CTRLV_CUDA(launch_pdl(upsample2x_kernel, dim3(nblk(total, 256)), dim3(256), (size_t)(0), stream, reinterpret_cast<const uint4*>(src), frames, H,
+                                                          Wd, C / 8, reinterpret_cast<uint4*>(out)));
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }
@@ -263,9 +279,9 @@ extern "C" int ctrlv_axpby(const void* x, const void* y, float a, float b, int64
                            void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTRLV_CHECK_ARG(x && y && out && n % 8 == 0, "axpby: bad arguments (n %% 8)");
-  axpby_kernel<<<nblk(n / 8, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+  CTRLV_CUDA(launch_pdl(axpby_kernel, dim3(nblk(n / 8, 256)), dim3(256), (size_t)(0), stream, reinterpret_cast<const uint4*>(x),
                                                      reinterpret_cast<const uint4*>(y), a, b, n / 8,
-                                                     reinterpret_cast<uint4*>(out));
+                                                     reinterpret_cast<uint4*>(out)));
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }
@@ -276,11 +292,11 @@ extern "C" int ctrlv_nchw_to_nhwc(const void* src, int32_t src_is_f32, int32_t f
   CTRLV_CHECK_ARG(src && out && c_off >= 0 && c_off + C <= Cpad, "nchw_to_nhwc: bad arguments");
   const long long total = (long long)frames * HW * C;
   if (src_is_f32)
-    nchw_to_nhwc_kernel<float><<<nblk(total, 256), 256, 0, stream>>>(
-        reinterpret_cast<const float*>(src), frames, C, HW, Cpad, c_off, reinterpret_cast<bf16*>(out));
+    CTRLV_CUDA(launch_pdl(nchw_to_nhwc_kernel<float>, dim3(nblk(total, 256)), dim3(256), (size_t)(0), stream, 
+        reinterpret_cast<const float*>(src), frames, C, HW, Cpad, c_off, reinterpret_cast<bf16*>(out)));
   else
-    nchw_to_nhwc_kernel<bf16><<<nblk(total, 256), 256, 0, stream>>>(
-        reinterpret_cast<const bf16*>(src), frames, C, HW, Cpad, c_off, reinterpret_cast<bf16*>(out));
+    CTRLV_CUDA(launch_pdl(nchw_to_nhwc_kernel<bf16>, dim3(nblk(total, 256)), dim3(256), (size_t)(0), stream, 
+        reinterpret_cast<const bf16*>(src), frames, C, HW, Cpad, c_off, reinterpret_cast<bf16*>(out)));
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }
@@ -292,13 +308,13 @@ extern "C" int ctrlv_nhwc_to_nchw(const void* src, int32_t src_is_f32, int64_t l
   const long long total = (long long)frames * HW * C;
   const unsigned g = nblk(total, 256);
   if (src_is_f32 && out_is_f32)
-    nhwc_to_nchw_kernel<float, float><<<g, 256, 0, stream>>>(reinterpret_cast<const float*>(src), ld, frames, C, HW, reinterpret_cast<float*>(out));
+    CTRLV_CUDA(launch_pdl(nhwc_to_nchw_kernel<float, float>, dim3(g), dim3(256), (size_t)(0), stream, reinterpret_cast<const float*>(src), ld, frames, C, HW, reinterpret_cast<float*>(out)));
   else if (src_is_f32)
-    nhwc_to_nchw_kernel<float, bf16><<<g, 256, 0, stream>>>(reinterpret_cast<const float*>(src), ld, frames, C, HW, reinterpret_cast<bf16*>(out));
+    CTRLV_CUDA(launch_pdl(nhwc_to_nchw_kernel<float, bf16>, dim3(g), dim3(256), (size_t)(0), stream, reinterpret_cast<const float*>(src), ld, frames, C, HW, reinterpret_cast<bf16*>(out)));
   else if (out_is_f32)
-    nhwc_to_nchw_kernel<bf16, float><<<g, 256, 0, stream>>>(reinterpret_cast<const bf16*>(src), ld, frames, C, HW, reinterpret_cast<float*>(out));
+    CTRLV_CUDA(launch_pdl(nhwc_to_nchw_kernel<bf16, float>, dim3(g), dim3(256), (size_t)(0), stream, reinterpret_cast<const bf16*>(src), ld, frames, C, HW, reinterpret_cast<float*>(out)));
   else
-    nhwc_to_nchw_kernel<bf16, bf16><<<g, 256, 0, stream>>>(reinterpret_cast<const bf16*>(src), ld, frames, C, HW, reinterpret_cast<bf16*>(out));
+    CTRLV_CUDA(launch_pdl(nhwc_to_nchw_kernel<bf16, bf16>, dim3(g), dim3(256), (size_t)(0), stream, reinterpret_cast<const bf16*>(src), ld, frames, C, HW, reinterpret_cast<bf16*>(out)));
   CTRLV_CUDA(cudaGetLastError());
   return CTRLV_OK;
 }

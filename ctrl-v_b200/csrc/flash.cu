@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   const int lane = threadIdx.x & 31;
   const int head = blockIdx.y;
   const int nkv = p.nkv;
+  pdl_trigger();
 
   if (MODE == 1) {
     // the temporal box covers G*T < 128 rows; the rest must be zero (0 * garbage would be NaN)
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
   const uint32_t tS = tmem_base;
   const uint32_t tO = tmem_base + 128;
 
@@ -346,8 +348,7 @@ extern "C" int ctrlv_attn_spatial(const void* qkv, int32_t frames, int32_t S, in
   rc = encode_tmap_bf16(&p.tm, qkv, 3, dims, strides, box, true);
   if (rc) return rc;
   dim3 grid((S + 127) / 128, heads, frames);
-  attn_kernel<0><<<grid, kAttnThreads, 6 * kTile + 1024, stream>>>(p);
-  CTRLV_CUDA(cudaGetLastError());
+  CTRLV_CUDA(launch_pdl(attn_kernel<0>, grid, dim3(kAttnThreads), (size_t)(6 * kTile + 1024), stream, p));
   return CTRLV_OK;
 }
 
@@ -374,7 +375,6 @@ extern "C" int ctrlv_attn_temporal(const void* qkv, int32_t B, int32_t T, int32_
   rc = encode_tmap_bf16(&p.tm, qkv, 4, dims, strides, box, true);
   if (rc) return rc;
   dim3 grid((S + p.G - 1) / p.G, heads, B);
-  attn_kernel<1><<<grid, kAttnThreads, 6 * kTile + 1024, stream>>>(p);
-  CTRLV_CUDA(cudaGetLastError());
+  CTRLV_CUDA(launch_pdl(attn_kernel<1>, grid, dim3(kAttnThreads), (size_t)(6 * kTile + 1024), stream, p));
   return CTRLV_OK;
 }

@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_con
                                              ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();  // the next kernel may be scheduled as SMs drain; it blocks in its own pdl_wait()
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nseg; ++i) tma_prefetch_desc(&p.tmA[p.seg[i].map]);
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;
+  pdl_wait();  // everything above overlapped the predecessor's tail; its results are needed from here
 
   // work unit: (super-tile of CG consecutive m-tiles, n-tile); units are dealt round-robin to
   // clusters; inside a pair CTA r owns m-tile CG*super + r
@@ -703,8 +705,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   if (p.cg == 1) {
     int grid = p.tiles_total < g_num_sms ? p.tiles_total : g_num_sms;
     if (p.bres) grid = (g_num_sms / p.tiles_n) * p.tiles_n;
-    igemm_kernel<1, 12><<<grid, threads, smem, stream>>>(p);
-    CTRLV_CUDA(cudaGetLastError());
+    CTRLV_CUDA(launch_pdl(igemm_kernel<1, 12>, dim3(grid), dim3(threads), smem, stream, p));
   } else {
     const int pairs = p.tiles_total < g_num_sms / 2 ? p.tiles_total : g_num_sms / 2;
     cudaLaunchConfig_t cfg;
@@ -713,11 +714,13 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
     CTRLV_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<2, 12>, p));
   }
   return CTRLV_OK;

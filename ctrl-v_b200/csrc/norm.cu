@@ -17,6 +17,8 @@ constexpr int kMaxSplit = 256;
 __global__ void gn_stats_kernel(const bf16* __restrict__ src0, int C0, const bf16* __restrict__ src1,
                                 int C1, int rows_per_unit, int rows_per_split, int nsplit,
                                 int nwork, float* __restrict__ partial) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float gn_smem[];  // [nwork][8] thread sums, then [vpr*4][2] channel-pair sums
   const int C = C0 + C1;
   const int vpr = C >> 3;
@@ -86,6 +88,8 @@ __global__ void __launch_bounds__(512, 3) gn_apply_kernel(const bf16* __restrict
                                 int nwork, const float* __restrict__ partial, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu,
                                 bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float mean_s[kGroups], rstd_s[kGroups];
   const int C = C0 + C1;
   const int vpr = C >> 3;
@@ -173,6 +177,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float eps, const float* __restrict__ rowbias, int ld_rowbias,
                                  int rb_div, int rb_mod, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = gtid / LPR;
   const int sl = threadIdx.x % LPR;  // sub-lane inside the row group
@@ -282,14 +288,13 @@ extern "C" int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, i
   nsplit = (rows_per_unit + rows_per_split - 1) / rows_per_split;
   float* partial = reinterpret_cast<float*>(workspace);
   const size_t st_smem = ((size_t)nwork * 8 + (size_t)vpr * 8) * sizeof(float);
-  gn_stats_kernel<<<n_units * nsplit, nthreads, st_smem, stream>>>(
-      reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1, rows_per_unit,
-      rows_per_split, nsplit, nwork, partial);
-  CTRLV_CUDA(cudaGetLastError());
-  gn_apply_kernel<<<n_units * nsplit, nthreads, 0, stream>>>(
-      reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1, rows_per_unit,
-      nsplit, nsplit, nwork, partial, gamma, beta, eps, silu, reinterpret_cast<bf16*>(out));
-  CTRLV_CUDA(cudaGetLastError());
+  CTRLV_CUDA(launch_pdl(gn_stats_kernel, dim3(n_units * nsplit), dim3(nthreads), st_smem, stream,
+                        reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1,
+                        rows_per_unit, rows_per_split, nsplit, nwork, partial));
+  CTRLV_CUDA(launch_pdl(gn_apply_kernel, dim3(n_units * nsplit), dim3(nthreads), (size_t)0, stream,
+                        reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1,
+                        rows_per_unit, nsplit, nsplit, nwork, (const float*)partial, gamma, beta, eps, silu,
+                        reinterpret_cast<bf16*>(out)));
   return CTRLV_OK;
 }
 
@@ -313,9 +318,10 @@ extern "C" int ctrlv_layernorm(const void* x, int64_t ldx, int32_t M, int32_t C,
   const int threads = 256;
   const long long total = (long long)M * lpr;
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-#define CTRLV_LN(L, V)                                                                            \
-  layernorm_kernel<L, V><<<blocks, threads, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, M, C, \
-      gamma, beta, eps, rowbias, ld_rowbias, rb_div, rb_mod, reinterpret_cast<bf16*>(out))
+#define CTRLV_LN(L, V)                                                                             \
+  CTRLV_CUDA(launch_pdl(layernorm_kernel<L, V>, dim3(blocks), dim3(threads), (size_t)0, stream,        \
+                        reinterpret_cast<const bf16*>(x), (long long)ldx, M, C, gamma, beta, eps, rowbias, \
+                        ld_rowbias, rb_div, rb_mod, reinterpret_cast<bf16*>(out)))
   if (lpr == 8 && vpl == 1) CTRLV_LN(8, 1);
   else if (lpr == 8 && vpl == 2) CTRLV_LN(8, 2);
   else if (lpr == 8 && vpl == 5) CTRLV_LN(8, 5);
