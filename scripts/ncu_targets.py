@@ -28,3 +28,13 @@ if which == "norms":
         ops.groupnorm(x, 2, 35840, g, b, 1e-5, True, out=o)
         ops.layernorm(x, g, b, out=o)
     torch.cuda.synchronize()
+if which == "conv":
+    x = torch.randn(28 * 40 * 64, 320, device=dev).to(BF); w = (torch.randn(320, 9 * 320, device=dev) / 54).to(BF); b = torch.randn(320, device=dev)
+    for _ in range(3): ops.conv3x3(x, 28, 40, 64, w, bias=b)
+    x = torch.randn(28 * 20 * 32, 640, device=dev).to(BF); w = (torch.randn(640, 9 * 640, device=dev) / 76).to(BF); b = torch.randn(640, device=dev)
+    for _ in range(3): ops.conv3x3(x, 28, 20, 32, w, bias=b)
+    torch.cuda.synchronize()
+if which == "tattn":
+    qkv = torch.randn(28 * 2560, 960, device=dev).to(BF)
+    for _ in range(3): ops.attn_temporal(qkv, 2, 14, 2560, 5)
+    torch.cuda.synchronize()
