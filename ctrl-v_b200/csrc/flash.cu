@@ -15,6 +15,8 @@
 //                   running-max rescale.
 //  TMEM: S 128 cols + O 64 cols (256 allocated) and ~97 KB smem -> 2 CTAs per SM overlap each
 //  other's softmax and MMA phases.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/ctrlv_b200.h"
 
@@ -314,12 +316,293 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Spatial attention, second generation (long sequences): one CTA owns TWO 128-query tiles of the
+// same (frame, head) and keeps both in flight, so the tensor pipe works under the softmax of both
+// (FlashAttention-4 style schedule, d = 64):
+//   * warp 0 TMA (Q0, Q1 once; K / V blocks through a 4-slot ring in consumption order, each
+//     loaded ONCE for both tiles), warp 1 MMA issuer, warps 2-5 softmax of tile 0, 6-9 of tile 1;
+//   * TMEM (512 cols): S0 | S1 (128 fp32 cols each), O0 | O1 (64 each), P0 | P1 (64 each: 128 bf16
+//     probabilities per row, two per column).  P never touches shared memory: the softmax warps
+//     tcgen05.st it and P V is a TMEM-A tcgen05.mma — shared-memory bandwidth is left to K and V;
+//   * a softmax thread owns one query row: it pulls the whole S row into registers and releases
+//     S_t at once (s_free), so Q K^T of the next block runs under the exponentials of this one;
+//   * O stays in TMEM for the whole key loop (the MMA accumulates across blocks); lazy rescale:
+//     the running max only moves when it grew by more than 2^8, then the owning warp rescales its
+//     O rows in place (tcgen05.ld / tcgen05.st) after P V of the previous block has completed.
+// ------------------------------------------------------------------------------------------
+constexpr int kAttn2Smem = (2 + 4) * kTile + 1024;  // Q0,Q1 | 4 K/V slots
+constexpr int kAttn2Threads = 64 + 8 * 32;
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+      "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+      "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_full, s_full[2], s_free[2], p_full[2], o_full[2];
+  __shared__ __align__(8) uint64_t kv_full[4], kv_empty[4];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                 // 2 tiles
+  uint8_t* sKV = smem + 2 * kTile;    // 4 slots
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int nkv = p.nkv;
+  pdl_trigger();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm);
+    mbar_init(&q_full, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_free[t], 4);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&o_full[t], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+  const int q0 = blockIdx.x * 256;  // first query row of tile 0
+
+  // K/V blocks travel through the ring in the order the MMA warp consumes them:
+  //   K0, then for j = 0..nkv-1: [K(j+1)], V(j).
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      const int colq = head * 64, colk = p.C + head * 64, colv = 2 * p.C + head * 64;
+      mbar_expect_tx(&q_full, 2u * kTile);
+      tma_load_3d(sQ, &p.tm, &q_full, colq, q0, blockIdx.z);
+      tma_load_3d(sQ + kTile, &p.tm, &q_full, colq, q0 + 128, blockIdx.z);
+      int n = 0;
+      auto load = [&](int col, int blk) {
+        const int slot = n & 3;
+        mbar_wait_relaxed(&kv_empty[slot], (uint32_t)(((n >> 2) & 1) ^ 1));
+        mbar_expect_tx(&kv_full[slot], (uint32_t)kTile);
+        tma_load_3d(sKV + slot * kTile, &p.tm, &kv_full[slot], col, blk * 128, blockIdx.z);
+        ++n;
+      };
+      load(colk, 0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) load(colk, j + 1);
+        load(colv, j);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (warp-uniform, elected lane issues) ============
+    const uint32_t idesc_qk = make_idesc(128, 128, 0, 0);
+    const uint32_t idesc_pv = make_idesc(128, 64, 0, 1);  // A (= P) from TMEM, B (= V) MN-major
+    const uint32_t aQ = smem_u32(sQ), aKV = smem_u32(sKV);
+    int n = 0;  // ring position of the block in use
+    auto issue_qk = [&](int t, bool release) {  // S_t = Q_t K^T
+      const int slot = n & 3;
+      if (t == 0) {
+        mbar_wait(&kv_full[slot], (uint32_t)((n >> 2) & 1));
+        tc_fence_after();
+      }
+      if (elect_one()) {
+        const uint32_t aK = aKV + slot * kTile;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem_base + t * 128, make_sdesc(aQ + t * kTile + k * 32, 16, 1024),
+                  make_sdesc(aK + k * 32, 16, 1024), idesc_qk, (uint32_t)(k != 0));
+        if (release) umma_commit(&kv_empty[slot]);
+        umma_commit(&s_full[t]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int t, int j, bool release) {  // O_t (+)= P_t V_j
+      const int slot = n & 3;
+      if (t == 0) {
+        mbar_wait(&kv_full[slot], (uint32_t)((n >> 2) & 1));
+        tc_fence_after();
+      }
+      if (elect_one()) {
+        const uint32_t aV = aKV + slot * kTile;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + k * 8,
+                  make_sdesc(aV + k * 2048, 1024, 1024), idesc_pv, (uint32_t)((j | k) != 0));
+        if (release) umma_commit(&kv_empty[slot]);
+        umma_commit(&o_full[t]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&q_full, 0);
+    issue_qk(0, false);
+    issue_qk(1, true);
+    ++n;
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) {
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&s_free[t], (uint32_t)(j & 1));  // S_t(j) is in the softmax warps' registers
+          tc_fence_after();
+          issue_qk(t, t == 1);
+        }
+        ++n;
+      }
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_full[t], (uint32_t)(j & 1));  // P_t(j) in TMEM, O_t rescaled if needed
+        tc_fence_after();
+        issue_pv(t, j, t == 1);
+      }
+      ++n;
+    }
+  } else {
+    // ============================ softmax warps =====================================
+    const int t = (warp - 2) >> 2;                // tile
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                  // row within the tile
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem_base + t * 128 + lane_off;
+    const uint32_t tO = tmem_base + 256 + t * 64 + lane_off;
+    const uint32_t tP = tmem_base + 384 + t * 64 + lane_off;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_full[t], (uint32_t)(j & 1));
+      tc_fence_after();
+      uint32_t sreg[128];
+      tmem_ld32(tS, sreg);
+      tmem_ld32(tS + 32, sreg + 32);
+      tmem_ld32(tS + 64, sreg + 64);
+      tmem_ld32(tS + 96, sreg + 96);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);
+      const int kv0 = j * 128;
+      const bool full_blk = (kv0 + 128 <= p.S);
+      // ---- pass 1: row max
+      float m_blk;
+      if (full_blk) {
+        float m0 = fmaxf(__uint_as_float(sreg[0]), __uint_as_float(sreg[1]));
+        float m1 = fmaxf(__uint_as_float(sreg[2]), __uint_as_float(sreg[3]));
+#pragma unroll
+        for (int i = 4; i < 128; i += 4) {
+          m0 = max3f(m0, __uint_as_float(sreg[i]), __uint_as_float(sreg[i + 1]));
+          m1 = max3f(m1, __uint_as_float(sreg[i + 2]), __uint_as_float(sreg[i + 3]));
+        }
+        m_blk = fmaxf(m0, m1);
+      } else {
+        m_blk = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (kv0 + i < p.S) m_blk = fmaxf(m_blk, __uint_as_float(sreg[i]));
+      }
+      // P_t and O_t are free once P V of the previous block has completed
+      if (j > 0) {
+        mbar_wait(&o_full[t], (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
+      // ---- lazy rescale of the running max (and of O in TMEM) when it grew by more than 2^8
+      if (j == 0) {
+        m_run = m_blk;
+      } else {
+        const bool grow = (m_blk - m_run) * p.c > 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = grow ? m_blk : m_run;
+          const float alpha = ex2f((m_run - m_new) * p.c);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tO + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tO + c * 16, o);
+          }
+          l_run *= alpha;
+          m_run = m_new;
+        }
+      }
+      const float mc = m_run * p.c;
+      // ---- pass 2: P = exp2(s*c - m*c), packed bf16 pairs -> TMEM
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+          float p0 = ex2f(fmaf(__uint_as_float(sreg[c * 64 + i]), p.c, -mc));
+          float p1 = ex2f(fmaf(__uint_as_float(sreg[c * 64 + i + 1]), p.c, -mc));
+          if (!full_blk) {
+            if (kv0 + c * 64 + i >= p.S) p0 = 0.f;
+            if (kv0 + c * 64 + i + 1 >= p.S) p1 = 0.f;
+          }
+          l0 += p0; l1 += p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st32(tP + c * 32, pk);
+      }
+      l_run += l0 + l1;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+    // ---- all P V of this tile done: normalise and store
+    mbar_wait(&o_full[t], (uint32_t)((nkv - 1) & 1));
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    const int srow = q0 + t * 128 + r;
+    const bool valid = srow < p.S;
+    bf16* orow = p.out + ((long long)blockIdx.z * p.S + srow) * p.C + head * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tO + c * 32, raw);
+      tmem_ld_wait();
+      if (valid) {
+        uint4* op = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(raw[8 * i]) * inv, __uint_as_float(raw[8 * i + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(raw[8 * i + 2]) * inv, __uint_as_float(raw[8 * i + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(raw[8 * i + 4]) * inv, __uint_as_float(raw[8 * i + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(raw[8 * i + 6]) * inv, __uint_as_float(raw[8 * i + 7]) * inv);
+          op[i] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static bool g_attn_init = false;
 static int attn_init() {
   if (g_attn_init) return CTRLV_OK;
   const int smem = 6 * kTile + 1024;
   CTRLV_CUDA(cudaFuncSetAttribute(attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CTRLV_CUDA(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CTRLV_CUDA(cudaFuncSetAttribute(attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2Smem));
   g_attn_init = true;
   return CTRLV_OK;
 }
@@ -347,6 +630,14 @@ extern "C" int ctrlv_attn_spatial(const void* qkv, int32_t frames, int32_t S, in
   uint32_t box[3] = {64, 128, 1};
   rc = encode_tmap_bf16(&p.tm, qkv, 3, dims, strides, box, true);
   if (rc) return rc;
+  // long sequences: two-tile kernel with P in TMEM; short ones: one tile per CTA, 2 CTAs per SM
+  const char* v = getenv("CTRLV_ATTN_V");
+  const int ver = v ? atoi(v) : (S >= 160 ? 2 : 1);
+  if (ver == 2) {
+    dim3 grid2((S + 255) / 256, heads, frames);
+    CTRLV_CUDA(launch_pdl(attn2_kernel, grid2, dim3(kAttn2Threads), (size_t)kAttn2Smem, stream, p));
+    return CTRLV_OK;
+  }
   dim3 grid((S + 127) / 128, heads, frames);
   CTRLV_CUDA(launch_pdl(attn_kernel<0>, grid, dim3(kAttnThreads), (size_t)(6 * kTile + 1024), stream, p));
   return CTRLV_OK;
