@@ -468,6 +468,29 @@ class _PackedModel(torch.nn.Module):
         self._pack()
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
+    # ---- diffusers-format checkpoints --------------------------------------
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None,
+                        variant: Optional[str] = None, time_context_order: str = "s_major", **kwargs):
+        """Load `<path>/<subfolder>/{config.json, diffusion_pytorch_model[.variant].safetensors|.bin}`
+        like `ModelMixin.from_pretrained` does for the reference
+        (tools/eval_video_controlnet.py:114-118).  Local directories only (no hub)."""
+        from . import checkpoint
+        kwargs.pop("torch_dtype", None); kwargs.pop("low_cpu_mem_usage", None)
+        config, sd = checkpoint.load_diffusers_dir(pretrained_model_name_or_path, subfolder, variant)
+        known = set(SVD_CONFIG) - ({"out_channels", "up_block_types"} if cls.is_controlnet else set())
+        over = {k: (tuple(v) if isinstance(v, list) else v) for k, v in config.items() if k in known}
+        over.update(kwargs)
+        return cls(state_dict=sd, time_context_order=time_context_order, **over)
+
+    def save_pretrained(self, save_directory: str, subfolder: Optional[str] = None,
+                        variant: Optional[str] = None, safe_serialization: bool = True,
+                        max_shard_bytes: Optional[int] = None):
+        from . import checkpoint
+        name = "ControlNetModel" if self.is_controlnet else "UNetSpatioTemporalConditionModel"
+        checkpoint.save_diffusers_dir(save_directory, self.cfg, self._sd, name, subfolder, variant,
+                                      safe_serialization, max_shard_bytes)
+
     def to(self, *a, **k):  # weights are device-resident bf16 by construction
         return self
 

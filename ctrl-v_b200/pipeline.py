@@ -300,3 +300,92 @@ class StableVideoControlPipeline:
         if not return_dict:
             return frames
         return StableVideoDiffusionPipelineOutput(frames=frames)
+
+
+class VideoDiffusionPipeline(StableVideoControlPipeline):
+    """Drop-in for ctrlv.pipelines.VideoDiffusionPipeline (pipeline_video_diffusion.py:19-330): the
+    plain SVD sampler of the bbox-predictor stage.  Same loop as the control
+    pipeline without the ControlNet (:259-293); the conditioning-frame overwrite (:200-206) puts the
+    bbox-frame latents of the first `num_cond_bbox_frames` frames and of the last frame in place of
+    the repeated image latents.  `bbox_images` must be 4-channel latents [B, T, 4, h, w] until the VAE
+    encoder row (f-1) is built; CLIP/VAE encodes are passed in as for the control pipeline."""
+
+    def __init__(self, vae=None, image_encoder=None, unet: UNetSpatioTemporalConditionModel = None,
+                 scheduler: EulerDiscreteScheduler = None, feature_extractor=None):
+        super().__init__(vae=vae, image_encoder=image_encoder, unet=unet, controlnet=None,
+                         scheduler=scheduler, feature_extractor=feature_extractor)
+
+    def check_inputs(self, image, height, width):  # diffusers check_inputs: only the size rule applies here
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+
+    @torch.no_grad()
+    def __call__(self, image=None, bbox_images: Optional[torch.Tensor] = None, bbox_conditions=None,
+                 original_size=(1242, 375), height: int = 576, width: int = 1024,
+                 num_frames: Optional[int] = None, num_inference_steps: int = 25,
+                 min_guidance_scale: float = 1.0, max_guidance_scale: float = 3.0, fps: int = 7,
+                 motion_bucket_id: int = 127, noise_aug_strength: float = 0.02,
+                 decode_chunk_size: Optional[int] = None, num_videos_per_prompt: Optional[int] = 1,
+                 generator=None, latents: Optional[torch.Tensor] = None, output_type: Optional[str] = "pil",
+                 callback_on_step_end: Optional[Callable] = None,
+                 callback_on_step_end_tensor_inputs: List[str] = ["latents"], return_dict: bool = True,
+                 num_cond_bbox_frames: int = 3, image_embeddings: Optional[torch.Tensor] = None,
+                 image_latents: Optional[torch.Tensor] = None, use_graph: bool = True):
+        num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
+        self.check_inputs(image, height, width)
+        if image_embeddings is None or image_latents is None:
+            raise NotImplementedError("CLIP / VAE image encoding is not part of this build (SURVEY.md §8 f-1, f-3): "
+                                      "pass image_embeddings=[B,1,D] and image_latents=[B,4,h,w]")
+        if output_type != "latent":
+            raise NotImplementedError("temporal VAE decode is not part of this build (SURVEY.md §8 f-1): "
+                                      "use output_type='latent'")
+        batch_size = image_embeddings.shape[0]
+        nvp = num_videos_per_prompt
+        self._guidance_scale = max_guidance_scale
+        do_cfg = self.do_classifier_free_guidance
+        h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
+        B = batch_size * nvp
+        emb = image_embeddings.to("cuda", torch.float32).reshape(batch_size, -1).repeat_interleave(nvp, 0)
+        il = image_latents.to("cuda", torch.float32).repeat_interleave(nvp, 0)
+        if do_cfg:
+            emb = torch.cat([torch.zeros_like(emb), emb])
+            il = torch.cat([torch.zeros_like(il), il])
+        il = il.unsqueeze(1).repeat(1, num_frames, 1, 1, 1)  # :196
+        if bbox_images is not None:  # :199-206
+            cond = self._encode_vae_condition(bbox_images, nvp, do_cfg)
+            il[:, 0:num_cond_bbox_frames] = cond[:, 0:num_cond_bbox_frames]
+            il[:, -1] = cond[:, -1]
+        ids = torch.tensor([[fps - 1, motion_bucket_id, noise_aug_strength]], dtype=torch.float32).repeat(B, 1)
+        if do_cfg:
+            ids = torch.cat([ids, ids])
+        self.scheduler.set_timesteps(num_inference_steps)
+        timesteps = self.scheduler.timesteps
+        if latents is None:
+            latents = torch.randn((B, num_frames, 4, h, w), generator=generator, dtype=torch.float32,
+                                  device=generator.device if generator is not None else "cpu")
+        latents = latents.to("cuda", torch.float32) * self.scheduler.init_noise_sigma
+        guidance = torch.linspace(min_guidance_scale, max_guidance_scale, num_frames)  # :249
+
+        key = (B, num_frames, h, w, do_cfg, num_inference_steps, use_graph)
+        st = self._steps.get(key)
+        if st is None:
+            st = DenoiseStep(self.unet, None, B, num_frames, h, w, do_cfg, 1.0, use_graph)
+            st.set_schedule(self.scheduler.sigmas, timesteps)
+            st.capture()
+            self._steps[key] = st
+        st.latents.copy_(latents)
+        st.image_latents.copy_(il)
+        st.ehs.copy_(emb)
+        st.added_time_ids.copy_(ids.to("cuda"))
+        st.guidance.copy_(guidance.to("cuda"))
+        for i, t in enumerate(timesteps):
+            st.step(i)
+            if callback_on_step_end is not None:
+                kw = {k: st.latents for k in callback_on_step_end_tensor_inputs if k == "latents"}
+                out = callback_on_step_end(self, i, t, kw)
+                if out and "latents" in out:
+                    st.latents.copy_(out["latents"])
+        frames = st.latents.clone()
+        if not return_dict:
+            return frames
+        return StableVideoDiffusionPipelineOutput(frames=frames)

@@ -127,3 +127,25 @@ def sample_loop(unet, controlnet, inputs, num_steps=25, conditioning_scale=1.0, 
         if trace is not None:
             trace.append(latents.clone())
     return latents
+
+
+def sample_loop_bbox_predictor(unet, inputs, num_steps=25, num_cond_bbox_frames=3, trace=None):
+    """/root/reference/src/ctrlv/pipelines/pipeline_video_diffusion.py:196-293 with precomputed
+    conditioning: the plain SVD sampler of the bbox-predictor stage.  The repeated image latents are
+    overwritten by the bbox-frame latents for the first `num_cond_bbox_frames` frames and the last
+    frame (:200-206; the CFG-uncond half receives the zeros of `_encode_vae_condition`)."""
+    sch = EulerDiscreteSchedulerOracle()
+    sch.set_timesteps(num_steps)
+    dev = inputs["latents"].device
+    image_latents = inputs["image_latents"].clone()
+    cond = inputs["cond_em"]
+    image_latents[:, 0:num_cond_bbox_frames] = cond[:, 0:num_cond_bbox_frames]
+    image_latents[:, -1] = cond[:, -1]
+    latents = inputs["latents"] * sch.init_noise_sigma
+    gs = inputs["guidance"].view(1, -1, 1, 1, 1).to(dev)
+    for t in sch.timesteps:
+        latents = denoise_step(unet, None, sch, latents, t, image_latents, inputs["image_embeddings"],
+                               inputs["added_time_ids"], None, gs)
+        if trace is not None:
+            trace.append(latents.clone())
+    return latents

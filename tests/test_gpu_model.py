@@ -129,6 +129,63 @@ def test_pipeline_loop_matches_oracle_loop(order):
     assert torch.equal(res[False], res[True])  # graph replay == eager launches, bit for bit
 
 
+def test_bbox_predictor_pipeline_matches_oracle_loop(tiny):
+    """VideoDiffusionPipeline (plain SVD sampler + conditioning-frame overwrite,
+    pipeline_video_diffusion.py:196-293) against the oracle loop, teacher-forced per step."""
+    from ctrlv_b200 import pipeline
+    from oracle import sampling as S
+    from oracle import svd_oracle as O
+    ou, _, mu, _ = tiny
+    T, h, w, steps = 5, 16, 8, 25
+    inp = S.make_inputs(T=T, h=h, w=w, xdim=O.TINY_CONFIG["cross_attention_dim"], device=dev)
+    trace = []
+    with torch.no_grad():
+        S.sample_loop_bbox_predictor(ou, inp, num_steps=steps, num_cond_bbox_frames=2, trace=trace)
+    pipe = pipeline.VideoDiffusionPipeline(unet=mu)
+    out = pipe(bbox_images=inp["cond_em_cond"], height=h * 8, width=w * 8, num_frames=T,
+               num_inference_steps=steps, latents=inp["latents"].clone(), output_type="latent",
+               image_embeddings=inp["image_embeds_cond"], image_latents=inp["image_latents_cond"],
+               num_cond_bbox_frames=2)
+    assert tuple(out.frames.shape) == (1, T, 4, h, w) and torch.isfinite(out.frames).all()
+    st = next(iter(pipe._steps.values()))
+    sch = S.EulerDiscreteSchedulerOracle(); sch.set_timesteps(steps)
+    prevs = [inp["latents"] * sch.init_noise_sigma] + trace[:-1]
+    for i in range(steps):
+        st.latents.copy_(prevs[i]); st.step(i)
+        assert rel(st.latents, trace[i]) < 1e-2, i
+    # without bbox frames the pipeline is the stock SVD sampler: image latents repeated over T
+    out2 = pipe(height=h * 8, width=w * 8, num_frames=T, num_inference_steps=steps,
+                latents=inp["latents"].clone(), output_type="latent",
+                image_embeddings=inp["image_embeds_cond"], image_latents=inp["image_latents_cond"])
+    assert not torch.equal(out2.frames, out.frames)
+
+
+def test_checkpoint_roundtrip_from_pretrained(tiny, tmp_path):
+    """save_pretrained -> from_pretrained (diffusers directory layout, the call of
+    tools/eval_video_controlnet.py:114-118) reproduces the networks bit for bit."""
+    from ctrlv_b200 import models
+    _, _, mu, mc = tiny
+    mu.save_pretrained(str(tmp_path), subfolder="unet")
+    mc.save_pretrained(str(tmp_path), subfolder="controlnet", max_shard_bytes=1 << 20)
+    mu2 = models.UNetSpatioTemporalConditionModel.from_pretrained(str(tmp_path), subfolder="unet")
+    mc2 = models.ControlNetModel.from_pretrained(str(tmp_path), subfolder="controlnet")
+    assert mu2.cfg == mu.cfg and mc2.cfg == mc.cfg
+    for a, b in ((mu, mu2), (mc, mc2)):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    inp, x = _inputs(3, 8, 16, 3.0)
+    t = torch.tensor(0.27, device=dev)
+    kw = dict(timestep=t, encoder_hidden_states=inp["image_embeddings"], added_time_ids=inp["added_time_ids"])
+    d1, m1 = mc(x, control_cond=inp["cond_em"], return_dict=False, **kw)
+    d2, m2 = mc2(x, control_cond=inp["cond_em"], return_dict=False, **kw)
+    assert torch.equal(m1, m2) and all(torch.equal(a, b) for a, b in zip(d1, d2))
+    y1 = mu(sample=x, down_block_additional_residuals=d1, mid_block_additional_residuals=m1, return_dict=False, **kw)[0]
+    y2 = mu2(sample=x, down_block_additional_residuals=d2, mid_block_additional_residuals=m2, return_dict=False, **kw)[0]
+    assert torch.equal(y1, y2)
+    with pytest.raises(OSError):
+        models.ControlNetModel.from_pretrained(str(tmp_path), subfolder="nope")
+
+
 def test_pipeline_errors():
     from ctrlv_b200 import pipeline, models
     from oracle import svd_oracle as O

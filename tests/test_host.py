@@ -125,3 +125,52 @@ def test_geglu_interleave_and_conv_packing():
     assert p.shape == (5, 63) and torch.equal(p[:, 7 * 4:7 * 5], cw[:, :, 1, 1])  # tap (1,1) = centre
     tw = torch.randn(5, 7, 3, 1, 1)
     assert torch.equal(models._conv_t3(tw)[:, 7:14], tw[:, :, 1, 0, 0])
+
+
+def test_safetensors_reader_writer_roundtrip_and_interop(tmp_path):
+    """f-4: the self-contained safetensors codec against the `safetensors` package (both ways)."""
+    import torch
+    from ctrlv_b200 import checkpoint
+    g = torch.Generator().manual_seed(0)
+    sd = {"a.weight": torch.randn(3, 5, generator=g), "b.bias": torch.randn(7, generator=g).to(torch.bfloat16),
+          "c": torch.randn(2, 2, 2, generator=g).to(torch.float16), "n": torch.arange(6).reshape(2, 3),
+          "scalar": torch.tensor(1.5), "empty": torch.zeros(0, 4)}
+    p = str(tmp_path / "x.safetensors")
+    checkpoint.write_safetensors(p, sd, {"format": "pt"})
+    back = checkpoint.read_safetensors(p)
+    assert set(back) == set(sd)
+    for k in sd:
+        assert back[k].dtype == sd[k].dtype and torch.equal(back[k], sd[k]), k
+    st = pytest.importorskip("safetensors.torch")
+    lib = st.load_file(p)
+    for k in sd:
+        assert torch.equal(lib[k], sd[k]), k
+    p2 = str(tmp_path / "y.safetensors")
+    st.save_file({k: v.contiguous() for k, v in sd.items()}, p2)
+    back2 = checkpoint.read_safetensors(p2)
+    for k in sd:
+        assert torch.equal(back2[k], sd[k]), k
+    with open(str(tmp_path / "bad.safetensors"), "wb") as f:
+        f.write(b"\xff" * 16)
+    with pytest.raises(ValueError):
+        checkpoint.read_safetensors(str(tmp_path / "bad.safetensors"))
+
+
+@pytest.mark.parametrize("mode", ["single", "sharded", "bin", "variant"])
+def test_diffusers_dir_layouts(tmp_path, mode):
+    import torch
+    from ctrlv_b200 import checkpoint
+    sd = {f"down_blocks.{i}.w": torch.full((4, 4), float(i)) for i in range(5)}
+    cfg = {"in_channels": 8, "block_out_channels": (64, 128)}
+    kw = dict(single={}, sharded=dict(max_shard_bytes=100), bin=dict(safe_serialization=False),
+              variant=dict(variant="fp16"))[mode]
+    checkpoint.save_diffusers_dir(str(tmp_path), cfg, sd, "ControlNetModel", subfolder="controlnet", **kw)
+    names = sorted(os.listdir(str(tmp_path / "controlnet")))
+    assert "config.json" in names
+    if mode == "sharded":
+        assert any(n.endswith(".index.json") for n in names) and sum(n.endswith(".safetensors") for n in names) > 1
+    config, back = checkpoint.load_diffusers_dir(str(tmp_path), "controlnet", kw.get("variant"))
+    assert config["_class_name"] == "ControlNetModel" and config["block_out_channels"] == [64, 128]
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    with pytest.raises(OSError):
+        checkpoint.load_diffusers_dir(str(tmp_path), "unet")
