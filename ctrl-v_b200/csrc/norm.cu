@@ -1,6 +1,8 @@
 // GroupNorm (statistics + apply [+ SiLU], one or two channel-concatenated sources) and LayerNorm
 // on channels-last bf16 rows.  HBM-bound kernels: 16-byte vector loads/stores, fp32 statistics,
 // deterministic two-stage reduction (no float atomics in global memory).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/ctrlv_b200.h"
 
@@ -91,37 +93,39 @@ __global__ void __launch_bounds__(512, 3) gn_apply_kernel(const bf16* __restrict
   pdl_wait();
   pdl_trigger();
   __shared__ float mean_s[kGroups], rstd_s[kGroups];
+  __shared__ double wsum[16][kGroups][2];
   const int C = C0 + C1;
   const int vpr = C >> 3;
   const int cg = C / kGroups;
   const int unit = blockIdx.x / blocks_per_unit;
   const int blk = blockIdx.x % blocks_per_unit;
   const int tid = threadIdx.x;
-  // deterministic reduction of the split partials: 8 lanes per group, each sums its strided
-  // share in a fixed order (fp64), then a fixed xor tree; works for any block size >= 32
-  for (int base_g = 0; base_g < kGroups; base_g += blockDim.x / 8) {
-    const int gi = base_g + tid / 8;
-    const int sl = tid & 7;
+  // deterministic reduction of the split partials: warp w sums splits w, w+nwarps, ... (lane =
+  // group, one coalesced 256-byte record per split, loads unrolled so they overlap), then group g
+  // adds the warp sums in warp order (fp64)
+  {
+    const int nwarps = blockDim.x >> 5;
+    const int wid = tid >> 5, lane = tid & 31;
+    const float2* rec = reinterpret_cast<const float2*>(partial) + (size_t)unit * nsplit * kGroups + lane;
     double s = 0.0, q = 0.0;
-    if (gi < kGroups && tid / 8 < (int)blockDim.x / 8) {
-      const float* pp = partial + (size_t)unit * nsplit * (kGroups * 2) + gi * 2;
-      for (int i = sl; i < nsplit; i += 8) {
-        s += (double)pp[(size_t)i * kGroups * 2];
-        q += (double)pp[(size_t)i * kGroups * 2 + 1];
-      }
+#pragma unroll 4
+    for (int i = wid; i < nsplit; i += nwarps) {
+      const float2 v = __ldg(rec + (size_t)i * kGroups);
+      s += (double)v.x;
+      q += (double)v.y;
     }
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if (gi < kGroups && sl == 0 && tid / 8 < (int)blockDim.x / 8) {
+    wsum[wid][lane][0] = s;
+    wsum[wid][lane][1] = q;
+    __syncthreads();
+    if (tid < kGroups) {
+      s = 0.0; q = 0.0;
+      for (int w = 0; w < nwarps; ++w) { s += wsum[w][tid][0]; q += wsum[w][tid][1]; }
       const double cnt = (double)rows_per_unit * cg;
       const double mean = s / cnt;
       double var = q / cnt - mean * mean;
       if (var < 0.0) var = 0.0;
-      mean_s[gi] = (float)mean;
-      rstd_s[gi] = (float)(1.0 / sqrt(var + (double)eps));
+      mean_s[tid] = (float)mean;
+      rstd_s[tid] = (float)(1.0 / sqrt(var + (double)eps));
     }
   }
   __syncthreads();
@@ -278,22 +282,41 @@ extern "C" int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, i
   if (rpar > rows_per_unit) rpar = rows_per_unit;
   const int nwork = vpr * rpar;
   const int nthreads = (nwork + 31) / 32 * 32;
-  // split each unit so that the grid has a few hundred blocks
-  int nsplit = (592 + n_units - 1) / n_units;
-  const int max_by_rows = (rows_per_unit + rpar - 1) / rpar;
-  if (nsplit > max_by_rows) nsplit = max_by_rows;
-  if (nsplit > kMaxSplit) nsplit = kMaxSplit;
-  if (nsplit < 1) nsplit = 1;
-  int rows_per_split = (rows_per_unit + nsplit - 1) / nsplit;
-  nsplit = (rows_per_unit + rows_per_split - 1) / rows_per_split;
-  float* partial = reinterpret_cast<float*>(workspace);
+  // Both kernels do uniform work per block: size each grid to ONE full wave of resident blocks
+  // (a 1.04-wave grid costs two waves).  Statistics splits and apply blocks are independent.
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    CTRLV_CUDA(cudaGetDevice(&dev));
+    CTRLV_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
   const size_t st_smem = ((size_t)nwork * 8 + (size_t)vpr * 8) * sizeof(float);
+  int occ_stats = 1, occ_apply = 1;
+  CTRLV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_stats, gn_stats_kernel, nthreads, st_smem));
+  CTRLV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_apply, gn_apply_kernel, nthreads, 0));
+  if (occ_stats < 1) occ_stats = 1;
+  if (occ_apply < 1) occ_apply = 1;
+  const int max_by_rows = (rows_per_unit + rpar - 1) / rpar;
+  auto per_unit = [&](int slots) {
+    int n = slots / n_units;  // floor: never spill into a second wave
+    if (n > max_by_rows) n = max_by_rows;
+    if (n > kMaxSplit) n = kMaxSplit;
+    if (n < 1) n = 1;
+    return n;
+  };
+  int nsplit = per_unit(occ_stats * n_sm);
+  const int rows_per_split = (rows_per_unit + nsplit - 1) / nsplit;
+  nsplit = (rows_per_unit + rows_per_split - 1) / rows_per_split;
+  int nblk = per_unit(occ_apply * n_sm);
+  const int rows_per_blk = (rows_per_unit + nblk - 1) / nblk;
+  nblk = (rows_per_unit + rows_per_blk - 1) / rows_per_blk;
+  float* partial = reinterpret_cast<float*>(workspace);
   CTRLV_CUDA(launch_pdl(gn_stats_kernel, dim3(n_units * nsplit), dim3(nthreads), st_smem, stream,
                         reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1,
                         rows_per_unit, rows_per_split, nsplit, nwork, partial));
-  CTRLV_CUDA(launch_pdl(gn_apply_kernel, dim3(n_units * nsplit), dim3(nthreads), (size_t)0, stream,
+  CTRLV_CUDA(launch_pdl(gn_apply_kernel, dim3(n_units * nblk), dim3(nthreads), (size_t)0, stream,
                         reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1,
-                        rows_per_unit, nsplit, nsplit, nwork, (const float*)partial, gamma, beta, eps, silu,
+                        rows_per_unit, nblk, nsplit, nwork, (const float*)partial, gamma, beta, eps, silu,
                         reinterpret_cast<bf16*>(out)));
   return CTRLV_OK;
 }
