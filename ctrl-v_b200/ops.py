@@ -333,3 +333,58 @@ def nhwc_to_nchw(src: torch.Tensor, frames: int, Cc: int, H: int, W: int, dtype=
                                    Cc, H * W, 1 if dtype == torch.float32 else 0, out.data_ptr(), _stream()),
           "ctrlv_nhwc_to_nchw")
     return out
+
+
+# ---- temporal VAE glue ---------------------------------------------------------
+def conv3x3_s2_pad01(x: torch.Tensor, frames: int, H: int, W: int, w: torch.Tensor, **kw) -> torch.Tensor:
+    """diffusers `Downsample2D(padding=0)` of the VAE encoder: F.pad(x, (0,1,0,1)) then a 3x3 stride-2
+    conv without padding, i.e. out(oy,ox) = sum_k w[ky][kx] x(2oy+ky, 2ox+kx).  Described to the
+    generic implicit GEMM as four parity sub-lattices: tap k -> parity k&1, lattice offset k>>1; the
+    out-of-range row/column of the last tap is the TMA zero fill."""
+    from ._lib import IgemmDesc
+    _req(x, BF16, "x"); _req(w, BF16, "w")
+    assert x.is_contiguous() and w.is_contiguous() and H % 2 == 0 and W % 2 == 0
+    C0 = x.shape[1]
+    N = w.shape[0]
+    assert C0 % 64 == 0 and w.shape[1] == 9 * C0 and x.shape[0] == frames * H * W
+    Ho, Wo = H // 2, W // 2
+    kw = _alloc_out(frames * Ho * Wo, N, False, kw)
+    d = IgemmDesc()
+    d.nsrc = 4
+    for py in range(2):
+        for px in range(2):
+            sr = d.src[py * 2 + px]
+            sr.ptr = x.data_ptr() + ((py * W + px) * C0) * 2
+            sr.C, sr.sx, sr.sy, sr.sz = C0, 2 * C0, 2 * C0 * W, C0 * W * H
+    d.X, d.Y, d.Z = Wo, Ho, frames
+    d.nseg = 9
+    for t in range(9):
+        ky, kx = t // 3, t % 3
+        sg = d.seg[t]
+        sg.src, sg.c0, sg.nchunk, sg.dx, sg.dy, sg.dz = (ky & 1) * 2 + (kx & 1), 0, C0 // 64, kx >> 1, ky >> 1, 0
+    d.W, d.N, d.K, d.bn = w.data_ptr(), N, 9 * C0, 0
+    d.ep = make_ep(**kw)
+    check(lib().ctrlv_igemm(C.byref(d), _stream()), "ctrlv_igemm")
+    return kw["out"] if kw.get("out") is not None else kw["out_f32"]
+
+
+def softmax_rows(scores: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(scores, torch.float32, "scores")
+    M, N = scores.shape
+    assert scores.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), dtype=BF16, device="cuda")
+    check(lib().ctrlv_softmax_rows(scores.data_ptr(), scores.stride(0), M, N, scale, out.data_ptr(), out.stride(0),
+                                   _stream()), "ctrlv_softmax_rows")
+    return out
+
+
+def time_conv_out(x: torch.Tensor, B: int, T: int, H: int, W: int, Cc: int, w: torch.Tensor,
+                  bias: torch.Tensor) -> torch.Tensor:
+    """x [B*T*H*W, ld] fp32 channels-last -> [B*T, Cc, H, W] fp32 after Conv3d(Cc, Cc, (3,1,1))."""
+    _req(x, torch.float32, "x"); _req(w, torch.float32, "w"); _req(bias, torch.float32, "bias")
+    assert x.stride(1) == 1 and x.shape[0] == B * T * H * W and w.is_contiguous() and w.numel() == Cc * Cc * 3
+    out = torch.empty((B * T, Cc, H, W), dtype=torch.float32, device="cuda")
+    check(lib().ctrlv_time_conv_out(x.data_ptr(), x.stride(0), B, T, H * W, Cc, w.data_ptr(), bias.data_ptr(),
+                                    out.data_ptr(), _stream()), "ctrlv_time_conv_out")
+    return out

@@ -197,6 +197,20 @@ int ctrlv_nchw_to_nhwc(const void* src, int32_t src_is_f32, int32_t frames, int3
 int ctrlv_nhwc_to_nchw(const void* src, int32_t src_is_f32, int64_t ld, int32_t frames, int32_t C,
                        int32_t HW, int32_t out_is_f32, void* out, void* stream);
 
+/* ---- temporal VAE glue (diffusers AutoencoderKLTemporalDecoder, reached from
+ * pipeline_video_control.py:84,235,346-347) -------------------------------------------------- */
+
+/* probs[m][n] = softmax_n(scale * scores[m][n]) (fp32 in, bf16 out): the softmax between the two
+ * GEMMs of the VAE mid-block attention (one head of width 512, F.scaled_dot_product_attention). */
+int ctrlv_softmax_rows(const float* scores, int64_t ld_scores, int32_t M, int32_t N, float scale,
+                       void* probs, int64_t ld_probs, void* stream);
+
+/* TemporalDecoder.time_conv_out = Conv3d(C, C, (3,1,1), padding (1,0,0)), C <= 4, fused with the
+ * channels-last -> NCHW conversion: x [B][T][HW][ld] fp32 (first C columns), w [C][C][3] fp32,
+ * out [B*T][C][HW] fp32. */
+int ctrlv_time_conv_out(const float* x, int32_t ld, int32_t B, int32_t T, int32_t HW, int32_t C,
+                        const float* w, const float* bias, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

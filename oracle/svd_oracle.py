@@ -145,10 +145,11 @@ class AlphaBlender(nn.Module):
 class SpatioTemporalResBlock(nn.Module):
     def __init__(self, in_channels: int, out_channels: int, temb_channels: int, eps: float = 1e-6,
                  merge_factor: float = 0.5, merge_strategy: str = "learned_with_images",
-                 switch_spatial_to_temporal_mix: bool = False):
+                 switch_spatial_to_temporal_mix: bool = False, temporal_eps: Optional[float] = None):
         super().__init__()
         self.spatial_res_block = ResnetBlock2D(in_channels, out_channels, temb_channels, eps)
-        self.temporal_res_block = TemporalResnetBlock(out_channels, out_channels, temb_channels, eps)
+        self.temporal_res_block = TemporalResnetBlock(out_channels, out_channels, temb_channels,
+                                                      temporal_eps if temporal_eps is not None else eps)
         self.time_mixer = AlphaBlender(merge_factor, merge_strategy, switch_spatial_to_temporal_mix)
 
     def forward(self, hidden_states, temb, image_only_indicator):

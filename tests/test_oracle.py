@@ -159,3 +159,45 @@ def test_golden_fixture():
     for k in ("noise_pred", "latents_after_step0", "ctrl_down_norms", "ctrl_mid"):
         err = (got[k] - want[k]).norm() / want[k].norm()
         assert err < 1e-4, (k, float(err))
+
+
+def test_vae_oracle_structure_pins():
+    """f-1 oracle (AutoencoderKLTemporalDecoder restatement): parameter counts of the SVD VAE config
+    (encoder = the Stable Diffusion VAE encoder, 34,163,592; whole module 97,742,847) and the
+    diffusers key families a real checkpoint carries."""
+    from oracle import vae_oracle as V
+    with torch.device("meta"):
+        m = V.AutoencoderKLTemporalDecoder()
+    assert sum(p.numel() for p in m.encoder.parameters()) == 34_163_592
+    assert sum(p.numel() for p in m.quant_conv.parameters()) == 72
+    assert sum(p.numel() for p in m.parameters()) == 97_742_847
+    keys = set(m.state_dict())
+    for k in ("encoder.down_blocks.0.downsamplers.0.conv.weight", "encoder.mid_block.attentions.0.group_norm.weight",
+              "encoder.mid_block.attentions.0.to_out.0.bias", "decoder.mid_block.resnets.1.temporal_res_block.conv2.weight",
+              "decoder.up_blocks.3.resnets.2.time_mixer.mix_factor", "decoder.up_blocks.2.upsamplers.0.conv.bias",
+              "decoder.time_conv_out.weight", "quant_conv.bias"):
+        assert k in keys, k
+    assert not any(k.startswith("post_quant_conv") or "time_emb_proj" in k for k in keys)
+    assert "decoder.up_blocks.3.upsamplers.0.conv.weight" not in keys
+
+
+def test_vae_oracle_algebra():
+    """Temporal layers only mix frames of one clip; with sigmoid(mix)=0 blend the decoder is per-frame."""
+    from oracle import vae_oracle as V
+    torch.manual_seed(0)
+    m = V.AutoencoderKLTemporalDecoder(**V.TINY_VAE_CONFIG).eval()
+    z = torch.randn(4, 4, 6, 6)
+    with torch.no_grad():
+        a = m.decode(z, num_frames=2)                       # two clips of two frames
+        b = torch.cat([m.decode(z[:2], 2), m.decode(z[2:], 2)])
+        assert torch.allclose(a, b, atol=1e-5)
+        x = torch.rand(2, 3, 16, 16) * 2 - 1
+        assert m.encode_mode(x).shape == (2, 4, 8, 8)
+        f = V.decode_latents(m, z.reshape(1, 4, 4, 6, 6), 4, 2)
+        assert f.shape == (1, 3, 4, 12, 12)
+        # switch_spatial_to_temporal_mix: alpha = 1 - sigmoid(mix); mix -> +inf keeps only the temporal branch
+        blk = m.decoder.mid_block.resnets[0]
+        blk.time_mixer.mix_factor.data.fill_(-30.0)         # alpha -> 1: spatial branch only
+        h = torch.randn(2, V.TINY_VAE_CONFIG["block_out_channels"][-1], 4, 4)
+        ioi = torch.zeros(1, 2)
+        assert torch.allclose(blk(h, None, ioi), blk.spatial_res_block(h, None), atol=1e-5)
