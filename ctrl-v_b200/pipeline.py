@@ -189,11 +189,12 @@ class StableVideoDiffusionPipelineOutput(SimpleNamespace):
 class StableVideoControlPipeline:
     """Drop-in for ctrlv.pipelines.StableVideoControlPipeline (pipeline_video_control.py:25-360).
 
-    The denoising loop (:298-343) runs on the sm_100a kernels.  The encoders around it — CLIP image
-    embedding (:220), VAE image/condition encode (:235, :84) and the temporal VAE decode (:346) —
-    are the "next" rows of SURVEY.md §8(f) and are NOT built yet: pass `image_embeddings=` and
-    `image_latents=` (and 4-channel `cond_images` latents, :86-88) and use `output_type="latent"`;
-    asking for pixel-space encode/decode raises."""
+    The denoising loop (:298-343) runs on the sm_100a kernels.  With a `vae`
+    (`ctrlv_b200.vae.AutoencoderKLTemporalDecoder`) the pipeline also encodes
+    3-channel bbox frames (:84) and the conditioning image (:235) and decodes the result (:346-347,
+    `output_type` "pt" / "np" / "pil").  The CLIP image encoder (:220, row f-3) is not built: pass
+    `image_embeddings=[B, 1, D]`.  Without a `vae`, pass `image_latents=` and 4-channel `cond_images`
+    latents (:86-88) and use `output_type="latent"`."""
 
     def __init__(self, vae=None, image_encoder=None, unet: UNetSpatioTemporalConditionModel = None,
                  controlnet: ControlNetModel = None, scheduler: EulerDiscreteScheduler = None,
@@ -203,7 +204,7 @@ class StableVideoControlPipeline:
         self.vae, self.image_encoder, self.feature_extractor = vae, image_encoder, feature_extractor
         self.unet, self.controlnet = unet, controlnet
         self.scheduler = scheduler if scheduler is not None else EulerDiscreteScheduler()
-        self.vae_scale_factor = 8
+        self.vae_scale_factor = (2 ** (len(vae.config.block_out_channels) - 1)) if vae is not None else 8
         self._steps: Dict[tuple, DenoiseStep] = {}
         self._guidance_scale = 1.0
 
@@ -219,14 +220,66 @@ class StableVideoControlPipeline:
             raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
 
     def _encode_vae_condition(self, cond_image, num_videos_per_prompt, do_cfg):  # :71-101
-        if cond_image.shape[2] == 3:
-            raise NotImplementedError("3-channel cond_images need the VAE encoder (SURVEY.md §8 f-1); "
-                                      "pass 4-channel bbox-frame latents")
+        if cond_image.shape[2] == 3:  # frames -> latents through the VAE encoder, `.mode()` (:84)
+            if self.vae is None:
+                raise NotImplementedError("3-channel cond_images need a `vae`; pass 4-channel bbox-frame latents")
+            b, f = cond_image.shape[:2]
+            em = self.vae.encode(cond_image.to("cuda", torch.float32).flatten(0, 1)).latent_dist.mode()
+            cond_image = em.reshape(b, f, *em.shape[1:])
         assert cond_image.shape[2] == 4, "The input tensor should have 3 or 4 channels. 3 for frames and 4 for latents."
         cond_em = cond_image.to("cuda", torch.float32).repeat(num_videos_per_prompt, 1, 1, 1, 1)
         if do_cfg:
             cond_em = torch.cat([torch.zeros_like(cond_em), cond_em])
         return cond_em
+
+    def _encode_vae_image(self, image, height, width, noise_aug_strength, generator):  # :228-241
+        """`image_processor.preprocess` for a tensor in [0, 1] (normalise to [-1, 1]; resizing is not
+        implemented: pass the image at the target size), noise augmentation, VAE `.mode()`."""
+        if self.vae is None:
+            raise NotImplementedError("pass image_latents=[B,4,h,w] or construct the pipeline with a `vae`")
+        if not isinstance(image, torch.Tensor) or image.ndim != 4 or image.shape[1] != 3:
+            raise NotImplementedError("`image` must be a [B, 3, H, W] tensor in [0, 1] (PIL input needs the "
+                                      "image processor, which is not part of this build)")
+        if tuple(image.shape[-2:]) != (height, width):
+            raise NotImplementedError(f"`image` must already be {height}x{width}; resizing is not implemented")
+        image = 2.0 * image.to(torch.float32) - 1.0
+        noise = torch.randn(image.shape, generator=generator, dtype=torch.float32,
+                            device=generator.device if generator is not None else "cpu")
+        image = image.to("cuda") + noise_aug_strength * noise.to("cuda")
+        return self.vae.encode(image).latent_dist.mode()
+
+    def decode_latents(self, latents, num_frames, decode_chunk_size=14):  # diffusers decode_latents (:346)
+        if self.vae is None:
+            raise NotImplementedError("decoding needs a `vae`; use output_type='latent'")
+        from . import vae as _vae
+        return _vae.decode_latents(self.vae, latents, num_frames, decode_chunk_size)
+
+    @staticmethod
+    def tensor2vid(video: torch.Tensor, output_type: str = "np"):
+        """diffusers `tensor2vid` + `VaeImageProcessor.postprocess`: [B, C, T, H, W] in [-1, 1] ->
+        "pt": [B, T, C, H, W] in [0, 1]; "np": [B, T, H, W, C]; "pil": list of lists of PIL images."""
+        if output_type not in ("pt", "np", "pil"):
+            raise ValueError(f"output_type {output_type!r} is not one of 'latent', 'pt', 'np', 'pil'")
+        vid = (video.permute(0, 2, 1, 3, 4) / 2 + 0.5).clamp(0, 1)
+        if output_type == "pt":
+            return vid
+        arr = vid.permute(0, 1, 3, 4, 2).float().cpu().numpy()
+        if output_type == "np":
+            return arr
+        from PIL import Image
+        return [[Image.fromarray((fr * 255).round().astype("uint8")) for fr in clip] for clip in arr]
+
+    def _finish(self, latents, num_frames, decode_chunk_size, output_type, return_dict, clamp=False):
+        if output_type == "latent":
+            frames = latents
+        else:
+            frames = self.decode_latents(latents, num_frames, decode_chunk_size or num_frames)
+            if clamp:  # pipeline_video_diffusion.py:297
+                frames = torch.clamp(frames, -1, 1)
+            frames = self.tensor2vid(frames, output_type)
+        if not return_dict:
+            return frames
+        return StableVideoDiffusionPipelineOutput(frames=frames)
 
     @torch.no_grad()
     def __call__(self, image=None, cond_images: torch.Tensor = None, height: int = 576, width: int = 1024,
@@ -242,12 +295,14 @@ class StableVideoControlPipeline:
                  image_latents: Optional[torch.Tensor] = None, use_graph: bool = True):
         num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
         self.check_inputs(image, cond_images, height, width)
-        if image_embeddings is None or image_latents is None:
-            raise NotImplementedError("CLIP / VAE image encoding is not part of this build (SURVEY.md §8 f-1, f-3): "
-                                      "pass image_embeddings=[B,1,D] and image_latents=[B,4,h,w]")
-        if output_type != "latent":
-            raise NotImplementedError("temporal VAE decode is not part of this build (SURVEY.md §8 f-1): "
+        if image_embeddings is None:
+            raise NotImplementedError("CLIP image encoding is not part of this build (SURVEY.md §8 f-3): "
+                                      "pass image_embeddings=[B,1,D]")
+        if output_type != "latent" and self.vae is None:
+            raise NotImplementedError("decoding needs a `vae` (ctrlv_b200.vae.AutoencoderKLTemporalDecoder); "
                                       "use output_type='latent'")
+        if image_latents is None:
+            image_latents = self._encode_vae_image(image, height, width, noise_aug_strength, generator)
         batch_size = image_embeddings.shape[0]
         nvp = num_videos_per_prompt
         self._guidance_scale = max_guidance_scale  # :217 — CFG on iff > 1
@@ -296,10 +351,7 @@ class StableVideoControlPipeline:
                 out = callback_on_step_end(self, i, t, kw)
                 if out and "latents" in out:
                     st.latents.copy_(out["latents"])
-        frames = st.latents.clone()
-        if not return_dict:
-            return frames
-        return StableVideoDiffusionPipelineOutput(frames=frames)
+        return self._finish(st.latents.clone(), num_frames, decode_chunk_size, output_type, return_dict)
 
 
 class VideoDiffusionPipeline(StableVideoControlPipeline):
@@ -307,8 +359,8 @@ class VideoDiffusionPipeline(StableVideoControlPipeline):
     plain SVD sampler of the bbox-predictor stage.  Same loop as the control
     pipeline without the ControlNet (:259-293); the conditioning-frame overwrite (:200-206) puts the
     bbox-frame latents of the first `num_cond_bbox_frames` frames and of the last frame in place of
-    the repeated image latents.  `bbox_images` must be 4-channel latents [B, T, 4, h, w] until the VAE
-    encoder row (f-1) is built; CLIP/VAE encodes are passed in as for the control pipeline."""
+    the repeated image latents.  `bbox_images` are frames [B, T, 3, H, W] (encoded by the `vae`) or
+    4-channel latents [B, T, 4, h, w]; decoded frames are clamped to [-1, 1] (:297)."""
 
     def __init__(self, vae=None, image_encoder=None, unet: UNetSpatioTemporalConditionModel = None,
                  scheduler: EulerDiscreteScheduler = None, feature_extractor=None):
@@ -333,12 +385,14 @@ class VideoDiffusionPipeline(StableVideoControlPipeline):
                  image_latents: Optional[torch.Tensor] = None, use_graph: bool = True):
         num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
         self.check_inputs(image, height, width)
-        if image_embeddings is None or image_latents is None:
-            raise NotImplementedError("CLIP / VAE image encoding is not part of this build (SURVEY.md §8 f-1, f-3): "
-                                      "pass image_embeddings=[B,1,D] and image_latents=[B,4,h,w]")
-        if output_type != "latent":
-            raise NotImplementedError("temporal VAE decode is not part of this build (SURVEY.md §8 f-1): "
+        if image_embeddings is None:
+            raise NotImplementedError("CLIP image encoding is not part of this build (SURVEY.md §8 f-3): "
+                                      "pass image_embeddings=[B,1,D]")
+        if output_type != "latent" and self.vae is None:
+            raise NotImplementedError("decoding needs a `vae` (ctrlv_b200.vae.AutoencoderKLTemporalDecoder); "
                                       "use output_type='latent'")
+        if image_latents is None:
+            image_latents = self._encode_vae_image(image, height, width, noise_aug_strength, generator)
         batch_size = image_embeddings.shape[0]
         nvp = num_videos_per_prompt
         self._guidance_scale = max_guidance_scale
@@ -385,7 +439,4 @@ class VideoDiffusionPipeline(StableVideoControlPipeline):
                 out = callback_on_step_end(self, i, t, kw)
                 if out and "latents" in out:
                     st.latents.copy_(out["latents"])
-        frames = st.latents.clone()
-        if not return_dict:
-            return frames
-        return StableVideoDiffusionPipelineOutput(frames=frames)
+        return self._finish(st.latents.clone(), num_frames, decode_chunk_size, output_type, return_dict, clamp=True)

@@ -156,3 +156,62 @@ def test_full_architecture_decode_and_encode():
         wz = ov.encode_mode(x)
     gz = mv.encode(x).latent_dist.mode()
     assert rel(gz, wz) < 2e-2, rel(gz, wz)
+
+
+def test_pipeline_pixels_in_pixels_out_psnr():
+    """North-star parity criterion: decoded frames after the 25-step loop, new path vs
+    the fp32 oracle chain (VAE encode -> ControlNet+UNet Euler loop -> temporal VAE decode), PSNR >= 40 dB.
+    Pixel-space bbox frames and conditioning image go in, frames come out (pipeline_video_control.py:84,235,346)."""
+    from ctrlv_b200 import models, pipeline
+    from oracle import sampling as S
+    from oracle import svd_oracle as O
+    from oracle import vae_oracle as V
+    ov, mv = _pair(dict(V.TINY_VAE_CONFIG))           # two levels: pixels = 2 x latent
+    over = dict(O.TINY_CONFIG)
+    torch.manual_seed(0)
+    ou = O.UNetSpatioTemporalConditionModel(**over).to(dev).eval()
+    oc = O.ControlNetModel(**over)
+    O.randomize_zero_convs(oc)
+    oc = oc.to(dev).eval()
+    mu = models.UNetSpatioTemporalConditionModel(state_dict=ou.state_dict(), **over)
+    mc = models.ControlNetModel(state_dict=oc.state_dict(), **over)
+    T, h, w, steps, aug = 4, 16, 16, 25, 0.02
+    H, W = 2 * h, 2 * w
+    g = torch.Generator("cpu").manual_seed(7)
+    image = torch.rand(1, 3, H, W, generator=g)
+    bbox = torch.rand(1, T, 3, H, W, generator=g) * 2 - 1
+    emb = torch.randn(1, 1, over["cross_attention_dim"], generator=g)
+    lat0 = torch.randn(1, T, 4, h, w, generator=g)
+    # oracle chain
+    with torch.no_grad():
+        noise = torch.randn(image.shape, generator=torch.Generator("cpu").manual_seed(11))
+        il = ov.encode_mode((2 * image - 1 + aug * noise).to(dev))
+        ce = ov.encode_mode(bbox.flatten(0, 1).to(dev)).reshape(1, T, 4, h, w)
+        ilr = il.unsqueeze(1).repeat(1, T, 1, 1, 1)
+        inp = dict(latents=lat0.to(dev), image_latents=torch.cat([torch.zeros_like(ilr), ilr]),
+                   image_embeddings=torch.cat([torch.zeros_like(emb), emb]).to(dev),
+                   cond_em=torch.cat([torch.zeros_like(ce), ce]),
+                   added_time_ids=torch.tensor([[6.0, 127.0, aug]] * 2, device=dev),
+                   guidance=torch.linspace(1.0, 3.0, T, device=dev))
+        lat_o = S.sample_loop(ou, oc, inp, num_steps=steps)
+        want = V.decode_latents(ov, lat_o, T, T)
+        want = (want.permute(0, 2, 1, 3, 4) / 2 + 0.5).clamp(0, 1)
+    # new path: pixels in, pixels out
+    pipe = pipeline.StableVideoControlPipeline(vae=mv, unet=mu, controlnet=mc)
+    assert pipe.vae_scale_factor == 2
+    out = pipe(image=image, cond_images=bbox, height=H, width=W, num_frames=T, num_inference_steps=steps,
+               latents=lat0.clone(), output_type="pt", image_embeddings=emb, noise_aug_strength=aug,
+               generator=torch.Generator("cpu").manual_seed(11))
+    got = out.frames
+    assert got.shape == (1, T, 3, H, W) and float(got.min()) >= 0 and float(got.max()) <= 1
+    mse = float(((got.float() - want.float()) ** 2).mean())
+    p = 10 * math.log10(1.0 / max(mse, 1e-30))
+    assert p >= 40.0, p
+    arr = pipe(image=image, cond_images=bbox, height=H, width=W, num_frames=T, num_inference_steps=steps,
+               latents=lat0.clone(), output_type="np", image_embeddings=emb, noise_aug_strength=aug,
+               generator=torch.Generator("cpu").manual_seed(11), decode_chunk_size=2).frames
+    assert arr.shape == (1, T, H, W, 3)
+    lat = pipe(image=image, cond_images=bbox, height=H, width=W, num_frames=T, num_inference_steps=steps,
+               latents=lat0.clone(), output_type="latent", image_embeddings=emb, noise_aug_strength=aug,
+               generator=torch.Generator("cpu").manual_seed(11)).frames
+    assert rel(lat, lat_o) < 2e-2, rel(lat, lat_o)
