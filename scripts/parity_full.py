@@ -89,6 +89,30 @@ def main(steps=25, T=14, h=40, w=64):
         tf.append(rel(st.latents, trace[i]))
     res["teacher_forced_per_step_rel_l2"] = tf
     log("teacher-forced per-step latent rel_l2:", [f"{r:.2e}" for r in tf], "max", max(tf))
+    # --- decoded-frame PSNR after the 25 steps (north-star criterion): full-size temporal VAE, random
+    # init; new chain (sm_100a loop + sm_100a decode) vs oracle chain (fp32 loop + fp32 decode)
+    import math
+    from oracle import vae_oracle as V
+    from ctrlv_b200 import vae
+    del ou, oc
+    torch.cuda.empty_cache()
+    torch.manual_seed(3)
+    ov = V.AutoencoderKLTemporalDecoder().to(dev).eval()
+    mv = vae.AutoencoderKLTemporalDecoder(state_dict=ov.state_dict())
+    # random-init UNets do not denoise: bring the final latents to the scale a VAE expects so that the
+    # decode is exercised in its working range (same factor on both chains)
+    k = float(0.18215 / ofinal.std())
+    with torch.no_grad():
+        want = V.decode_latents(ov, ofinal * k, T, T)
+    got = vae.decode_latents(mv, out.frames * k, T, T)
+    to01 = lambda v: (v / 2 + 0.5).clamp(0, 1)
+    mse = float(((to01(got) - to01(want)) ** 2).mean())
+    mse_raw = float(((got - want) ** 2).mean()); peak = float(want.max() - want.min())
+    res["decoded_psnr_db_clamped_0_1"] = 10 * math.log10(1.0 / max(mse, 1e-30))
+    res["decoded_psnr_db_oracle_range"] = 10 * math.log10(peak * peak / max(mse_raw, 1e-30))
+    res["decoded_rel_l2"] = rel(got, want)
+    log("decoded frames", list(got.shape), "PSNR [0,1]-clamped:", res["decoded_psnr_db_clamped_0_1"],
+        "PSNR oracle-range:", res["decoded_psnr_db_oracle_range"], "rel_l2:", res["decoded_rel_l2"])
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/parity_full.json", "w"), indent=1)
     # quick timing of the graph step
