@@ -98,6 +98,9 @@ SIGNATURES = {
     "ctrlv_nhwc_to_nchw": (_I, [_P, _I, _L, _I, _I, _I, _I, _P, _P]),
     "ctrlv_softmax_rows": (_I, [_P, _L, _I, _I, _F, _P, _L, _P]),
     "ctrlv_time_conv_out": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "ctrlv_blur1d_reflect": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P]),
+    "ctrlv_resize_bicubic_ac": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "ctrlv_clip_patchify": (_I, [_P, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P, _I, _P, _P]),
 }
 
 _lib = None

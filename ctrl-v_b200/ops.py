@@ -388,3 +388,38 @@ def time_conv_out(x: torch.Tensor, B: int, T: int, H: int, W: int, Cc: int, w: t
     check(lib().ctrlv_time_conv_out(x.data_ptr(), x.stride(0), B, T, H * W, Cc, w.data_ptr(), bias.data_ptr(),
                                     out.data_ptr(), _stream()), "ctrlv_time_conv_out")
     return out
+
+
+# ---- image-conditioning prologue ------------------------------------------------
+def blur1d_reflect(x: torch.Tensor, taps: torch.Tensor, axis: int) -> torch.Tensor:
+    """x [..., H, W] fp32; one pass of the separable Gaussian (reflect padding) along x (0) or y (1)."""
+    _req(x, torch.float32, "x"); _req(taps, torch.float32, "taps")
+    assert x.is_contiguous() and taps.is_contiguous()
+    H, W = x.shape[-2:]
+    out = torch.empty_like(x)
+    check(lib().ctrlv_blur1d_reflect(x.data_ptr(), x.numel() // (H * W), H, W, axis, taps.data_ptr(), taps.numel(),
+                                     out.data_ptr(), _stream()), "ctrlv_blur1d_reflect")
+    return out
+
+
+def resize_bicubic_ac(x: torch.Tensor, Ho: int, Wo: int) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    assert x.is_contiguous()
+    H, W = x.shape[-2:]
+    out = torch.empty(x.shape[:-2] + (Ho, Wo), dtype=torch.float32, device="cuda")
+    check(lib().ctrlv_resize_bicubic_ac(x.data_ptr(), x.numel() // (H * W), H, W, Ho, Wo, out.data_ptr(), _stream()),
+          "ctrlv_resize_bicubic_ac")
+    return out
+
+
+def clip_patchify(img: torch.Tensor, patch: int, mean: torch.Tensor, std: torch.Tensor, a: float = 1.0,
+                  s: float = 0.0, clamp01: bool = False) -> torch.Tensor:
+    """img [B, C, H, W] fp32 -> bf16 rows [B*(H/P)*(W/P), Kpad] (Kpad = C*P*P rounded up to 64)."""
+    _req(img, torch.float32, "img"); _req(mean, torch.float32, "mean"); _req(std, torch.float32, "std")
+    assert img.is_contiguous()
+    B, Cc, H, W = img.shape
+    Kpad = (Cc * patch * patch + 63) // 64 * 64
+    out = torch.empty((B * (H // patch) * (W // patch), Kpad), dtype=BF16, device="cuda")
+    check(lib().ctrlv_clip_patchify(img.data_ptr(), B, Cc, H, W, patch, a, s, 1 if clamp01 else 0, mean.data_ptr(),
+                                    std.data_ptr(), Kpad, out.data_ptr(), _stream()), "ctrlv_clip_patchify")
+    return out

@@ -192,9 +192,12 @@ class StableVideoControlPipeline:
     The denoising loop (:298-343) runs on the sm_100a kernels.  With a `vae`
     (`ctrlv_b200.vae.AutoencoderKLTemporalDecoder`) the pipeline also encodes
     3-channel bbox frames (:84) and the conditioning image (:235) and decodes the result (:346-347,
-    `output_type` "pt" / "np" / "pil").  The CLIP image encoder (:220, row f-3) is not built: pass
-    `image_embeddings=[B, 1, D]`.  Without a `vae`, pass `image_latents=` and 4-channel `cond_images`
-    latents (:86-88) and use `output_type="latent"`."""
+    `output_type` "pt" / "np" / "pil"); with an `image_encoder`
+    (`ctrlv_b200.clip.CLIPVisionModelWithProjection`, row f-3) it embeds the conditioning image (:220:
+    antialiased resize to 224 + CLIP ViT-H).  `image` is a PIL image, a list of them, or a
+    [B, 3, H, W] tensor in [0, 1], already at `height` x `width`.  Without those modules pass
+    `image_embeddings=`, `image_latents=` and 4-channel `cond_images` latents (:86-88) and use
+    `output_type="latent"`."""
 
     def __init__(self, vae=None, image_encoder=None, unet: UNetSpatioTemporalConditionModel = None,
                  controlnet: ControlNetModel = None, scheduler: EulerDiscreteScheduler = None,
@@ -232,14 +235,43 @@ class StableVideoControlPipeline:
             cond_em = torch.cat([torch.zeros_like(cond_em), cond_em])
         return cond_em
 
+    @staticmethod
+    def _image_to_tensor01(image) -> torch.Tensor:
+        """PIL image / list of PIL images / [B, 3, H, W] tensor -> float tensor in [0, 1]
+        (`VaeImageProcessor.pil_to_numpy` + `numpy_to_pt`)."""
+        if isinstance(image, torch.Tensor):
+            if image.ndim != 4 or image.shape[1] != 3:
+                raise ValueError(f"`image` tensor must be [B, 3, H, W] in [0, 1], got {tuple(image.shape)}")
+            return image.to(torch.float32)
+        import numpy as np
+        imgs = image if isinstance(image, list) else [image]
+        arr = np.stack([np.array(im.convert("RGB")).astype("float32") / 255.0 for im in imgs])
+        return torch.from_numpy(arr).permute(0, 3, 1, 2).contiguous()
+
+    def _encode_image(self, image) -> torch.Tensor:  # diffusers `_encode_image`, called at :220
+        """-> conditional image embeddings [B, 1, D] (the CFG zeros are prepended by the caller)."""
+        if self.image_encoder is None:
+            raise NotImplementedError("pass image_embeddings=[B,1,D] or construct the pipeline with an "
+                                      "`image_encoder` (ctrlv_b200.clip.CLIPVisionModelWithProjection)")
+        return self.image_encoder.encode_image(self._image_to_tensor01(image))
+
+    def _get_add_time_ids(self, fps, motion_bucket_id, noise_aug_strength, batch_size):  # :247-255
+        add_time_ids = [fps, motion_bucket_id, noise_aug_strength]
+        passed = self.unet.config.addition_time_embed_dim * len(add_time_ids)
+        expected = self.unet.add_embedding.linear_1.in_features
+        if expected != passed:
+            raise ValueError(
+                f"Model expects an added time embedding vector of length {expected}, but a vector of "
+                f"{passed} was created. The model has an incorrect config. Please check "
+                "`unet.config.time_embedding_type` and `text_encoder_2.config.projection_dim`.")
+        return torch.tensor([add_time_ids], dtype=torch.float32).repeat(batch_size, 1)
+
     def _encode_vae_image(self, image, height, width, noise_aug_strength, generator):  # :228-241
         """`image_processor.preprocess` for a tensor in [0, 1] (normalise to [-1, 1]; resizing is not
         implemented: pass the image at the target size), noise augmentation, VAE `.mode()`."""
         if self.vae is None:
             raise NotImplementedError("pass image_latents=[B,4,h,w] or construct the pipeline with a `vae`")
-        if not isinstance(image, torch.Tensor) or image.ndim != 4 or image.shape[1] != 3:
-            raise NotImplementedError("`image` must be a [B, 3, H, W] tensor in [0, 1] (PIL input needs the "
-                                      "image processor, which is not part of this build)")
+        image = self._image_to_tensor01(image)
         if tuple(image.shape[-2:]) != (height, width):
             raise NotImplementedError(f"`image` must already be {height}x{width}; resizing is not implemented")
         image = 2.0 * image.to(torch.float32) - 1.0
@@ -296,8 +328,7 @@ class StableVideoControlPipeline:
         num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
         self.check_inputs(image, cond_images, height, width)
         if image_embeddings is None:
-            raise NotImplementedError("CLIP image encoding is not part of this build (SURVEY.md §8 f-3): "
-                                      "pass image_embeddings=[B,1,D]")
+            image_embeddings = self._encode_image(image)
         if output_type != "latent" and self.vae is None:
             raise NotImplementedError("decoding needs a `vae` (ctrlv_b200.vae.AutoencoderKLTemporalDecoder); "
                                       "use output_type='latent'")
@@ -317,7 +348,7 @@ class StableVideoControlPipeline:
             il = torch.cat([torch.zeros_like(il), il])
         il = il.unsqueeze(1).repeat(1, num_frames, 1, 1, 1)
         fps = fps - 1  # :224
-        ids = torch.tensor([[fps, motion_bucket_id, noise_aug_strength]], dtype=torch.float32).repeat(B, 1)
+        ids = self._get_add_time_ids(fps, motion_bucket_id, noise_aug_strength, B)
         if do_cfg:
             ids = torch.cat([ids, ids])
         self.scheduler.set_timesteps(num_inference_steps)
@@ -386,8 +417,7 @@ class VideoDiffusionPipeline(StableVideoControlPipeline):
         num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
         self.check_inputs(image, height, width)
         if image_embeddings is None:
-            raise NotImplementedError("CLIP image encoding is not part of this build (SURVEY.md §8 f-3): "
-                                      "pass image_embeddings=[B,1,D]")
+            image_embeddings = self._encode_image(image)
         if output_type != "latent" and self.vae is None:
             raise NotImplementedError("decoding needs a `vae` (ctrlv_b200.vae.AutoencoderKLTemporalDecoder); "
                                       "use output_type='latent'")
@@ -409,7 +439,7 @@ class VideoDiffusionPipeline(StableVideoControlPipeline):
             cond = self._encode_vae_condition(bbox_images, nvp, do_cfg)
             il[:, 0:num_cond_bbox_frames] = cond[:, 0:num_cond_bbox_frames]
             il[:, -1] = cond[:, -1]
-        ids = torch.tensor([[fps - 1, motion_bucket_id, noise_aug_strength]], dtype=torch.float32).repeat(B, 1)
+        ids = self._get_add_time_ids(fps - 1, motion_bucket_id, noise_aug_strength, B)
         if do_cfg:
             ids = torch.cat([ids, ids])
         self.scheduler.set_timesteps(num_inference_steps)

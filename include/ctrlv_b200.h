@@ -211,6 +211,27 @@ int ctrlv_softmax_rows(const float* scores, int64_t ld_scores, int32_t M, int32_
 int ctrlv_time_conv_out(const float* x, int32_t ld, int32_t B, int32_t T, int32_t HW, int32_t C,
                         const float* w, const float* bias, float* out, void* stream);
 
+/* ---- image-conditioning prologue (`_encode_image` of the diffusers SVD pipeline
+ * reached from pipeline_video_control.py:220; `_resize_with_antialiasing` as restated in
+ * src/ctrlv/bbox_generator_baseline/utils/image_encoder.py:184-290, used by
+ * src/ctrlv/utils/util.py:97-125) ------------------------------------------------------------- */
+
+/* One pass of the separable Gaussian blur with reflect padding ((ks-1)/2 in front) over
+ * [planes][H][W] fp32; axis 0 = along x, 1 = along y; taps[ks] already normalised.  src != dst. */
+int ctrlv_blur1d_reflect(const float* src, int32_t planes, int32_t H, int32_t W, int32_t axis,
+                         const float* taps, int32_t ks, float* dst, void* stream);
+
+/* F.interpolate(mode="bicubic", align_corners=True) of [planes][H][W] -> [planes][Ho][Wo], fp32. */
+int ctrlv_resize_bicubic_ac(const float* src, int32_t planes, int32_t H, int32_t W, int32_t Ho,
+                            int32_t Wo, float* dst, void* stream);
+
+/* CLIP input normalisation + patch gather: img [B][C][H][W] fp32 -> rows [B*(H/P)*(W/P)][Kpad] bf16,
+ * column c*P*P + iy*P + ix = (u - mean[c]) / std[c], u = a*img + s (clamped to [0,1] if clamp01);
+ * columns >= C*P*P are zero.  The patch-embedding Conv2d(kernel = stride = P) is then ctrlv_linear. */
+int ctrlv_clip_patchify(const float* img, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P, float a,
+                        float s, int32_t clamp01, const float* mean, const float* stdv, int32_t Kpad,
+                        void* rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -201,3 +201,39 @@ def test_vae_oracle_algebra():
         h = torch.randn(2, V.TINY_VAE_CONFIG["block_out_channels"][-1], 4, 4)
         ioi = torch.zeros(1, 2)
         assert torch.allclose(blk(h, None, ioi), blk.spatial_res_block(h, None), atol=1e-5)
+
+
+def test_resize_oracle_matches_reference_golden():
+    """PINNED: golden outputs of the reference's own `_resize_with_antialiasing`
+    (tests/golden/make_resize_golden.py executes image_encoder.py:184-290 unmodified)."""
+    from oracle import clip_oracle as CO
+    cases = torch.load(os.path.join(os.path.dirname(__file__), "golden", "resize_antialias.pt"))
+    assert len(cases) == 4
+    for c in cases:
+        got = CO.resize_with_antialiasing(c["input"], c["size"])
+        assert got.shape == c["output"].shape
+        assert torch.allclose(got, c["output"], atol=2e-6, rtol=1e-5), float((got - c["output"]).abs().max())
+
+
+def test_clip_oracle_matches_transformers():
+    """PINNED against the installed `transformers` CLIPVisionModelWithProjection (the reference's
+    image_encoder class, pipeline_video_control.py:30): same state dict -> same image_embeds."""
+    tf = pytest.importorskip("transformers")
+    from oracle import clip_oracle as CO
+    for act in ("gelu", "quick_gelu"):
+        cfg = dict(CO.TINY_CLIP_CONFIG, hidden_act=act)
+        hf_cfg = tf.CLIPVisionConfig(**cfg)
+        torch.manual_seed(0)
+        hf = tf.CLIPVisionModelWithProjection(hf_cfg).eval()
+        mine = CO.CLIPVisionModelWithProjection(**cfg).eval()
+        sd = {k: v for k, v in hf.state_dict().items() if not k.endswith("position_ids")}
+        assert set(sd) == set(mine.state_dict()), set(sd) ^ set(mine.state_dict())
+        mine.load_state_dict(sd)
+        x = torch.randn(2, 3, cfg["image_size"], cfg["image_size"])
+        with torch.no_grad():
+            want = hf(pixel_values=x).image_embeds
+            got = mine(x)
+        assert torch.allclose(got, want, atol=1e-5, rtol=1e-4), float((got - want).abs().max())
+    with torch.device("meta"):
+        full = CO.CLIPVisionModelWithProjection()
+    assert sum(p.numel() for p in full.parameters()) == 632_076_800  # ViT-H/14 vision tower + projection
