@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libctrlv_b200.so")
+# CTRLV_B200_LIB: developer override for A/B runs of two builds on one box (same exported symbols)
+LIB_PATH = os.environ.get("CTRLV_B200_LIB") or os.path.join(HERE, "libctrlv_b200.so")
 
 CTRLV_MAX_SRC = 4
 CTRLV_MAX_SEG = 20

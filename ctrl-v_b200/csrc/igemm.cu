@@ -34,6 +34,32 @@ struct IgemmSeg {
   int map, c0, nchunk, dx, dy, dz;
 };
 
+// exact unsigned division by a launch-time constant (Granlund-Montgomery round-up method):
+// q = (t + ((n - t) >> sh1)) >> sh2 with t = umulhi(n, mul) — 4 instructions instead of the ~25 of
+// a hardware-less 32-bit division, which the per-tile index decomposition paid six times.
+struct FastDiv {
+  uint32_t d, mul, sh1, sh2;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  if (d <= 1) { f.mul = 0; f.sh1 = 0; f.sh2 = 0; return f; }
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.mul = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
+  f.sh1 = 1;
+  f.sh2 = l - 1;
+  return f;
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(n, f.mul);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+__device__ __forceinline__ void fd_divmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
+  q = fd_div(n, f);
+  r = n - q * f.d;
+}
+
 struct IgemmParams {
   CUtensorMap tmA[CTRLV_MAX_SRC];
   CUtensorMap tmB;
@@ -41,6 +67,7 @@ struct IgemmParams {
   int nseg, kblocks;
   int X, Y, Z, bx, by, bz;
   int tiles_x, tiles_y, tiles_z, tiles_n, tiles_total;
+  FastDiv fd_n, fd_x, fd_y;  // division by tiles_n / tiles_x / tiles_y
   int BN, N, stages, a_bytes, stage_bytes, tmem_cols;
   int cg;  // 1 or 2 CTAs per tile (tcgen05 cta_group)
   int bres;       // 1: weight-stationary — the CTA's whole B tile (all K) stays resident in smem
@@ -115,7 +142,7 @@ struct ResPrefetch {
   }
 };
 
-__device__ __forceinline__ void add_bf16x8(float* v, const uint4& u, float s) {
+__device__ __forceinline__ void add_bf16x8(float* v, const uint4& u, float s) {  // v += s * u, packed fp32x2
   float2 f;
   f = unpack_bf16x2(u.x); v[0] += s * f.x; v[1] += s * f.y;
   f = unpack_bf16x2(u.y); v[2] += s * f.x; v[3] += s * f.y;
@@ -132,8 +159,10 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
   constexpr int CPR = NV / 8;
   constexpr int RPI = 32 / CPR;
   const int lane = threadIdx.x & 31;
+  if (ep.s_acc != 1.0f) {  // warp-uniform
 #pragma unroll
-  for (int j = 0; j < NV; ++j) v[j] *= ep.s_acc;
+    for (int j = 0; j < NV; ++j) v[j] *= ep.s_acc;
+  }
   if (pf.full) {
     if (ep.res1) {
       __syncwarp();
@@ -218,7 +247,7 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
+  for (int j = 0; j < 32; j += 4) {  // packed fp32x2 adds: 16 instead of 32 issue slots
     const float4 b = *reinterpret_cast<const float4*>(sb + j);
     v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
   }
@@ -349,12 +378,12 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_con
       }
       for (int it = 0; it < nloc; ++it) {
         const int tile = unit0 + it * nunits;
-        const int nt = tile % p.tiles_n;
-        int mt = (tile / p.tiles_n) * CG + (int)crank;
-        const int tx = mt % p.tiles_x;
-        mt /= p.tiles_x;
-        const int ty = mt % p.tiles_y;
-        const int tz = mt / p.tiles_y;  // may run past tiles_z for the odd tail: TMA zero-fills
+        uint32_t q_, nt_, tx_, ty_, tz_;
+        fd_divmod((uint32_t)tile, p.fd_n, q_, nt_);
+        fd_divmod(q_ * CG + crank, p.fd_x, q_, tx_);
+        fd_divmod(q_, p.fd_y, tz_, ty_);
+        const int nt = (int)nt_, tx = (int)tx_, ty = (int)ty_;
+        const int tz = (int)tz_;  // may run past tiles_z for the odd tail: TMA zero-fills
         const int x0 = tx * p.bx, y0 = ty * p.by, z0 = tz * p.bz;
         int kb = 0;
         for (int s = 0; s < p.nseg; ++s) {
@@ -446,17 +475,17 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_con
     const int n_store = ep.n_store > 0 ? ep.n_store : n_out_total;
     const uint32_t tempty_lead0 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
     const uint32_t tempty_lead1 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u;
+    // position of this thread's row inside the tile box (loop invariant)
+    const int ix = r % p.bx;
+    const int iy = (r / p.bx) % p.by;
+    const int iz = r / (p.bx * p.by);
     for (int it = 0; it < nloc; ++it) {
       const int tile = unit0 + it * nunits;
-      const int nt = tile % p.tiles_n;
-      int mt = (tile / p.tiles_n) * CG + (int)crank;
-      const int tx = mt % p.tiles_x;
-      mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int tz = mt / p.tiles_y;
-      const int ix = r % p.bx;
-      const int iy = (r / p.bx) % p.by;
-      const int iz = r / (p.bx * p.by);
+      uint32_t q_, nt_, tx_, ty_, tz_;
+      fd_divmod((uint32_t)tile, p.fd_n, q_, nt_);
+      fd_divmod(q_ * CG + crank, p.fd_x, q_, tx_);
+      fd_divmod(q_, p.fd_y, tz_, ty_);
+      const int nt = (int)nt_, tx = (int)tx_, ty = (int)ty_, tz = (int)tz_;
       const int x = tx * p.bx + ix, y = ty * p.by + iy, z = tz * p.bz + iz;
       const bool valid = (iz < p.bz) && (x < p.X) && (y < p.Y) && (z < p.Z);
       const long long m = ((long long)z * p.Y + y) * p.X + x;
@@ -639,6 +668,9 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
           (kblocks_pre >= 20 || (kblocks_pre >= 10 && d->N >= 2560))) ? 2 : 1;
   if (const char* e = getenv("CTRLV_DEBUG_CG")) p.cg = atoi(e);  // developer override
   p.tiles_total = ((tiles_m + p.cg - 1) / p.cg) * p.tiles_n;
+  p.fd_n = make_fastdiv((uint32_t)p.tiles_n);
+  p.fd_x = make_fastdiv((uint32_t)p.tiles_x);
+  p.fd_y = make_fastdiv((uint32_t)p.tiles_y);
 
 
   for (int i = 0; i < d->nsrc; ++i) {
