@@ -382,10 +382,17 @@ class _Transformer:
         n = ops.layernorm(hm)
         qkv = ops.linear(n, self.tattn1.wqkv, bias=self.tattn1.bqkv)
         att = ops.attn_temporal(qkv, B, T, S, self.heads)
-        ctx_t = aux.ctx[:, self.tattn2.off:self.tattn2.off + self.C]
         if self.order == "s_major":  # diffusers 0.27.2: context of row (b, s) is ctx[(b*S + s) % B]
-            kw = dict(rb_mode=3, rb_div=T * S, rb_mod=S, rb_B=B)
+            # over the WHOLE batch (vB rows); a branch-sharded process owns global rows b0 .. b0+B-1, so
+            # its local index (b*S + s) is offset by b0*S: rotate the table instead of the index
+            tab = aux.ctx_all
+            rot = (aux.b0 * S) % aux.vB
+            if rot:
+                tab = torch.roll(tab, shifts=-rot, dims=0)
+            ctx_t = tab[:, self.tattn2.off:self.tattn2.off + self.C]
+            kw = dict(rb_mode=3, rb_div=T * S, rb_mod=S, rb_B=aux.vB)
         else:
+            ctx_t = aux.ctx[:, self.tattn2.off:self.tattn2.off + self.C]
             kw = dict(rb_mode=1, rb_div=T * S)
         hm = ops.linear(att, self.tattn1.out.w, bias=self.tattn1.out.b, rowbias=ctx_t, res1=hm, **kw)
         n = ops.layernorm(hm)
@@ -566,11 +573,24 @@ class _PackedModel(torch.nn.Module):
         ids = added_time_ids.to(device="cuda", dtype=torch.float32).contiguous()
         return self.embed(ts, ids)  # [B, 4*C0] fp32
 
-    def _aux(self, emb, ehs):
+    def _aux(self, emb, ehs, branch: Optional[int] = None):
         """All per-sample vectors of one forward in two batched launches:
-        temb[b] = every time_emb_proj(silu(emb[b])); ctx[b] = every to_out(to_v(ehs[b]))."""
-        return SimpleNamespace(temb=ops.small_linear(emb, self.temb_w, self.temb_b, act_in=True),
-                               ctx=ops.small_linear(ehs, self.ctx_w, self.ctx_b))
+        temb[b] = every time_emb_proj(silu(emb[b])); ctx[b] = every to_out(to_v(ehs[b])).
+
+        `branch` = 0/1 selects the CFG-branch-sharded mode: this process runs only the
+        uncond (0) or cond (1) half of the CFG batch — `emb` has the local B rows — while `ehs` still
+        holds the contexts of BOTH halves [2B, D], because the diffusers-0.27.2 `time_context` order
+        pairs row (b, s) with context (b*S + s) % 2B of the whole batch (Appendix A.5)."""
+        temb = ops.small_linear(emb, self.temb_w, self.temb_b, act_in=True)
+        ctx = ops.small_linear(ehs, self.ctx_w, self.ctx_b)
+        if branch is None:
+            return SimpleNamespace(temb=temb, ctx=ctx, ctx_all=ctx, vB=ctx.shape[0], b0=0)
+        Bl = emb.shape[0]
+        if ehs.shape[0] != 2 * Bl:
+            raise ValueError(f"branch-sharded forward needs the contexts of both CFG halves: got {ehs.shape[0]} rows "
+                             f"for a local batch of {Bl}")
+        return SimpleNamespace(temb=temb, ctx=ctx[branch * Bl:(branch + 1) * Bl], ctx_all=ctx, vB=2 * Bl,
+                               b0=branch * Bl)
 
     def _finish_pack(self, resblocks, transformers):
         tw, tb, off = [], [], 0
@@ -664,10 +684,10 @@ class ControlNetModel(_PackedModel):
             ctrl.load_state_dict(sd)
         return ctrl
 
-    def forward_rows(self, inp64, emb, ehs, g, conditioning_scale: float = 1.0):
+    def forward_rows(self, inp64, emb, ehs, g, conditioning_scale: float = 1.0, branch: Optional[int] = None):
         """inp64: [M, 64] padded channels-last input [sample(8) | control_cond(4) | 0]."""
         B, T, H, W = g
-        aux = self._aux(emb, ehs)
+        aux = self._aux(emb, ehs, branch)
         x = ops.conv3x3(inp64, B * T, H, W, self.conv_in_w, bias=self.conv_in_b)
         x, skips, geoms, gm = self._encode(x, aux, g)
         x = self._mid(x, aux, gm)
@@ -752,10 +772,11 @@ class UNetSpatioTemporalConditionModel(_PackedModel):
             att += a or []
         self._finish_pack(res, att)
 
-    def forward_rows(self, inp64, emb, ehs, g, down_res=None, mid_res=None, out_f32=None, join=None):
+    def forward_rows(self, inp64, emb, ehs, g, down_res=None, mid_res=None, out_f32=None, join=None,
+                     branch: Optional[int] = None):
         """inp64 [M, 64] -> noise prediction rows [M, out_channels] fp32."""
         B, T, H, W = g
-        aux = self._aux(emb, ehs)
+        aux = self._aux(emb, ehs, branch)
         x = ops.conv3x3(inp64, B * T, H, W, self.conv_in_w, bias=self.conv_in_b)
         x, skips, geoms, gm = self._encode(x, aux, g)
         if join is not None:

@@ -1,5 +1,7 @@
 """Sample-parallel execution of Box2Video sampling: one process per GPU, clips sharded across
-ranks, no data-path collective during sampling, one all-gather of the final latents.
+ranks, no data-path collective during sampling, one all-gather of the final latents.  When there
+are fewer clips than GPUs, `CfgPair` shards the two CFG branches of a clip over a GPU pair
+(uncond on rank 2k, cond on rank 2k+1) with one small exchange of the model output per step.
 
 The reference has no multi-GPU inference at all (every eval tool runs under
 `if accelerator.is_main_process:`, /root/reference/tools/eval_video_controlnet.py:109); the unit
@@ -53,3 +55,40 @@ def gather_latents(local: torch.Tensor, n_clips: int, world_size: int, rank: int
     bufs = [torch.empty_like(pad) for _ in range(world_size)]
     dist.all_gather(bufs, pad.contiguous())
     return torch.cat([b[:c] for b, c in zip(bufs, counts)])
+
+
+# ---- CFG-branch sharding: one clip on a pair of GPUs ---------------------------------
+def cfg_pair_of(rank: int) -> tuple[int, int]:
+    """(pair index, CFG branch) of a rank: ranks 2k / 2k+1 run the uncond / cond half of pair k."""
+    if rank < 0:
+        raise ValueError(f"bad rank {rank}")
+    return rank // 2, rank % 2
+
+
+def time_context_rotation(branch: int, local_batch: int, sites: int) -> int:
+    """Rows by which a branch-sharded process rotates the whole-batch context table.
+
+    diffusers 0.27.2 builds `time_context` S-major (Appendix A.5): hidden row (b, s) of the batch of
+    2B samples is paired with context (b*S + s) % 2B.  A process that owns global samples
+    b0 = branch*B .. b0+B-1 sees local index (b_local*S + s), i.e. the global index minus b0*S."""
+    return (branch * local_batch * sites) % (2 * local_batch)
+
+
+class CfgPair:
+    """Process-group plumbing of one GPU pair: `exchange(step)` all-gathers the two halves of the model
+    output (fp32 [B*T*h*w, 4] per rank, 573 KB at 14x40x64) into `step.noise` over NVLink."""
+
+    def __init__(self, rank: int, world_size: int):
+        if world_size % 2:
+            raise ValueError(f"CFG-branch sharding needs an even number of ranks, got {world_size}")
+        self.pair, self.branch = cfg_pair_of(rank)
+        self.n_pairs = world_size // 2
+        self.group = None
+        if world_size > 2:
+            for k in range(self.n_pairs):  # every rank must create every group, in the same order
+                grp = dist.new_group([2 * k, 2 * k + 1])
+                if k == self.pair:
+                    self.group = grp
+
+    def exchange(self, step) -> None:
+        dist.all_gather_into_tensor(step.noise, step.noise_local, group=self.group)

@@ -68,11 +68,20 @@ class EulerDiscreteScheduler:
 
 class DenoiseStep:
     """One CFG Euler-EDM iteration of ControlNet + UNet on a fixed shape, replayed from a CUDA
-    graph.  State: `latents` fp32 [B, T, 4, h, w] updated in place on the device."""
+    graph.  State: `latents` fp32 [B, T, 4, h, w] updated in place on the device.
+
+    `cfg_branch` = 0 / 1 is the CFG-branch-sharded mode: this process computes only
+    the uncond / cond half of the CFG batch; `exchange(step)` must then fill the other half of
+    `step.noise` (an NCCL all-gather inside the GPU pair, `parallel.CfgPair`) before the CFG
+    combine + Euler update, which both processes of a pair run redundantly on identical inputs."""
 
     def __init__(self, unet: UNetSpatioTemporalConditionModel, controlnet: Optional[ControlNetModel],
                  batch: int, num_frames: int, h: int, w: int, cfg: bool = True,
-                 conditioning_scale: float = 1.0, use_graph: bool = True, two_streams: bool = True):
+                 conditioning_scale: float = 1.0, use_graph: bool = True, two_streams: bool = True,
+                 cfg_branch: Optional[int] = None, exchange: Optional[Callable] = None):
+        if cfg_branch is not None and (not cfg or cfg_branch not in (0, 1)):
+            raise ValueError("cfg_branch is 0 (uncond) or 1 (cond) and needs cfg=True")
+        self.cfg_branch, self.exchange = cfg_branch, exchange
         self.unet, self.controlnet = unet, controlnet
         self.two_streams = two_streams
         self._side = torch.cuda.Stream() if two_streams else None
@@ -93,18 +102,37 @@ class DenoiseStep:
         self.step_params = torch.zeros((2 + self.nb,), device=dev, dtype=torch.float32)
         self.noise = torch.zeros((self.nb * num_frames * h * w, unet.cfg["out_channels"]), device=dev,
                                  dtype=torch.float32)
-        self.inp = torch.zeros((self.nb * num_frames * h * w, 64), device=dev, dtype=BF16)
+        nloc = batch if cfg_branch is not None else self.nb  # samples this process pushes through the nets
+        self.inp = torch.zeros((nloc * num_frames * h * w, 64), device=dev, dtype=BF16)
+        # branch-sharded: the local half of the model output, sent to the peer by `exchange`
+        self.noise_local = (torch.zeros((nloc * num_frames * h * w, unet.cfg["out_channels"]), device=dev,
+                                        dtype=torch.float32) if cfg_branch is not None else None)
         self._graph = None
         self._host_params = None
         self.launches_per_step = None
 
     # -- the work of one step (kernel launches only) ------------------------------------------------
     def _body(self):
-        g = (self.nb, self.T, self.h, self.w)
+        self._body_model()
+        if self.cfg_branch is None:
+            self._body_update()
+
+    def _body_update(self):
+        ops.cfg_euler(self.latents, self.noise, self.cfg, self.guidance, self.step_params[0:2])
+
+    def _body_model(self):
         sig = self.step_params[0:2]
-        ts = self.step_params[2:]
-        ops.prep_input(self.latents, self.image_latents, self.cond_em if self.controlnet is not None else None,
-                       self.cfg, sig, out=self.inp)
+        br = self.cfg_branch
+        if br is None:
+            g = (self.nb, self.T, self.h, self.w)
+            ts, ids, out = self.step_params[2:], self.added_time_ids, self.noise
+            il, ce, dup = self.image_latents, self.cond_em, self.cfg
+        else:  # this process owns global batch rows br*B .. br*B + B - 1
+            lo, hi = br * self.B, (br + 1) * self.B
+            g = (self.B, self.T, self.h, self.w)
+            ts, ids, out = self.step_params[2 + lo:2 + hi], self.added_time_ids[lo:hi], self.noise_local
+            il, ce, dup = self.image_latents[lo:hi], self.cond_em[lo:hi], False
+        ops.prep_input(self.latents, il, ce if self.controlnet is not None else None, dup, sig, out=self.inp)
         down = mid = None
         join = None
         if self.controlnet is not None:
@@ -115,17 +143,16 @@ class DenoiseStep:
                 main = torch.cuda.current_stream()
                 self._side.wait_stream(main)
                 with torch.cuda.stream(self._side):
-                    emb_c = self.controlnet.embed(ts, self.added_time_ids)
-                    down, mid, _, _ = self.controlnet.forward_rows(self.inp, emb_c, self.ehs, g, self.scale)
+                    emb_c = self.controlnet.embed(ts, ids)
+                    down, mid, _, _ = self.controlnet.forward_rows(self.inp, emb_c, self.ehs, g, self.scale, branch=br)
                     for t in list(down) + [mid]:
                         t.record_stream(main)
                 join = lambda: main.wait_stream(self._side)
             else:
-                emb_c = self.controlnet.embed(ts, self.added_time_ids)
-                down, mid, _, _ = self.controlnet.forward_rows(self.inp, emb_c, self.ehs, g, self.scale)
-        emb_u = self.unet.embed(ts, self.added_time_ids)
-        self.unet.forward_rows(self.inp, emb_u, self.ehs, g, down, mid, out_f32=self.noise, join=join)
-        ops.cfg_euler(self.latents, self.noise, self.cfg, self.guidance, sig)
+                emb_c = self.controlnet.embed(ts, ids)
+                down, mid, _, _ = self.controlnet.forward_rows(self.inp, emb_c, self.ehs, g, self.scale, branch=br)
+        emb_u = self.unet.embed(ts, ids)
+        self.unet.forward_rows(self.inp, emb_u, self.ehs, g, down, mid, out_f32=out, join=join, branch=br)
 
     def set_schedule(self, sigmas: torch.Tensor, timesteps: torch.Tensor):
         n = timesteps.numel()
@@ -151,12 +178,28 @@ class DenoiseStep:
         self.latents.copy_(keep)
         torch.cuda.synchronize()
 
-    def step(self, i: int):
+    def run_model(self, i: int):
+        """Everything of step i up to the model output (the whole step when not branch-sharded)."""
         self.step_params.copy_(self._host_params[i], non_blocking=True)
         if self._graph is not None:
             self._graph.replay()
         else:
             self._body()
+
+    def finish(self):
+        """Branch-sharded mode: fetch the peer's half of the model output, then CFG + Euler."""
+        if self.cfg_branch is None:
+            return
+        M = self.noise_local.shape[0]
+        self.noise[self.cfg_branch * M:(self.cfg_branch + 1) * M].copy_(self.noise_local)
+        if self.exchange is None:
+            raise RuntimeError("branch-sharded DenoiseStep needs an `exchange` callable (parallel.CfgPair.exchange)")
+        self.exchange(self)
+        self._body_update()
+
+    def step(self, i: int):
+        self.run_model(i)
+        self.finish()
 
     # -- host-buffer entry point (what a reference-side caller holding host tensors would use) -----
     HOST_INPUTS = ("latents", "image_latents", "cond_em", "ehs", "added_time_ids", "guidance")

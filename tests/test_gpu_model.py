@@ -238,3 +238,60 @@ def test_full_size_single_step(T, h, w):
         got_noise = st.noise.view(2, T, h, w, 4).permute(0, 1, 4, 2, 3)
         assert rel(got_noise, noise) < 2e-2, i          # model output (bf16 path vs fp32 oracle)
         assert rel(st.latents, want) < 1e-2, i          # north_star: per-step latent rel L2 <= 1e-2
+
+
+@pytest.mark.parametrize("order,T,h,w,exact", [("s_major", 4, 16, 32, True), ("b_major", 4, 16, 32, True),
+                                               ("s_major", 3, 8, 24, False)])
+def test_cfg_branch_sharded_step_equals_batched_step(order, T, h, w, exact):
+    """uncond and cond halves computed by two branch-sharded DenoiseSteps (here on one
+    GPU, the exchange being a copy) reproduce the batched CFG step, including the diffusers-0.27.2
+    time_context coupling of the two branches.  When no 32-row warp straddles two samples (T*S a
+    multiple of 32 at every level) the result is bit-identical; in the 3x8x24 case (odd S = 3 at the
+    mid level: exercises the context-table rotation) a straddling warp adds bias and time embedding in
+    a different order, which flips single bf16 roundings."""
+    from ctrlv_b200 import pipeline
+    from oracle import sampling as S
+    from oracle import svd_oracle as O
+    _, _, mu, mc = _build(order, dict(O.TINY_CONFIG))
+    steps = 25
+    inp = S.make_inputs(T=T, h=h, w=w, xdim=O.TINY_CONFIG["cross_attention_dim"], device=dev)
+    sch = pipeline.EulerDiscreteScheduler().set_timesteps(steps)
+
+    def fill(st):
+        st.set_schedule(sch.sigmas, sch.timesteps)
+        st.image_latents.copy_(inp["image_latents"]); st.cond_em.copy_(inp["cond_em"])
+        st.ehs.copy_(inp["image_embeddings"].reshape(2, -1)); st.added_time_ids.copy_(inp["added_time_ids"])
+        st.guidance.copy_(inp["guidance"])
+        st.capture()
+        st.latents.copy_(inp["latents"] * sch.init_noise_sigma)
+
+    full = pipeline.DenoiseStep(mu, mc, 1, T, h, w, cfg=True)
+    halves = [pipeline.DenoiseStep(mu, mc, 1, T, h, w, cfg=True, cfg_branch=br) for br in (0, 1)]
+    M = halves[0].noise_local.shape[0]
+
+    def make_exchange(me):
+        other = halves[1 - me]
+        return lambda st: st.noise[(1 - me) * M:(2 - me) * M].copy_(other.noise_local)
+
+    for br in (0, 1):
+        halves[br].exchange = make_exchange(br)
+    for st in [full] + halves:
+        fill(st)
+    for i in (0, 7, 20):
+        for st in halves:  # restart every step from the batched state (no drift between the two runs)
+            st.latents.copy_(full.latents)
+        full.step(i)
+        for st in halves:
+            st.run_model(i)
+        for st in halves:
+            st.finish()
+        torch.cuda.synchronize()
+        assert torch.equal(halves[0].latents, halves[1].latents)
+        if exact:
+            assert torch.equal(halves[0].noise, full.noise), (order, i, rel(halves[0].noise, full.noise))
+            assert torch.equal(halves[0].latents, full.latents)
+        else:
+            assert rel(halves[0].noise, full.noise) < 2e-2, (order, i, rel(halves[0].noise, full.noise))
+            assert rel(halves[0].latents, full.latents) < 1e-2
+    with pytest.raises(ValueError):
+        pipeline.DenoiseStep(mu, mc, 1, T, h, w, cfg=False, cfg_branch=0)
