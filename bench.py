@@ -302,8 +302,17 @@ def run_b200(a):
         pass
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # DRAM bytes per igemm launch (average over the step's 429 launches) from the committed ncu pass
+    traffic = None
+    if (T, h, w) == (14, 40, 64):
+        try:
+            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r01_step_dram_traffic.json")))
+                            ["igemm_dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
     roofline = {"bound": "tensor", "kernel": "ctrlv::igemm_kernel (tcgen05 implicit GEMM: Linear / 3x3 / temporal conv)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/r01_step_dram_traffic.json: ncu dram__bytes_read+write, cold caches, mean per igemm launch",
                 "peak_source": peak_src, "launches_per_step": int(gemm_n),
                 "algorithmic_tflop_per_step": gemm_fl / 1e12, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
                 "whole_step_tflops": STEP_TFLOP * value / world if (T, h, w) == (14, 40, 64) else None}
