@@ -333,6 +333,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------
 constexpr int kAttn2Smem = (2 + 4) * kTile + 1024;  // Q0,Q1 | 4 K/V slots
 constexpr int kAttn2Threads = 64 + 8 * 32;
+#ifndef CTRLV_ATTN_EMU_EVERY
+#define CTRLV_ATTN_EMU_EVERY 2
+#endif
+constexpr int kEmuEvery = CTRLV_ATTN_EMU_EVERY;  // every n-th pair of exponentials runs on the FMA pipe (0 = none);
+// measured at S = 2560: none 380 us, 1/4 351, 1/3 351, 1/2 346, 2/3 372, 3/4 394, all 436
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
   asm volatile(
@@ -543,8 +548,30 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 64; i += 2) {
-          float p0 = ex2f(fmaf(__uint_as_float(sreg[c * 64 + i]), p.c, -mc));
-          float p1 = ex2f(fmaf(__uint_as_float(sreg[c * 64 + i + 1]), p.c, -mc));
+          float p0, p1;
+          if (kEmuEvery > 0 && ((i >> 1) % kEmuEvery) == kEmuEvery - 1) {
+            // exp2 on the FMA pipe for a fraction of the pairs (the MUFU pipe is this kernel's floor):
+            // x = n + f with n = round(x) taken from the mantissa of x + 1.5*2^23, 2^f by a cubic
+            // (max rel. error 7.5e-5, below bf16), 2^n by adding n to the exponent field
+            const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(sreg[c * 64 + i]), __uint_as_float(sreg[c * 64 + i + 1])),
+                                       f2_splat(p.c), f2_splat(-mc));
+            float x0, x1;
+            f2_unpack(x2, x0, x1);
+            const uint64_t xc = f2_pack(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+            const uint64_t tt = f2_add(xc, f2_splat(12582912.0f));
+            const uint64_t ff = f2_fma(f2_add(tt, f2_splat(-12582912.0f)), f2_splat(-1.0f), xc);
+            uint64_t q = f2_fma(ff, f2_splat(0.0551716676924127f), f2_splat(0.24261112208903293f));
+            q = f2_fma(ff, q, f2_splat(0.6932609857127214f));
+            q = f2_fma(ff, q, f2_splat(0.9999280735522258f));
+            float q0, q1, t0, t1;
+            f2_unpack(q, q0, q1);
+            f2_unpack(tt, t0, t1);
+            p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+            p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+          } else {
+            p0 = ex2f(fmaf(__uint_as_float(sreg[c * 64 + i]), p.c, -mc));
+            p1 = ex2f(fmaf(__uint_as_float(sreg[c * 64 + i + 1]), p.c, -mc));
+          }
           if (!full_blk) {
             if (kv0 + c * 64 + i >= p.S) p0 = 0.f;
             if (kv0 + c * 64 + i + 1 >= p.S) p1 = 0.f;
