@@ -244,12 +244,12 @@ def run_b200(a):
     st._graph = gsave
     st.latents.copy_(lat_keep)
     # launches: every profiled op is one kernel except groupnorm (2); plus the un-profiled glue ops
-    n_prof = sum(v[0] * (2 if k[0] == "groupnorm" else 1) for k, v in prof.items())
-    glue = 2 + 2 * (2 + 4 + 2) + 13 + 3  # prep + cfg_euler, per-model embeds (sinusoid x2, MLP x4, aux x2), axpby, upsample
+    n_prof = sum(v[0] * {"groupnorm": 2, "upconv3x3": 4}.get(k[0], 1) for k, v in prof.items())
+    glue = 2 + 2 * (2 + 4 + 2) + 13  # prep + cfg_euler, per-model embeds (sinusoid x2, MLP x4, aux x2), axpby
     launches_per_step = int(n_prof + glue)
-    gemm_ms = sum(v[1] for k, v in prof.items() if k[0] in ("linear", "conv3x3", "conv_t3"))
-    gemm_fl = sum(v[2] for k, v in prof.items() if k[0] in ("linear", "conv3x3", "conv_t3"))
-    gemm_n = sum(v[0] for k, v in prof.items() if k[0] in ("linear", "conv3x3", "conv_t3"))
+    gemm_ms = sum(v[1] for k, v in prof.items() if k[0] in ("linear", "conv3x3", "conv_t3", "upconv3x3"))
+    gemm_fl = sum(v[2] for k, v in prof.items() if k[0] in ("linear", "conv3x3", "conv_t3", "upconv3x3"))
+    gemm_n = sum(v[0] for k, v in prof.items() if k[0] in ("linear", "conv3x3", "conv_t3", "upconv3x3"))
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps
     for i in range(a.warmup):

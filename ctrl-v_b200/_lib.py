@@ -65,6 +65,8 @@ class IgemmDesc(C.Structure):
         ("W", C.c_void_p),
         ("N", C.c_int32), ("K", C.c_int32),
         ("bn", C.c_int32),
+        ("out_mul_x", C.c_int32), ("out_mul_y", C.c_int32), ("out_off_x", C.c_int32), ("out_off_y", C.c_int32),
+        ("out_X", C.c_int32), ("out_Y", C.c_int32),
         ("ep", Epilogue),
     ]
 

@@ -69,6 +69,7 @@ struct IgemmParams {
   int tiles_x, tiles_y, tiles_z, tiles_n, tiles_total;
   FastDiv fd_n, fd_x, fd_y;  // division by tiles_n / tiles_x / tiles_y
   int BN, N, stages, a_bytes, stage_bytes, tmem_cols;
+  int omx, omy, oox, ooy, oX, oY;  // output-row remap (identity: 1, 1, 0, 0, X, Y)
   int cg;  // 1 or 2 CTAs per tile (tcgen05 cta_group)
   int bres;       // 1: weight-stationary — the CTA's whole B tile (all K) stays resident in smem
   int bres_off;   // byte offset of the resident B region (after the A ring)
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_con
       const int nt = (int)nt_, tx = (int)tx_, ty = (int)ty_, tz = (int)tz_;
       const int x = tx * p.bx + ix, y = ty * p.by + iy, z = tz * p.bz + iz;
       const bool valid = (iz < p.bz) && (x < p.X) && (y < p.Y) && (z < p.Z);
-      const long long m = ((long long)z * p.Y + y) * p.X + x;
+      const long long m = ((long long)z * p.oY + y * p.omy + p.ooy) * p.oX + x * p.omx + p.oox;
 
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -668,6 +669,14 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
           (kblocks_pre >= 20 || (kblocks_pre >= 10 && d->N >= 2560))) ? 2 : 1;
   if (const char* e = getenv("CTRLV_DEBUG_CG")) p.cg = atoi(e);  // developer override
   p.tiles_total = ((tiles_m + p.cg - 1) / p.cg) * p.tiles_n;
+  if (d->out_X > 0) {
+    CTRLV_CHECK_ARG(d->out_Y > 0 && d->out_mul_x >= 1 && d->out_mul_y >= 1 && d->out_off_x >= 0 && d->out_off_y >= 0 &&
+                        (d->X - 1) * d->out_mul_x + d->out_off_x < d->out_X && (d->Y - 1) * d->out_mul_y + d->out_off_y < d->out_Y,
+                    "igemm: output-row remap does not fit the %dx%d output grid", d->out_X, d->out_Y);
+    p.omx = d->out_mul_x; p.omy = d->out_mul_y; p.oox = d->out_off_x; p.ooy = d->out_off_y; p.oX = d->out_X; p.oY = d->out_Y;
+  } else {
+    p.omx = 1; p.omy = 1; p.oox = 0; p.ooy = 0; p.oX = d->X; p.oY = d->Y;
+  }
   p.fd_n = make_fastdiv((uint32_t)p.tiles_n);
   p.fd_x = make_fastdiv((uint32_t)p.tiles_x);
   p.fd_y = make_fastdiv((uint32_t)p.tiles_y);

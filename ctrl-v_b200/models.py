@@ -756,7 +756,7 @@ class UNetSpatioTemporalConditionModel(_PackedModel):
             us = None
             if i != n - 1:
                 us = _Lin(sd, f"up_blocks.{i}.upsamplers.0.conv")
-                us.w = _w(_conv9(sd[f"up_blocks.{i}.upsamplers.0.conv.weight"].float()))
+                us.w = ops.pack_upconv3x3(sd[f"up_blocks.{i}.upsamplers.0.conv.weight"])  # four 2x2 phase kernels
             self.up.append((res, att, us))
         self.norm_out = _Norm(sd, "conv_norm_out")
         oc = cfg["out_channels"]
@@ -794,9 +794,9 @@ class UNetSpatioTemporalConditionModel(_PackedModel):
                 if att is not None:
                     x = att[j](x, aux, g)
             if us is not None:
-                x = ops.upsample2x(x, B * T, g[2], g[3])
+                # Upsample2D: nearest 2x + 3x3 conv, fused as four 2x2 phase convs of the low-res frame
+                x = ops.upsample2x_conv3x3(x, B * T, g[2], g[3], us.w, bias=us.b)
                 g = (B, T, g[2] * 2, g[3] * 2)
-                x = ops.conv3x3(x, B * T, g[2], g[3], us.w, bias=us.b)
         a = ops.groupnorm(x, B * T, g[2] * g[3], self.norm_out.g, self.norm_out.b, 1e-5, True)
         oc = self.cfg["out_channels"]
         if out_f32 is None:

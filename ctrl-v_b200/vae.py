@@ -315,7 +315,7 @@ class AutoencoderKLTemporalDecoder(torch.nn.Module):
             us = None
             if i != len(boc) - 1:
                 n = f"decoder.up_blocks.{i}.upsamplers.0.conv"
-                us = (_w(_conv9(sd[n + ".weight"].float())), _f(sd[n + ".bias"]))
+                us = (ops.pack_upconv3x3(sd[n + ".weight"]), _f(sd[n + ".bias"]))
             self.d_up.append((res, us))
         self.d_norm_out = _Norm(sd, "decoder.conv_norm_out")
         oc = cfg["out_channels"]
@@ -388,9 +388,8 @@ class AutoencoderKLTemporalDecoder(torch.nn.Module):
             for r in res:
                 h = r(h, B, T, H, W)
             if us is not None:
-                h = ops.upsample2x(h, F_, H, W)
+                h = ops.upsample2x_conv3x3(h, F_, H, W, us[0], bias=us[1])
                 H, W = 2 * H, 2 * W
-                h = ops.conv3x3(h, F_, H, W, us[0], bias=us[1])
         a = ops.groupnorm(h, F_, H * W, self.d_norm_out.g, self.d_norm_out.b, 1e-6, True)
         oc = self.cfg["out_channels"]
         img = torch.empty((F_ * H * W, 4), dtype=torch.float32, device="cuda")

@@ -98,6 +98,10 @@ typedef struct ctrlv_igemm_desc {
   const void* W;   /* bf16 [N][K], K = 64 * sum(nchunk), K contiguous */
   int32_t N, K;
   int32_t bn;      /* n-tile override (0 = auto) */
+  /* Optional output-row remap (all zero = identity): the row of (x, y, z) in out / res1 / res2 /
+   * rowbias indexing becomes (z*out_Y + y*out_mul_y + out_off_y)*out_X + x*out_mul_x + out_off_x.
+   * Used to scatter the four parity phases of a fused nearest-2x-upsample + 3x3 conv. */
+  int32_t out_mul_x, out_mul_y, out_off_x, out_off_y, out_X, out_Y;
   ctrlv_epilogue ep;
 } ctrlv_igemm_desc;
 

@@ -263,3 +263,17 @@ def test_errors_are_loud(ops):
         ops.linear(a, w)
     with pytest.raises(ValueError):
         ops.linear(a.float(), w)
+
+
+@pytest.mark.parametrize("frames,H,W,C,N", [(2, 4, 6, 64, 64), (3, 10, 16, 128, 64), (1, 5, 8, 64, 128), (2, 20, 32, 64, 96)])
+def test_upsample2x_conv3x3_fused(ops, frames, H, W, C, N):
+    """Upsample2D (nearest 2x + 3x3 conv) as four 2x2 phase convs of the low-res frame."""
+    g = torch.Generator("cpu").manual_seed(5)
+    x = torch.randn(frames, C, H, W, generator=g).cuda().to(BF)
+    w = (torch.randn(N, C, 3, 3, generator=g) / (9 * C) ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    want = F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w.to(BF).float(), b, padding=1)
+    rows = x.permute(0, 2, 3, 1).reshape(-1, C).contiguous()
+    got = ops.upsample2x_conv3x3(rows, frames, H, W, ops.pack_upconv3x3(w), bias=b)
+    got = got.float().reshape(frames, 2 * H, 2 * W, N).permute(0, 3, 1, 2)
+    assert rel(got, want) < 6e-3, rel(got, want)
