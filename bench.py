@@ -249,7 +249,8 @@ def run_b200(a):
     launches_per_step = int(n_prof + glue)
     gemm_ms = sum(v[1] for k, v in prof.items() if k[0] in ("linear", "conv3x3", "conv_t3", "upconv3x3"))
     gemm_fl = sum(v[2] for k, v in prof.items() if k[0] in ("linear", "conv3x3", "conv_t3", "upconv3x3"))
-    gemm_n = sum(v[0] for k, v in prof.items() if k[0] in ("linear", "conv3x3", "conv_t3", "upconv3x3"))
+    gemm_n = sum(v[0] * (4 if k[0] == "upconv3x3" else 1) for k, v in prof.items()
+                 if k[0] in ("linear", "conv3x3", "conv_t3", "upconv3x3"))
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps
     for i in range(a.warmup):
