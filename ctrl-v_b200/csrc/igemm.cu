@@ -286,11 +286,13 @@ __device__ __forceinline__ void ep_tile(const ctrlv_epilogue& ep, uint64_t* tful
   rows.init(m, valid);
   ResPrefetch<NV> pa, pb;
   auto o_of = [&](int c) { return GEGLU ? ((n_base + c * 32) >> 1) : (n_base + c * 32); };
+  // the first TWO chunks' residual rows are requested before the accumulator is ready: their HBM
+  // latency hides under the MMA wait instead of under one chunk of epilogue math
   if (c0 < nch) pa.issue(ep, rows, o_of(c0), n_store, n_base + c0 * 32, N, rb_uniform);
+  if (c1 < nch) pb.issue(ep, rows, o_of(c1), n_store, n_base + c1 * 32, N, rb_uniform);
   mbar_wait(tfull, tphase);
   tc_fence_after();
   if (c0 >= nch) return;
-  if (c1 < nch) pb.issue(ep, rows, o_of(c1), n_store, n_base + c1 * 32, N, rb_uniform);
   __syncwarp();
   ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c0 * 32), m, valid, n_base + c0 * 32, n_store, sbias, wst, rb, pa, rows);
   if (c1 >= nch) return;
