@@ -41,7 +41,7 @@ def _inputs(T, h, w, sigma):
     return inp, torch.cat([x, inp["image_latents"]], dim=2)
 
 
-@pytest.mark.parametrize("T,h,w", [(4, 16, 16), (3, 8, 24)])
+@pytest.mark.parametrize("T,h,w", [(4, 16, 16), (3, 8, 24), (1, 8, 8), (25, 8, 16), (2, 40, 8)])
 def test_controlnet_and_unet_forward(tiny, T, h, w):
     ou, oc, mu, mc = tiny
     inp, x = _inputs(T, h, w, 15.59)
