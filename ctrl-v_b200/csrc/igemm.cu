@@ -592,7 +592,9 @@ static int choose_bn(int N, long long tiles_m, int num_sms) {
     if (N % bn != 0) continue;
     const long long tiles = tiles_m * (N / bn);
     const long long waves = (tiles + num_sms - 1) / num_sms;
-    const double cost = (double)waves * (bn < 96 ? 96 : bn) + 1e-3 * (256 - bn);
+    // a tile costs its width plus a fixed share (pipeline fill/drain, epilogue set-up) worth ~96
+    // columns: fitted to the measured n-tile sweep (scripts/sweep_tiles.py)
+    const double cost = (double)waves * (bn + 96) + 1e-3 * (256 - bn);
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -667,8 +669,9 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   // (TMA writes + MMA reads ~ 96 KB per k-block); a pair halves the B traffic and deepens the TMA
   // ring.  Measured on this path's shapes (profiles/r01_cg2_vs_cg1.txt): +15-19 % on the 3x3 convs,
   // a win for K >= 1280 and for wide-N K = 640, a loss for K = 320 and tiny M.
-  p.cg = (tiles_m >= 16 && p.BN % 32 == 0 && d->N % p.BN == 0 &&
-          (kblocks_pre >= 20 || (kblocks_pre >= 10 && d->N >= 2560))) ? 2 : 1;
+  p.cg = (p.BN % 32 == 0 && d->N % p.BN == 0 &&
+          ((tiles_m >= 16 && (kblocks_pre >= 20 || (kblocks_pre >= 10 && d->N >= 2560))) ||
+           (tiles_m >= 8 && kblocks_pre >= 100))) ? 2 : 1;  // (few m-tiles: only the long-K convs gain)
   if (const char* e = getenv("CTRLV_DEBUG_CG")) p.cg = atoi(e);  // developer override
   p.tiles_total = ((tiles_m + p.cg - 1) / p.cg) * p.tiles_n;
   if (d->out_X > 0) {
