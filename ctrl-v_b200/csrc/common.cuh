@@ -493,6 +493,19 @@ __device__ __forceinline__ void geglu2_f(float h0, float g0, float h1, float g1,
   const uint64_t hg = f2_mul(f2_mul(f2_pack(h0, h1), f2_splat(0.5f)), g);
   f2_unpack(f2_fma(hg, t, hg), o0, o1);
 }
+// 256-bit global store (sm_100: STG.256): one full 32-byte sector per lane; p must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                             uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2),
+               "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+// 256-bit read-only global load (two 16-byte halves of one 32-byte sector); p must be 32-byte aligned
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

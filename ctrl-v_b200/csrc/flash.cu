@@ -294,16 +294,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
       orow = ((long long)blockIdx.z * p.T + t) * p.S + s;
     }
     if (valid) {
-      uint4* op = reinterpret_cast<uint4*>(p.out + orow * p.C + head * 64 + half * 32);
+      bf16* op = p.out + orow * p.C + head * 64 + half * 32;  // 64 B = two whole sectors, 256-bit stores
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = pack_bf16x2(o_acc[8 * i] * inv, o_acc[8 * i + 1] * inv);
-        u.y = pack_bf16x2(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
-        u.z = pack_bf16x2(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv);
-        u.w = pack_bf16x2(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv);
-        op[i] = u;
-      }
+      for (int i = 0; i < 2; ++i)
+        st_global_v8(op + 16 * i,
+                     pack_bf16x2(o_acc[16 * i] * inv, o_acc[16 * i + 1] * inv), pack_bf16x2(o_acc[16 * i + 2] * inv, o_acc[16 * i + 3] * inv),
+                     pack_bf16x2(o_acc[16 * i + 4] * inv, o_acc[16 * i + 5] * inv), pack_bf16x2(o_acc[16 * i + 6] * inv, o_acc[16 * i + 7] * inv),
+                     pack_bf16x2(o_acc[16 * i + 8] * inv, o_acc[16 * i + 9] * inv), pack_bf16x2(o_acc[16 * i + 10] * inv, o_acc[16 * i + 11] * inv),
+                     pack_bf16x2(o_acc[16 * i + 12] * inv, o_acc[16 * i + 13] * inv), pack_bf16x2(o_acc[16 * i + 14] * inv, o_acc[16 * i + 15] * inv));
     }
   }
 
@@ -600,15 +598,13 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
       tmem_ld32(tO + c * 32, raw);
       tmem_ld_wait();
       if (valid) {
-        uint4* op = reinterpret_cast<uint4*>(orow + c * 32);
+        bf16* op = orow + c * 32;  // whole 32-byte sectors per store (256-bit)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(raw[8 * i]) * inv, __uint_as_float(raw[8 * i + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(raw[8 * i + 2]) * inv, __uint_as_float(raw[8 * i + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(raw[8 * i + 4]) * inv, __uint_as_float(raw[8 * i + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(raw[8 * i + 6]) * inv, __uint_as_float(raw[8 * i + 7]) * inv);
-          op[i] = u;
+        for (int i = 0; i < 2; ++i) {
+          auto f = [&](int j) { return __uint_as_float(raw[16 * i + j]) * inv; };
+          st_global_v8(op + 16 * i, pack_bf16x2(f(0), f(1)), pack_bf16x2(f(2), f(3)), pack_bf16x2(f(4), f(5)),
+                       pack_bf16x2(f(6), f(7)), pack_bf16x2(f(8), f(9)), pack_bf16x2(f(10), f(11)),
+                       pack_bf16x2(f(12), f(13)), pack_bf16x2(f(14), f(15)));
         }
       }
     }

@@ -175,17 +175,36 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
     }
     if (ep.res2 && valid) {
       const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res2) + (size_t)m * ep.ld_res2 + o0);
+      if ((reinterpret_cast<uintptr_t>(rp) & 31) == 0) {  // whole 32-byte sectors per load
 #pragma unroll
-      for (int j = 0; j < CPR; ++j) add_bf16x8(v + 8 * j, __ldg(rp + j), ep.s_res2);
+        for (int j = 0; j < CPR; j += 2) {
+          uint4 lo, hi;
+          ld_global_nc_v8(rp + j, lo, hi);
+          add_bf16x8(v + 8 * j, lo, ep.s_res2);
+          add_bf16x8(v + 8 * j + 8, hi, ep.s_res2);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CPR; ++j) add_bf16x8(v + 8 * j, __ldg(rp + j), ep.s_res2);
+      }
     }
     if (ep.out && NV == 16) {
       // GEGLU chunks yield only 32 B per row: the transpose does not pay (measured), store directly
+      // One 256-bit store per lane = one whole 32-byte sector (two 16-byte stores leave the L2 with
+      // half-written sectors: measured, the store path cost a quarter of the K = 320 GEGLU kernel).
       if (valid) {
-        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)m * ep.ld_out + o0);
+        bf16* op = reinterpret_cast<bf16*>(ep.out) + (size_t)m * ep.ld_out + o0;
+        if ((reinterpret_cast<uintptr_t>(op) & 31) == 0) {
+          st_global_v8(op, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                       pack_bf16x2(v[6], v[7]), pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                       pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        } else {
+          uint4* o4 = reinterpret_cast<uint4*>(op);
 #pragma unroll
-        for (int j = 0; j < CPR; ++j)
-          op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          for (int j = 0; j < CPR; ++j)
+            o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        }
       }
     } else if (ep.out) {
       __syncwarp();
