@@ -170,7 +170,11 @@ def test_attn_temporal(ops, B, T, S, heads, sc):
 @pytest.mark.parametrize("units,rows,C0,C1,silu,eps", [(4, 256, 64, 0, True, 1e-5), (28, 2560, 320, 0, True, 1e-6),
                                                        (2, 8960, 640, 0, True, 1e-5), (6, 160, 1280, 640, True, 1e-6),
                                                        (6, 40, 1280, 1280, False, 1e-6), (3, 640, 640, 320, True, 1e-5),
-                                                       (2, 4, 64, 0, True, 1e-5)])
+                                                       (2, 4, 64, 0, True, 1e-5),
+                                                       # many small units, two sources, ragged row counts
+                                                       (8, 40, 1280, 1280, False, 1e-6), (12, 160, 640, 320, True, 1e-5),
+                                                       (28, 640, 640, 0, True, 1e-6), (9, 7, 64, 0, True, 1e-5),
+                                                       (16, 2561, 128, 0, True, 1e-6)])
 def test_groupnorm(ops, units, rows, C0, C1, silu, eps):
     dev = "cuda"
     C = C0 + C1
