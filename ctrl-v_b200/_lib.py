@@ -99,6 +99,8 @@ SIGNATURES = {
     "ctrlv_axpby": (_I, [_P, _P, _F, _F, _L, _P, _P]),
     "ctrlv_nchw_to_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ctrlv_nhwc_to_nchw": (_I, [_P, _I, _L, _I, _I, _I, _I, _P, _P]),
+    "ctrlv_conv3x3_s2_pad01": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(Epilogue), _P]),
+    "ctrlv_upsample2x_conv3x3": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(Epilogue), _P]),
     "ctrlv_softmax_rows": (_I, [_P, _L, _I, _I, _F, _P, _L, _P]),
     "ctrlv_time_conv_out": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ctrlv_blur1d_reflect": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P]),

@@ -894,6 +894,66 @@ extern "C" int ctrlv_conv3x3(const void* src0, int32_t C0, const void* src1, int
   return igemm_launch(&d, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int ctrlv_conv3x3_s2_pad01(const void* src, int32_t C, int32_t frames, int32_t H, int32_t Wd,
+                                      const void* W, int32_t N, const ctrlv_epilogue* ep, void* stream) {
+  CTRLV_CHECK_ARG(ep != nullptr && src != nullptr, "conv3x3_s2_pad01: null argument");
+  CTRLV_CHECK_ARG(C > 0 && C % 64 == 0, "conv3x3_s2_pad01: C=%d must be a multiple of 64", C);
+  CTRLV_CHECK_ARG(H % 2 == 0 && Wd % 2 == 0, "conv3x3_s2_pad01: needs even H, W");
+  ctrlv_igemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.X = Wd / 2; d.Y = H / 2; d.Z = frames;
+  // out(oy, ox) = sum_k w[ky][kx] x(2oy + ky, 2ox + kx): tap k reads parity lattice k & 1 at offset k >> 1;
+  // the row / column past the frame (the F.pad(0,1,0,1) of diffusers' Downsample2D(padding=0)) is TMA zero fill
+  d.nsrc = 4;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      ctrlv_src& s = d.src[py * 2 + px];
+      s.ptr = reinterpret_cast<const bf16*>(src) + ((int64_t)py * Wd + px) * C;
+      s.C = C; s.sx = 2 * (int64_t)C; s.sy = 2 * (int64_t)C * Wd; s.sz = (int64_t)C * Wd * H;
+    }
+  d.nseg = 9;
+  for (int t = 0; t < 9; ++t) {
+    const int ky = t / 3, kx = t % 3;
+    ctrlv_seg& s = d.seg[t];
+    s.src = (ky & 1) * 2 + (kx & 1); s.c0 = 0; s.nchunk = C / 64; s.dx = kx >> 1; s.dy = ky >> 1; s.dz = 0;
+  }
+  d.W = W; d.N = N; d.K = 9 * C;
+  d.ep = *ep;
+  return igemm_launch(&d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ctrlv_upsample2x_conv3x3(const void* src, int32_t C, int32_t frames, int32_t H, int32_t Wd,
+                                        const void* Wp, int32_t N, const ctrlv_epilogue* ep, void* stream) {
+  CTRLV_CHECK_ARG(ep != nullptr && src != nullptr && Wp != nullptr, "upsample2x_conv3x3: null argument");
+  CTRLV_CHECK_ARG(C > 0 && C % 64 == 0, "upsample2x_conv3x3: C=%d must be a multiple of 64", C);
+  CTRLV_CHECK_ARG(ep->rb_mode == 0 && ep->res1 == nullptr && ep->res2 == nullptr,
+                  "upsample2x_conv3x3: bias-only epilogue");
+  // conv3x3(nearest2x(x)) at output pixel (2y+py, 2x+px) only sees a 2x2 patch of x: four phase convs with
+  // summed taps (phase matrix [N][4*C], patch order (dy, dx) increasing), written to their strided rows
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      ctrlv_igemm_desc d;
+      memset(&d, 0, sizeof(d));
+      d.nsrc = 1;
+      d.src[0].ptr = src; d.src[0].C = C; d.src[0].sx = C; d.src[0].sy = (int64_t)C * Wd; d.src[0].sz = (int64_t)C * Wd * H;
+      d.X = Wd; d.Y = H; d.Z = frames;
+      d.nseg = 4;
+      int i = 0;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          ctrlv_seg& s = d.seg[i++];
+          s.src = 0; s.c0 = 0; s.nchunk = C / 64; s.dx = (px == 0 ? -1 : 0) + b; s.dy = (py == 0 ? -1 : 0) + a; s.dz = 0;
+        }
+      d.W = reinterpret_cast<const bf16*>(Wp) + (size_t)(py * 2 + px) * N * 4 * C;
+      d.N = N; d.K = 4 * C;
+      d.out_mul_x = 2; d.out_mul_y = 2; d.out_off_x = px; d.out_off_y = py; d.out_X = 2 * Wd; d.out_Y = 2 * H;
+      d.ep = *ep;
+      const int rc = igemm_launch(&d, reinterpret_cast<cudaStream_t>(stream));
+      if (rc) return rc;
+    }
+  return CTRLV_OK;
+}
+
 extern "C" int ctrlv_conv_t3(const void* src, int32_t C, int32_t B, int32_t T, int32_t HW,
                              const void* W, int32_t N, const ctrlv_epilogue* ep, void* stream) {
   CTRLV_CHECK_ARG(ep != nullptr, "conv_t3: null epilogue");

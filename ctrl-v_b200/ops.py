@@ -341,30 +341,15 @@ def conv3x3_s2_pad01(x: torch.Tensor, frames: int, H: int, W: int, w: torch.Tens
     conv without padding, i.e. out(oy,ox) = sum_k w[ky][kx] x(2oy+ky, 2ox+kx).  Described to the
     generic implicit GEMM as four parity sub-lattices: tap k -> parity k&1, lattice offset k>>1; the
     out-of-range row/column of the last tap is the TMA zero fill."""
-    from ._lib import IgemmDesc
     _req(x, BF16, "x"); _req(w, BF16, "w")
     assert x.is_contiguous() and w.is_contiguous() and H % 2 == 0 and W % 2 == 0
     C0 = x.shape[1]
     N = w.shape[0]
     assert C0 % 64 == 0 and w.shape[1] == 9 * C0 and x.shape[0] == frames * H * W
-    Ho, Wo = H // 2, W // 2
-    kw = _alloc_out(frames * Ho * Wo, N, False, kw)
-    d = IgemmDesc()
-    d.nsrc = 4
-    for py in range(2):
-        for px in range(2):
-            sr = d.src[py * 2 + px]
-            sr.ptr = x.data_ptr() + ((py * W + px) * C0) * 2
-            sr.C, sr.sx, sr.sy, sr.sz = C0, 2 * C0, 2 * C0 * W, C0 * W * H
-    d.X, d.Y, d.Z = Wo, Ho, frames
-    d.nseg = 9
-    for t in range(9):
-        ky, kx = t // 3, t % 3
-        sg = d.seg[t]
-        sg.src, sg.c0, sg.nchunk, sg.dx, sg.dy, sg.dz = (ky & 1) * 2 + (kx & 1), 0, C0 // 64, kx >> 1, ky >> 1, 0
-    d.W, d.N, d.K, d.bn = w.data_ptr(), N, 9 * C0, 0
-    d.ep = make_ep(**kw)
-    check(lib().ctrlv_igemm(C.byref(d), _stream()), "ctrlv_igemm")
+    kw = _alloc_out(frames * (H // 2) * (W // 2), N, False, kw)
+    ep = make_ep(**kw)
+    check(lib().ctrlv_conv3x3_s2_pad01(x.data_ptr(), C0, frames, H, W, w.data_ptr(), N, C.byref(ep), _stream()),
+          "ctrlv_conv3x3_s2_pad01")
     return kw["out"] if kw.get("out") is not None else kw["out_f32"]
 
 
@@ -454,7 +439,6 @@ def pack_upconv3x3(w: torch.Tensor) -> torch.Tensor:
 def upsample2x_conv3x3(x: torch.Tensor, frames: int, H: int, W: int, wp: torch.Tensor,
                        bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [frames*H*W, C] -> conv3x3(nearest2x(x)) as rows [frames*2H*2W, N]; wp from pack_upconv3x3."""
-    from ._lib import IgemmDesc
     _req(x, BF16, "x"); _req(wp, BF16, "wp")
     assert x.is_contiguous() and wp.is_contiguous() and x.shape[0] == frames * H * W
     C0 = x.shape[1]
@@ -463,23 +447,8 @@ def upsample2x_conv3x3(x: torch.Tensor, frames: int, H: int, W: int, wp: torch.T
     if out is None:
         out = torch.empty((frames * 4 * H * W, N), dtype=BF16, device="cuda")
     tok = _prof("upconv3x3", (frames, H, W, C0, N), 2.0 * frames * H * W * 16 * C0 * N)
-    for py in (0, 1):
-        for px in (0, 1):
-            d = IgemmDesc()
-            d.nsrc = 1
-            sr = d.src[0]
-            sr.ptr, sr.C, sr.sx, sr.sy, sr.sz = x.data_ptr(), C0, C0, C0 * W, C0 * W * H
-            d.X, d.Y, d.Z = W, H, frames
-            d.nseg = 4
-            i = 0
-            for dy in ((-1, 0) if py == 0 else (0, 1)):
-                for dx in ((-1, 0) if px == 0 else (0, 1)):
-                    sg = d.seg[i]
-                    sg.src, sg.c0, sg.nchunk, sg.dx, sg.dy, sg.dz = 0, 0, C0 // 64, dx, dy, 0
-                    i += 1
-            d.W, d.N, d.K, d.bn = wp[py * 2 + px].data_ptr(), N, 4 * C0, 0
-            d.out_mul_x, d.out_mul_y, d.out_off_x, d.out_off_y, d.out_X, d.out_Y = 2, 2, px, py, 2 * W, 2 * H
-            d.ep = make_ep(out=out, bias=bias)
-            check(lib().ctrlv_igemm(C.byref(d), _stream()), "ctrlv_igemm")
+    ep = make_ep(out=out, bias=bias)
+    check(lib().ctrlv_upsample2x_conv3x3(x.data_ptr(), C0, frames, H, W, wp.data_ptr(), N, C.byref(ep), _stream()),
+          "ctrlv_upsample2x_conv3x3")
     _prof_end(tok)
     return out

@@ -201,6 +201,20 @@ int ctrlv_nchw_to_nhwc(const void* src, int32_t src_is_f32, int32_t frames, int3
 int ctrlv_nhwc_to_nchw(const void* src, int32_t src_is_f32, int64_t ld, int32_t frames, int32_t C,
                        int32_t HW, int32_t out_is_f32, void* out, void* stream);
 
+/* diffusers Downsample2D(padding=0) of the VAE encoder: F.pad(x, (0,1,0,1)) then Conv2d 3x3 stride 2
+ * without padding, on channels-last frames; W [N][9*C] tap-major. */
+int ctrlv_conv3x3_s2_pad01(const void* src, int32_t C, int32_t frames, int32_t H, int32_t Wd, const void* W,
+                           int32_t N, const ctrlv_epilogue* ep, void* stream);
+
+/* diffusers Upsample2D: F.interpolate(scale_factor=2, mode="nearest") followed by Conv2d 3x3 pad 1, fused as
+ * four 2x2 phase convolutions of the LOW-resolution frame (2.25x fewer MACs, no upsampled intermediate).
+ * src [frames][H][Wd][C]; out rows [frames][2H][2Wd][N]; Wp [4][N][4*C]: phase p = py*2+px holds, for the
+ * 2x2 patch offsets (dy, dx) in increasing order, the sums of the 3x3 taps that fall on that source pixel
+ * (py = 0: rows {ky=0 | ky=1,2} at dy = {-1, 0};  py = 1: {ky=0,1 | ky=2} at dy = {0, +1};  same in x).
+ * Bias-only epilogue. */
+int ctrlv_upsample2x_conv3x3(const void* src, int32_t C, int32_t frames, int32_t H, int32_t Wd, const void* Wp,
+                             int32_t N, const ctrlv_epilogue* ep, void* stream);
+
 /* ---- temporal VAE glue (diffusers AutoencoderKLTemporalDecoder, reached from
  * pipeline_video_control.py:84,235,346-347) -------------------------------------------------- */
 
