@@ -640,6 +640,8 @@ extern "C" int ctrlv_attn_spatial(const void* qkv, int32_t frames, int32_t S, in
   int rc = attn_init();
   if (rc) return rc;
   CTRLV_CHECK_ARG(qkv && out && frames > 0 && S > 0 && heads > 0, "attn_spatial: bad arguments");
+  CTRLV_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 31) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0,
+                  "attn_spatial: out must be 32-byte aligned (256-bit stores), qkv 16-byte aligned");
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.C = heads * 64; p.S = S; p.T = 1; p.G = 1; p.heads = heads;
@@ -672,6 +674,8 @@ extern "C" int ctrlv_attn_temporal(const void* qkv, int32_t B, int32_t T, int32_
   int rc = attn_init();
   if (rc) return rc;
   CTRLV_CHECK_ARG(qkv && out && B > 0 && S > 0 && heads > 0, "attn_temporal: bad arguments");
+  CTRLV_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 31) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0,
+                  "attn_temporal: out must be 32-byte aligned (256-bit stores), qkv 16-byte aligned");
   CTRLV_CHECK_ARG(T >= 1 && T <= 128, "attn_temporal: T=%d unsupported (1..128)", T);
   AttnParams p;
   memset(&p, 0, sizeof(p));

@@ -153,7 +153,7 @@ int ctrlv_layernorm(const void* x, int64_t ldx, int32_t M, int32_t C, const floa
  *  spatial : rows = frames*S, sequences are the S sites of one frame;
  *  temporal: rows = B*T*S, sequences are the T frames of one site (row stride S between
  *            sequence elements) — no permute copy.
- * out: bf16 [rows][C]. */
+ * out: bf16 [rows][C], 32-byte aligned (rows are written with 256-bit stores); qkv 16-byte aligned. */
 int ctrlv_attn_spatial(const void* qkv, int32_t frames, int32_t S, int32_t heads, float scale,
                        void* out, void* stream);
 int ctrlv_attn_temporal(const void* qkv, int32_t B, int32_t T, int32_t S, int32_t heads,
