@@ -157,6 +157,18 @@ class CLIPVisionModelWithProjection(torch.nn.Module):
         over.update(kwargs)
         return cls(state_dict=sd, **over)
 
+    def save_pretrained(self, save_directory: str, subfolder: Optional[str] = None, variant: Optional[str] = None):
+        """transformers layout: config.json + model[.variant].safetensors."""
+        import json
+        import os
+        from . import checkpoint
+        d = os.path.join(save_directory, subfolder) if subfolder else save_directory
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "config.json"), "w", encoding="utf-8") as f:
+            json.dump(dict(architectures=["CLIPVisionModelWithProjection"], model_type="clip_vision_model", **self.cfg), f, indent=2)
+        checkpoint.write_safetensors(os.path.join(d, "model" + (f".{variant}" if variant else "") + ".safetensors"),
+                                     self._sd, {"format": "pt"})
+
     def to(self, *a, **k):
         return self
 

@@ -254,6 +254,38 @@ class StableVideoControlPipeline:
         self._steps: Dict[tuple, DenoiseStep] = {}
         self._guidance_scale = 1.0
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, **kwargs):
+        """`DiffusionPipeline.from_pretrained` for a LOCAL Stable-Video-Diffusion directory
+        (tools/eval_video_controlnet.py:116-118): loads `vae/` and `image_encoder/` (and `unet/` unless a
+        `unet=` is passed) with the sm_100a drop-ins; `controlnet=` / `unet=` keyword modules are used as
+        given.  The scheduler is the SVD EulerDiscreteScheduler configuration.  No hub download."""
+        import os
+        from . import clip as _clip
+        from . import vae as _vae
+        root = pretrained_model_name_or_path
+        if not os.path.isdir(root):
+            raise OSError(f"{root} is not a local directory (this build does not download from the hub)")
+        kwargs.pop("torch_dtype", None); variant = kwargs.pop("variant", None)
+        parts = {}
+        for name, loader in (("vae", _vae.AutoencoderKLTemporalDecoder), ("image_encoder", _clip.CLIPVisionModelWithProjection),
+                             ("unet", UNetSpatioTemporalConditionModel), ("controlnet", ControlNetModel)):
+            if name in kwargs:
+                parts[name] = kwargs.pop(name)
+            elif os.path.isdir(os.path.join(root, name)):
+                parts[name] = loader.from_pretrained(root, subfolder=name, variant=variant)
+            else:
+                parts[name] = None
+        if cls is VideoDiffusionPipeline:
+            parts.pop("controlnet", None)
+        return cls(scheduler=kwargs.pop("scheduler", None), feature_extractor=kwargs.pop("feature_extractor", None), **parts)
+
+    def to(self, *a, **k):  # modules are device-resident by construction
+        return self
+
+    def set_progress_bar_config(self, **k):
+        pass
+
     @property
     def do_classifier_free_guidance(self):
         g = self._guidance_scale

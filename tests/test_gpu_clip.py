@@ -151,3 +151,37 @@ def test_pipeline_end_to_end_from_pixels():
                 latents=lat0.clone(), output_type="pil", noise_aug_strength=aug,
                 generator=torch.Generator("cpu").manual_seed(13)).frames
     assert len(got2) == 1 and len(got2[0]) == T and got2[0][0].size == (W, H)
+
+
+def test_pipeline_from_pretrained_directory(tmp_path):
+    """tools/eval_video_controlnet.py:114-118: load unet/controlnet from a training output directory and the
+    rest of the pipeline (vae, image_encoder) from a local Stable-Video-Diffusion directory."""
+    from ctrlv_b200 import models, pipeline, vae, clip
+    from oracle import clip_oracle as CO
+    from oracle import svd_oracle as O
+    from oracle import vae_oracle as V
+    over = dict(O.TINY_CONFIG)
+    ccfg = dict(CO.TINY_CLIP_CONFIG, projection_dim=over["cross_attention_dim"])
+    svd, run = str(tmp_path / "svd"), str(tmp_path / "run")
+    mv = vae.AutoencoderKLTemporalDecoder(seed=3, **V.TINY_VAE_CONFIG); mv.save_pretrained(svd, subfolder="vae")
+    me = clip.CLIPVisionModelWithProjection(seed=4, **ccfg); me.save_pretrained(svd, subfolder="image_encoder")
+    mu = models.UNetSpatioTemporalConditionModel(seed=5, **over); mu.save_pretrained(run, subfolder="unet")
+    mc = models.ControlNetModel(seed=6, **over); mc.save_pretrained(run, subfolder="controlnet")
+    ctrlnet = models.ControlNetModel.from_pretrained(run, subfolder="controlnet")
+    unet = models.UNetSpatioTemporalConditionModel.from_pretrained(run, subfolder="unet")
+    pipe = pipeline.StableVideoControlPipeline.from_pretrained(svd, controlnet=ctrlnet, unet=unet).to("cuda")
+    pipe.set_progress_bar_config(disable=True)
+    assert pipe.vae is not None and pipe.image_encoder is not None and pipe.unet is unet and pipe.controlnet is ctrlnet
+    ref = pipeline.StableVideoControlPipeline(vae=mv, image_encoder=me, unet=mu, controlnet=mc)
+    g = torch.Generator("cpu").manual_seed(21)
+    T, h, w = 2, 8, 8
+    image = torch.rand(1, 3, 2 * h, 2 * w, generator=g)
+    bbox = torch.rand(1, T, 3, 2 * h, 2 * w, generator=g) * 2 - 1
+    lat0 = torch.randn(1, T, 4, h, w, generator=g)
+    kw = dict(image=image, cond_images=bbox, height=2 * h, width=2 * w, num_frames=T, num_inference_steps=4,
+              output_type="pt", noise_aug_strength=0.02)
+    a = pipe(latents=lat0.clone(), generator=torch.Generator("cpu").manual_seed(1), **kw).frames
+    b = ref(latents=lat0.clone(), generator=torch.Generator("cpu").manual_seed(1), **kw).frames
+    assert torch.equal(a, b)
+    with pytest.raises(OSError):
+        pipeline.StableVideoControlPipeline.from_pretrained(str(tmp_path / "missing"))
