@@ -336,3 +336,25 @@ def test_two_clips_per_gpu_cfg_batch_4(order):
                     latents=a["latents"].clone(), output_type="latent", image_embeddings=a["image_embeds_cond"],
                     image_latents=a["image_latents_cond"])
         assert rel(solo.frames[0], out.frames[0]) < 2e-2
+
+
+def test_fp16_and_fp32_inputs_like_autocast_callers(tiny):
+    """callers may run the modules under torch.autocast(fp16) with fp32 or
+    fp16 tensors; the drop-in fixes its compute dtype and casts at entry/exit (output dtype = input)."""
+    _, _, mu, mc = tiny
+    inp, x = _inputs(3, 8, 16, 2.0)
+    t = torch.tensor(0.17, device=dev)
+    outs = {}
+    for dt in (torch.float32, torch.float16, torch.bfloat16):
+        with torch.autocast("cuda", dtype=torch.float16, enabled=dt is torch.float16):
+            d, m = mc(x.to(dt), timestep=t, encoder_hidden_states=inp["image_embeddings"].to(dt),
+                      added_time_ids=inp["added_time_ids"].to(dt), control_cond=inp["cond_em"].to(dt), return_dict=False)
+            y = mu(sample=x.to(dt), timestep=t, encoder_hidden_states=inp["image_embeddings"].to(dt),
+                   added_time_ids=inp["added_time_ids"].to(dt), down_block_additional_residuals=d,
+                   mid_block_additional_residuals=m, return_dict=False)[0]
+        assert y.dtype == dt and m.dtype == dt and all(r.dtype == dt for r in d)
+        outs[dt] = y.float()
+    # (the inputs themselves are rounded to the caller's dtype: a few 1e-3 of input noise, amplified by the
+    #  random-init tiny network)
+    assert rel(outs[torch.float16], outs[torch.float32]) < 3e-2
+    assert rel(outs[torch.bfloat16], outs[torch.float32]) < 5e-2
