@@ -49,7 +49,9 @@ for (T, h, w) in ((14, 40, 64), (25, 72, 128)):
         tr.attn2.off, tr.tattn2.off = 0, C
         ctx_w = models._w(torch.cat(cw)); ctx_b = models._f(torch.cat(cb))
         from types import SimpleNamespace
-        aux = SimpleNamespace(temb=ops.small_linear(emb, holder.temb_w, holder.temb_b, act_in=True), ctx=ops.small_linear(ehs, ctx_w, ctx_b))
+        ctx = ops.small_linear(ehs, ctx_w, ctx_b)
+        aux = SimpleNamespace(temb=ops.small_linear(emb, holder.temb_w, holder.temb_b, act_in=True), ctx=ctx,
+                              ctx_all=ctx, vB=ctx.shape[0], b0=0)
         x = torch.randn(M, C, device=dev).to(BF)
         ms = timeit(lambda: rb(x, aux, g))
         fl = 2.0 * M * (18 * C * C + 6 * C * C)
