@@ -411,7 +411,7 @@ def clip_patchify(img: torch.Tensor, patch: int, mean: torch.Tensor, std: torch.
 
 
 # ---- fused nearest-2x upsample + 3x3 conv (diffusers Upsample2D) --------------------------------------
-def pack_upconv3x3(w: torch.Tensor) -> torch.Tensor:
+def pack_upconv3x3(w: torch.Tensor, device="cuda", dtype=BF16) -> torch.Tensor:
     """Conv2d weight [N, C, 3, 3] of `Upsample2D.conv` -> four phase matrices [4, N, 4*C] (bf16).
 
     conv3x3(nearest2x(x)) at output pixel (2y+py, 2x+px) only ever sees a 2x2 patch of x: for py = 0 the
@@ -433,7 +433,7 @@ def pack_upconv3x3(w: torch.Tensor) -> torch.Tensor:
                             acc += w[:, :, a, b]
                     blocks.append(acc)
             out[py * 2 + px] = torch.cat(blocks, dim=1)
-    return out.to(device="cuda", dtype=BF16).contiguous()
+    return out.to(device=device, dtype=dtype).contiguous()
 
 
 def upsample2x_conv3x3(x: torch.Tensor, frames: int, H: int, W: int, wp: torch.Tensor,

@@ -174,3 +174,31 @@ def test_diffusers_dir_layouts(tmp_path, mode):
     assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
     with pytest.raises(OSError):
         checkpoint.load_diffusers_dir(str(tmp_path), "unet")
+
+
+def test_subpixel_upsample_conv_algebra_cpu():
+    """conv3x3(nearest2x(x)) == four 2x2 phase convs of x with the summed taps of ops.pack_upconv3x3
+    (pure fp32 on the CPU: pins the weight packing and the patch/offset convention of
+    ctrlv_upsample2x_conv3x3 without a GPU)."""
+    import torch.nn.functional as F
+    from ctrlv_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    N, Cc, H, W = 5, 3, 6, 7
+    x = torch.randn(2, Cc, H, W, generator=g)
+    w = torch.randn(N, Cc, 3, 3, generator=g)
+    want = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, padding=1)
+    wp = ops.pack_upconv3x3(w, device="cpu", dtype=torch.float32)          # [4, N, 4*C]
+    assert tuple(wp.shape) == (4, N, 4 * Cc)
+    xp = F.pad(x, (1, 1, 1, 1))                                            # zero halo = TMA out-of-bounds fill
+    got = torch.zeros_like(want)
+    for py in (0, 1):
+        for px in (0, 1):
+            acc = torch.zeros(2, N, H, W)
+            i = 0
+            for dy in ((-1, 0) if py == 0 else (0, 1)):
+                for dx in ((-1, 0) if px == 0 else (0, 1)):
+                    patch = xp[:, :, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W]  # x(y + dy, x + dx)
+                    acc += torch.einsum("nc,bchw->bnhw", wp[py * 2 + px][:, i * Cc:(i + 1) * Cc], patch)
+                    i += 1
+            got[:, :, py::2, px::2] = acc
+    assert torch.allclose(got, want, atol=1e-5), float((got - want).abs().max())
