@@ -202,3 +202,33 @@ def test_subpixel_upsample_conv_algebra_cpu():
                     i += 1
             got[:, :, py::2, px::2] = acc
     assert torch.allclose(got, want, atol=1e-5), float((got - want).abs().max())
+
+
+def test_device_polynomial_constants():
+    """The two fitted approximations used on the device, checked on the CPU with the constants read
+    from the sources: the tanh-form erf-GELU of the GEGLU epilogue (max abs error 2.5e-5) and the cubic
+    2^f of the attention softmax's FMA-pipe exponentials (max rel. error 7.5e-5 on [-0.5, 0.5])."""
+    import math
+    import numpy as np
+    src = open(os.path.join(ROOT, "ctrl-v_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("void geglu2_f("):]
+    c2, c1 = (float(v) for v in re.findall(r"f2_splat\((-?[0-9.eE+-]+)f\)", body[:body.index("f2_fma(u, p")])[:2])
+    c0 = float(re.search(r"p = f2_fma\(u, p, f2_splat\((-?[0-9.eE+-]+)f\)\)", body).group(1))
+    g = np.linspace(-12.0, 12.0, 480001)
+    u = np.minimum(g * g, 64.0)
+    approx = 0.5 * g * (1.0 + np.tanh(g * (c0 + u * (c1 + u * c2))))
+    exact = 0.5 * g * (1.0 + np.vectorize(math.erf)(g / math.sqrt(2.0)))
+    assert float(np.abs(approx - exact).max()) < 3e-5
+    fl = open(os.path.join(ROOT, "ctrl-v_b200", "csrc", "flash.cu")).read()
+    seg = fl[fl.index("uint64_t q = f2_fma(ff"):]
+    k3, k2 = (float(v) for v in re.findall(r"f2_splat\((-?[0-9.eE+-]+)f\)", seg[:seg.index(";")]))
+    k1 = float(re.search(r"q = f2_fma\(ff, q, f2_splat\((0\.69[0-9]+)f\)\)", seg).group(1))
+    k0 = float(re.search(r"q = f2_fma\(ff, q, f2_splat\((0\.99[0-9]+)f\)\)", seg).group(1))
+    f = np.linspace(-0.5, 0.5, 100001)
+    p = ((k3 * f + k2) * f + k1) * f + k0
+    assert float(np.abs(p / 2.0 ** f - 1.0).max()) < 1e-4
+    # the exponent insert: 2^x = 2^f * 2^n with n = round(x) taken from the low mantissa bits of x + 1.5 * 2^23
+    x = np.float32(-37.3)
+    t = np.float32(x + np.float32(12582912.0))
+    n = int(t.view(np.uint32)) - 0x4B400000
+    assert n == round(float(x)) and abs(float(x) - n) <= 0.5
