@@ -17,6 +17,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "fastdiv.h"
 #include "../../include/ctrlv_b200.h"
 
 namespace ctrlv {
@@ -33,32 +34,6 @@ __device__ long long g_trace[8 * 64];
 struct IgemmSeg {
   int map, c0, nchunk, dx, dy, dz;
 };
-
-// exact unsigned division by a launch-time constant (Granlund-Montgomery round-up method):
-// q = (t + ((n - t) >> sh1)) >> sh2 with t = umulhi(n, mul) — 4 instructions instead of the ~25 of
-// a hardware-less 32-bit division, which the per-tile index decomposition paid six times.
-struct FastDiv {
-  uint32_t d, mul, sh1, sh2;
-};
-static FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f;
-  f.d = d;
-  if (d <= 1) { f.mul = 0; f.sh1 = 0; f.sh2 = 0; return f; }
-  uint32_t l = 0;
-  while ((1ull << l) < d) ++l;
-  f.mul = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
-  f.sh1 = 1;
-  f.sh2 = l - 1;
-  return f;
-}
-__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) {
-  const uint32_t t = __umulhi(n, f.mul);
-  return (t + ((n - t) >> f.sh1)) >> f.sh2;
-}
-__device__ __forceinline__ void fd_divmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
-  q = fd_div(n, f);
-  r = n - q * f.d;
-}
 
 struct IgemmParams {
   CUtensorMap tmA[CTRLV_MAX_SRC];

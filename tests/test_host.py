@@ -232,3 +232,37 @@ def test_device_polynomial_constants():
     t = np.float32(x + np.float32(12582912.0))
     n = int(t.view(np.uint32)) - 0x4B400000
     assert n == round(float(x)) and abs(float(x) - n) <= 0.5
+
+
+def test_fastdiv_header_exact_on_cpu(tmp_path):
+    """ctrl-v_b200/csrc/fastdiv.h (tile-index decomposition of the implicit GEMM) against the hardware
+    division: every divisor up to 4096 over a dense range of dividends plus the 32-bit corner values."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    src = tmp_path / "fd.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "fastdiv.h"
+int main() {
+  long bad = 0;
+  const uint32_t corner[] = {0u, 1u, 2u, 0x7fffffffu, 0x80000000u, 0xfffffffeu, 0xffffffffu, 123456789u, 4000000000u};
+  for (uint32_t d = 1; d <= 4096; ++d) {
+    const ctrlv::FastDiv f = ctrlv::make_fastdiv(d);
+    for (uint32_t n = 0; n < 300000; n += (d < 64 ? 1 : 7)) {
+      uint32_t q, r;
+      ctrlv::fd_divmod(n, f, q, r);
+      if (q != n / d || r != n % d) ++bad;
+    }
+    for (uint32_t n : corner) if (ctrlv::fd_div(n, f) != n / d) ++bad;
+  }
+  std::printf("bad=%ld\n", bad);
+  return bad != 0;
+}
+''')
+    exe = tmp_path / "fd"
+    inc = os.path.join(ROOT, "ctrl-v_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", inc, "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout + out.stderr
