@@ -82,6 +82,7 @@ SIGNATURES = {
     "ctrlv_version": (C.c_char_p, []),
     "ctrlv_device_check": (_I, []),
     "ctrlv_igemm": (_I, [C.POINTER(IgemmDesc), _P]),
+    "ctrlv_igemm_plan": (_I, [C.POINTER(IgemmDesc), _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ctrlv_linear": (_I, [_P, _L, _I, _I, _P, _I, C.POINTER(Epilogue), _P]),
     "ctrlv_conv3x3": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I,
                            C.POINTER(Epilogue), _P]),

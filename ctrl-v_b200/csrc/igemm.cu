@@ -594,6 +594,14 @@ static int choose_bn(int N, long long tiles_m, int num_sms) {
   return best;
 }
 
+// CTA pairs (cta_group::2) or single CTAs for a problem (see the comment at the call site)
+static int choose_cg(int BN, int N, int tiles_m, int kblocks) {
+  return (BN % 32 == 0 && N % BN == 0 &&
+          ((tiles_m >= 16 && (kblocks >= 20 || (kblocks >= 10 && N >= 2560))) ||
+           (tiles_m >= 8 && kblocks >= 100)))  // (few m-tiles: only the long-K convs gain)
+             ? 2 : 1;
+}
+
 static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   int rc = device_props();
   if (rc) return rc;
@@ -663,9 +671,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   // (TMA writes + MMA reads ~ 96 KB per k-block); a pair halves the B traffic and deepens the TMA
   // ring.  Measured on this path's shapes (profiles/r01_cg2_vs_cg1.txt): +15-19 % on the 3x3 convs,
   // a win for K >= 1280 and for wide-N K = 640, a loss for K = 320 and tiny M.
-  p.cg = (p.BN % 32 == 0 && d->N % p.BN == 0 &&
-          ((tiles_m >= 16 && (kblocks_pre >= 20 || (kblocks_pre >= 10 && d->N >= 2560))) ||
-           (tiles_m >= 8 && kblocks_pre >= 100))) ? 2 : 1;  // (few m-tiles: only the long-K convs gain)
+  p.cg = choose_cg(p.BN, d->N, tiles_m, kblocks_pre);
   if (const char* e = getenv("CTRLV_DEBUG_CG")) p.cg = atoi(e);  // developer override
   p.tiles_total = ((tiles_m + p.cg - 1) / p.cg) * p.tiles_n;
   if (d->out_X > 0) {
@@ -945,4 +951,25 @@ extern "C" int ctrlv_conv_t3(const void* src, int32_t C, int32_t B, int32_t T, i
   d.W = W; d.N = N; d.K = 3 * C;
   d.ep = *ep;
   return igemm_launch(&d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Tile plan of a problem without launching it (no CUDA calls: usable on a host without a GPU): the
+// row-box, the n-tile width and the cta_group the launcher would pick on a device with `num_sms` SMs.
+extern "C" int ctrlv_igemm_plan(const ctrlv_igemm_desc* d, int32_t num_sms, int32_t* box_xyz, int32_t* bn,
+                                int32_t* cta_group) {
+  CTRLV_CHECK_ARG(d != nullptr && box_xyz != nullptr && bn != nullptr && cta_group != nullptr && num_sms > 0,
+                  "igemm_plan: bad arguments");
+  CTRLV_CHECK_ARG(d->X > 0 && d->Y > 0 && d->Z > 0 && d->N > 0 && d->N % 32 == 0 && d->nseg >= 1 && d->nseg <= CTRLV_MAX_SEG,
+                  "igemm_plan: bad descriptor");
+  int bx, by, bz;
+  choose_box(d->X, d->Y, d->Z, &bx, &by, &bz);
+  const int tiles_m = ((d->X + bx - 1) / bx) * ((d->Y + by - 1) / by) * ((d->Z + bz - 1) / bz);
+  int kblocks = 0;
+  for (int s = 0; s < d->nseg; ++s) kblocks += d->seg[s].nchunk;
+  int BN = d->bn > 0 ? d->bn : choose_bn(d->N, tiles_m, num_sms);
+  if (BN == 0) BN = d->N >= 256 ? 256 : ((d->N + 31) / 32) * 32;
+  box_xyz[0] = bx; box_xyz[1] = by; box_xyz[2] = bz;
+  *bn = BN;
+  *cta_group = choose_cg(BN, d->N, tiles_m, kblocks);
+  return CTRLV_OK;
 }

@@ -109,6 +109,11 @@ typedef struct ctrlv_igemm_desc {
  * Everything below that is a convolution or a Linear is a thin wrapper over it. */
 int ctrlv_igemm(const ctrlv_igemm_desc* desc, void* stream);
 
+/* Introspection (no CUDA calls): the row box (bx, by, bz), n-tile width and cta_group (1 or 2) the
+ * launcher picks for `desc` on a device with `num_sms` SMs — lets host tests pin the tiling heuristics. */
+int ctrlv_igemm_plan(const ctrlv_igemm_desc* desc, int32_t num_sms, int32_t* box_xyz, int32_t* bn,
+                     int32_t* cta_group);
+
 /* nn.Linear (diffusers Attention.to_q/k/v/to_out, FeedForward, proj_in/out, 1x1 convs incl. the
  * ControlNet zero-convs controlnet.py:148-185,331-339):  out[M][N] = A[M][K] * W[N][K]^T. */
 int ctrlv_linear(const void* A, int64_t lda, int32_t M, int32_t K, const void* W, int32_t N,

@@ -266,3 +266,37 @@ int main() {
     subprocess.run(["g++", "-O2", "-std=c++17", "-I", inc, "-o", str(exe), str(src)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout + out.stderr
+
+
+def test_tile_plan_heuristics_cpu():
+    """ctrlv_igemm_plan (no CUDA calls): the n-tile / cta_group choices for the step's characteristic
+    problems on a 148-SM device, as measured best in profiles/r01_igemm_tile_sweep.json."""
+    from ctrlv_b200 import _lib
+    lib = _lib.load(build_if_missing=False)
+
+    def plan(X, Y, Z, K, N):
+        d = _lib.IgemmDesc()
+        d.nsrc = 1
+        d.X, d.Y, d.Z, d.N, d.K = X, Y, Z, N, K
+        d.nseg = 1
+        d.seg[0].nchunk = K // 64
+        box = (ctypes.c_int32 * 3)(); bn = ctypes.c_int32(); cg = ctypes.c_int32()
+        assert lib.ctrlv_igemm_plan(ctypes.byref(d), 148, box, ctypes.byref(bn), ctypes.byref(cg)) == 0
+        return tuple(box), bn.value, cg.value
+
+    # level-0 GEGLU up-projection: widest tile, single CTAs (K = 320 loses with CTA pairs)
+    assert plan(71680, 1, 1, 320, 2560)[1:] == (256, 1)
+    # level-2 GEGLU (was BN=128 before the cost-model refit: 115 -> 86 us), level-1 QKV, level-1 residual linear
+    assert plan(4480, 1, 1, 1280, 10240)[1:] == (256, 2)
+    assert plan(17920, 1, 1, 640, 1920)[1:] == (192, 1)
+    assert plan(17920, 1, 1, 640, 640)[1:] == (160, 1)
+    # 3x3 convs: level 0 (K = 2880) pairs; level 3 (9 m-tiles, K = 11520) pairs since the refit
+    box, bn, cg = plan(64, 40, 28, 2880, 320)
+    assert box[0] * box[1] * box[2] <= 128 and (bn, cg) == (160, 2)
+    assert plan(8, 5, 28, 11520, 1280)[2] == 2
+    # tiny M, short K: single CTA
+    assert plan(1120, 1, 1, 1280, 1280)[2] == 1
+    # the box never exceeds one 128-row MMA tile and covers the row space
+    for X, Y, Z in ((64, 40, 28), (16, 10, 28), (2560, 14, 2), (7, 3, 5)):
+        b = plan(X, Y, Z, 64, 64)[0]
+        assert 1 <= b[0] * b[1] * b[2] <= 128 and b[0] <= max(X, 128) and b[1] <= Y and b[2] <= Z
