@@ -72,16 +72,12 @@ template <int NV>
 struct EpRows {  // per (tile, warp): the rows this lane touches in the transposed (coalesced) mapping
   static constexpr int CPR = NV / 8;    // 16-byte pieces per row of one chunk
   static constexpr int RPI = 32 / CPR;  // rows covered by one warp-wide 16-byte access
-  int mT[CPR];
-  bool vT[CPR];
+  int mT[CPR];  // output row (>= 0), or -1 for a row outside the problem (one register instead of two)
   __device__ __forceinline__ void init(long long m, bool valid) {
     const int lane = threadIdx.x & 31;
+    const int mv = valid ? (int)m : -1;
 #pragma unroll
-    for (int i = 0; i < CPR; ++i) {
-      const int r = lane / CPR + RPI * i;
-      mT[i] = __shfl_sync(0xffffffffu, (int)m, r);
-      vT[i] = __shfl_sync(0xffffffffu, (int)valid, r) != 0;
-    }
+    for (int i = 0; i < CPR; ++i) mT[i] = __shfl_sync(0xffffffffu, mv, lane / CPR + RPI * i);
   }
   // 16-byte slot of (row, piece) in the warp tile, XOR-swizzled so that both the row-owner access
   // (lane = row) and the transposed access (CPR lanes per row) are bank-conflict free
@@ -110,7 +106,7 @@ struct ResPrefetch {
 #pragma unroll
       for (int i = 0; i < CPR; ++i) {
         r1[i] = make_uint4(0, 0, 0, 0);
-        if (rows.vT[i])
+        if (rows.mT[i] >= 0)
           r1[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res1) +
                                                        (size_t)rows.mT[i] * ep.ld_res1 + o0 + (lane % CPR) * 8));
       }
@@ -196,7 +192,7 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
 #pragma unroll
       for (int i = 0; i < CPR; ++i) {
         const uint4 u = wst[EpRows<NV>::slot(lane / CPR + RPI * i, lane % CPR)];
-        if (rows.vT[i])
+        if (rows.mT[i] >= 0)
           *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)rows.mT[i] * ep.ld_out + o0 +
                                     (lane % CPR) * 8) = u;
       }
