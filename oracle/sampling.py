@@ -6,7 +6,10 @@ Restates the sampling arithmetic of the Box2Video hot path:
     scale_model_input / step) — called from
     /root/reference/src/ctrlv/pipelines/pipeline_video_control.py:259,301,332;
   * the loop body pipeline_video_control.py:298-343 (`denoise_step`) and the loop (`sample_loop`).
-PARITY UNPINNED (no reference fixtures exist); pinned by the known answers in tests/test_oracle.py.
+PARITY: the loops (`denoise_step`, `sample_loop`, `sample_loop_bbox_predictor`) are PINNED bit-exact against the
+reference's own `__call__`s run through tests/golden/ref_shim.py (tests/test_reference_pin.py); the scheduler
+arithmetic (a diffusers restatement) is UNPINNED — no reference fixtures exist — and held by the known answers
+in tests/test_oracle.py.
 """
 from __future__ import annotations
 

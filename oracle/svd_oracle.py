@@ -11,10 +11,17 @@ the reference's own two forwards on top:
                                              (constructor: diffusers UNetSpatioTemporalConditionModel)
   * ``denoise_step`` / ``sample_loop``    <- src/ctrlv/pipelines/pipeline_video_control.py:298-343
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
- and diffusers cannot be imported here, so this oracle is pinned only by
-self-made checks (tests/test_oracle.py): exact parameter counts 1,524,623,082 (UNet) and
-680,946,897 (ControlNet), the diffusers key set, scheduler known answers, algebraic identities.
+PARITY — two layers with different status:
+  * the reference's IN-REPO code (the two forwards, the ControlNet constructor / from_unet, the
+    pipeline loops) is PINNED: tests/test_reference_pin.py loads those files from /root/reference as
+    they lie, runs them on a stand-in `diffusers` whose blocks are the classes below
+    (tests/golden/ref_shim.py) and requires bit-exact equality with this module; the vectors the
+    reference code produced are committed (tests/golden/ref_forward.pt) and checked everywhere;
+  * the arithmetic INSIDE the diffusers blocks (below) is UNPINNED: the reference ships no tests,
+    golden vectors or fixtures and diffusers cannot be imported here, so it is
+    held only by self-made checks (tests/test_oracle.py): exact parameter counts 1,524,623,082
+    (UNet) and 680,946,897 (ControlNet), the diffusers key set, scheduler known answers, algebraic
+    identities.
 
 diffusers source files restated (0.27.2): models/unets/unet_spatio_temporal_condition.py,
 models/unets/unet_3d_blocks.py, models/resnet.py, models/transformers/transformer_temporal.py,

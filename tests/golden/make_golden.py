@@ -2,7 +2,8 @@
 
 The reference ships no golden vectors and its arithmetic lives in the absent
 diffusers==0.27.2, so these fixtures pin the ORACLE RESTATEMENT against drift, not the reference:
-parity stays "unpinned" in the sense of the task statement.  Re-run:  python tests/golden/make_golden.py
+that part of the parity stays "unpinned" in the sense of the task statement (the in-repo reference code is
+pinned separately: make_ref_golden.py / ref_forward.pt).  Re-run:  python tests/golden/make_golden.py
 """
 import os
 import sys
