@@ -292,6 +292,12 @@ class StableVideoControlPipeline:
         return (g > 1) if isinstance(g, (int, float)) else bool(g.max() > 1)
 
     def check_inputs(self, image, cond_images, height, width):  # pipeline_video_control.py:51-68
+        # `image=None` is this package's extension (precomputed image_embeddings= / image_latents=)
+        if image is not None and not isinstance(image, (torch.Tensor, list)):
+            import PIL.Image
+            if not isinstance(image, PIL.Image.Image):
+                raise ValueError("`image` has to be of type `torch.FloatTensor` or `PIL.Image.Image` or "
+                                 f"`List[PIL.Image.Image]` but is {type(image)}")
         if not isinstance(cond_images, torch.Tensor):
             raise ValueError("`cond_images` has to be of type `torch.FloatTensor` but is " f"{type(cond_images)}")
         if height % 8 != 0 or width % 8 != 0:
@@ -473,7 +479,12 @@ class VideoDiffusionPipeline(StableVideoControlPipeline):
         super().__init__(vae=vae, image_encoder=image_encoder, unet=unet, controlnet=None,
                          scheduler=scheduler, feature_extractor=feature_extractor)
 
-    def check_inputs(self, image, height, width):  # diffusers check_inputs: only the size rule applies here
+    def check_inputs(self, image, height, width):  # diffusers StableVideoDiffusionPipeline.check_inputs
+        if image is not None and not isinstance(image, (torch.Tensor, list)):  # None: precomputed conditioning
+            import PIL.Image
+            if not isinstance(image, PIL.Image.Image):
+                raise ValueError("`image` has to be of type `torch.FloatTensor` or `PIL.Image.Image` or "
+                                 f"`List[PIL.Image.Image]` but is {type(image)}")
         if height % 8 != 0 or width % 8 != 0:
             raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
 

@@ -194,3 +194,84 @@ def test_oracle_reproduces_reference_pipeline_vectors(models):
         assert rel(got, gold["control_pipeline_latents_from_frames"]) < 1e-4
         got = S.sample_loop_bbox_predictor(ou, inp, num_steps=G.STEPS, num_cond_bbox_frames=1)
         assert rel(got, gold["bbox_pipeline_latents"]) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# row f-3: the image-embedding prologue against the reference's own `encode_video_image`
+# ------------------------------------------------------------------------------------------------
+def _reference_functions(relpath, names, extra_ns=None):
+    """Function definitions taken from a reference source file's AST and executed as they are (the
+    modules import diffusers at the top and cannot be imported whole)."""
+    import ast
+    path = os.path.join(R.REFERENCE_SRC, relpath)
+    tree = ast.parse(open(path).read())
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    ns = {"torch": torch}
+    ns.update(extra_ns or {})
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    assert set(names) <= set(ns)
+    return ns
+
+
+@live
+def test_reference_encode_video_image_equals_oracle_encode_image():
+    """src/ctrlv/utils/util.py:97-125 (antialiased resize to 224, un-normalise + clamp, CLIP
+    normalisation by the real `CLIPImageProcessor`, `image_encoder(...).image_embeds`) with a small
+    random `transformers` CLIP tower, against `clip_oracle.encode_image(clamp=True)`."""
+    tf = pytest.importorskip("transformers")
+    from oracle import clip_oracle as CO
+    resize = _reference_functions("bbox_generator_baseline/utils/image_encoder.py",
+                                  {"_resize_with_antialiasing", "_compute_padding", "_filter2d", "_gaussian",
+                                   "_gaussian_blur2d"})
+    ref = _reference_functions("utils/util.py", {"encode_video_image"},
+                               {"_resize_with_antialiasing": resize["_resize_with_antialiasing"]})
+    cfg = dict(CO.TINY_CLIP_CONFIG, image_size=224, patch_size=32)
+    torch.manual_seed(3)
+    hf = tf.CLIPVisionModelWithProjection(tf.CLIPVisionConfig(**cfg)).eval()
+    mine = CO.CLIPVisionModelWithProjection(**cfg).eval()
+    mine.load_state_dict({k: v for k, v in hf.state_dict().items() if not k.endswith("position_ids")})
+    g = torch.Generator().manual_seed(4)
+    for shape in ((2, 3, 320, 512), (1, 3, 96, 160)):
+        image01 = torch.rand(shape, generator=g)
+        with torch.no_grad():
+            want = ref["encode_video_image"](image01 * 2.0 - 1.0, tf.CLIPImageProcessor(), torch.float32, hf)
+            got = CO.encode_image(mine, image01, clamp=True)
+        assert got.shape == (shape[0], 1, cfg["projection_dim"]) and want.shape == (shape[0], cfg["projection_dim"])
+        assert torch.allclose(got[:, 0], want, atol=2e-5, rtol=1e-4), float((got[:, 0] - want).abs().max())
+
+
+@live
+def test_product_host_helpers_equal_reference_helpers():
+    """Host-side glue of this repo's pipeline (no CUDA involved) against the reference's own helpers:
+    `get_add_time_ids` (src/ctrlv/utils/util.py:147-170), `_encode_vae_condition`'s layout rules and
+    `check_inputs` (pipeline_video_control.py:51-68)."""
+    from types import SimpleNamespace
+    from ctrlv_b200.pipeline import StableVideoControlPipeline as Mine
+    ref = _reference_functions("utils/util.py", {"get_add_time_ids", "get_model_attr"}, {"nn": torch.nn})
+    unet = SimpleNamespace(config=SimpleNamespace(addition_time_embed_dim=256),
+                           add_embedding=SimpleNamespace(linear_1=SimpleNamespace(in_features=768)))
+    me = Mine.__new__(Mine)
+    me.unet = unet
+    for fps, mb, na, bs in ((6, 127, 0.02, 1), (24, 40, 0.1, 3)):
+        want = ref["get_add_time_ids"](fps, mb, na, torch.float32, bs, unet)
+        got = me._get_add_time_ids(fps, mb, na, bs)
+        assert got.dtype == want.dtype and torch.equal(got, want)
+    unet.add_embedding.linear_1.in_features = 512  # mis-configured model: same exception type
+    with pytest.raises(ValueError):
+        ref["get_add_time_ids"](6, 127, 0.02, torch.float32, 1, unet)
+    with pytest.raises(ValueError):
+        me._get_add_time_ids(6, 127, 0.02, 1)
+    # check_inputs: the reference's own method (through the shim) and ours reject the same calls
+    r = R.load_reference()
+    theirs = r.StableVideoControlPipeline.__new__(r.StableVideoControlPipeline)
+    img, cond = torch.zeros(1, 3, 64, 64), torch.zeros(1, 2, 4, 8, 8)
+    for args in ((img, cond, 64, 64), (img, cond, 60, 64), (img, cond, 64, 36), (3.0, cond, 64, 64),
+                 (img, [cond], 64, 64), (img, None, 64, 64)):
+        outcome = []
+        for p in (theirs, me):
+            try:
+                p.check_inputs(*args)
+                outcome.append("ok")
+            except ValueError:
+                outcome.append("ValueError")
+        assert outcome[0] == outcome[1], (args[2:], type(args[0]), type(args[1]), outcome)
