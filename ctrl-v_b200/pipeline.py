@@ -40,6 +40,35 @@ class EulerDiscreteScheduler:
         self._step_index = None
         self.num_inference_steps = None
 
+    @classmethod
+    def from_config(cls, config: dict) -> "EulerDiscreteScheduler":
+        """From a diffusers `scheduler_config.json` dictionary.  Only the mode the fused CFG + Euler
+        kernel implements is accepted (the SVD configuration: v-prediction, continuous timesteps,
+        Karras sigmas); anything else raises instead of silently sampling with other arithmetic."""
+        want = {"prediction_type": "v_prediction", "timestep_type": "continuous", "use_karras_sigmas": True}
+        for k, v in want.items():
+            if config.get(k, v) != v:
+                raise NotImplementedError(f"scheduler config {k}={config[k]!r}: only {k}={v!r} (the SVD "
+                                          "EulerDiscreteScheduler configuration) runs on the sm_100a path")
+        name = config.get("_class_name", "EulerDiscreteScheduler")
+        if name != "EulerDiscreteScheduler":
+            raise NotImplementedError(f"scheduler class {name!r}: only EulerDiscreteScheduler is implemented")
+        return cls(sigma_min=float(config.get("sigma_min", 0.002)), sigma_max=float(config.get("sigma_max", 700.0)),
+                   num_train_timesteps=int(config.get("num_train_timesteps", 1000)),
+                   timestep_spacing=config.get("timestep_spacing", "leading"))
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None, **_unused):
+        """`SchedulerMixin.from_pretrained` for a local directory holding `scheduler_config.json`."""
+        import json
+        import os
+        d = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        path = os.path.join(d, "scheduler_config.json")
+        if not os.path.isfile(path):
+            raise OSError(f"{path} not found (this build does not download from the hub)")
+        with open(path) as f:
+            return cls.from_config(json.load(f))
+
     def set_timesteps(self, num_inference_steps: int, device=None):
         c = self.config
         self.num_inference_steps = num_inference_steps
@@ -259,7 +288,8 @@ class StableVideoControlPipeline:
         """`DiffusionPipeline.from_pretrained` for a LOCAL Stable-Video-Diffusion directory
         (tools/eval_video_controlnet.py:116-118): loads `vae/` and `image_encoder/` (and `unet/` unless a
         `unet=` is passed) with the sm_100a drop-ins; `controlnet=` / `unet=` keyword modules are used as
-        given.  The scheduler is the SVD EulerDiscreteScheduler configuration.  No hub download."""
+        given.  The scheduler comes from `scheduler/scheduler_config.json` when the directory has one (it must
+        be the SVD EulerDiscreteScheduler mode), else it is the SVD default configuration.  No hub download."""
         import os
         from . import clip as _clip
         from . import vae as _vae
@@ -278,7 +308,10 @@ class StableVideoControlPipeline:
                 parts[name] = None
         if cls is VideoDiffusionPipeline:
             parts.pop("controlnet", None)
-        return cls(scheduler=kwargs.pop("scheduler", None), feature_extractor=kwargs.pop("feature_extractor", None), **parts)
+        scheduler = kwargs.pop("scheduler", None)
+        if scheduler is None and os.path.isfile(os.path.join(root, "scheduler", "scheduler_config.json")):
+            scheduler = EulerDiscreteScheduler.from_pretrained(root, subfolder="scheduler")
+        return cls(scheduler=scheduler, feature_extractor=kwargs.pop("feature_extractor", None), **parts)
 
     def to(self, *a, **k):  # modules are device-resident by construction
         return self

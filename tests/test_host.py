@@ -300,3 +300,30 @@ def test_tile_plan_heuristics_cpu():
     for X, Y, Z in ((64, 40, 28), (16, 10, 28), (2560, 14, 2), (7, 3, 5)):
         b = plan(X, Y, Z, 64, 64)[0]
         assert 1 <= b[0] * b[1] * b[2] <= 128 and b[0] <= max(X, 128) and b[1] <= Y and b[2] <= Z
+
+
+def test_scheduler_from_pretrained_config(tmp_path):
+    """A Stable-Video-Diffusion directory's scheduler/scheduler_config.json is honoured; modes the
+    fused CFG + Euler kernel does not implement are refused, not silently replaced."""
+    import json
+    from ctrlv_b200.pipeline import EulerDiscreteScheduler
+    svd = {"_class_name": "EulerDiscreteScheduler", "_diffusers_version": "0.24.0.dev0", "beta_end": 0.012,
+           "beta_schedule": "scaled_linear", "beta_start": 0.00085, "clip_sample": False,
+           "interpolation_type": "linear", "num_train_timesteps": 1000, "prediction_type": "v_prediction",
+           "set_alpha_to_one": False, "sigma_max": 700.0, "sigma_min": 0.002, "skip_prk_steps": True,
+           "steps_offset": 1, "timestep_spacing": "leading", "timestep_type": "continuous",
+           "trained_betas": None, "use_karras_sigmas": True}
+    d = tmp_path / "svd" / "scheduler"
+    d.mkdir(parents=True)
+    (d / "scheduler_config.json").write_text(json.dumps(svd))
+    a = EulerDiscreteScheduler.from_pretrained(str(tmp_path / "svd"), subfolder="scheduler").set_timesteps(25)
+    b = EulerDiscreteScheduler().set_timesteps(25)
+    assert torch.equal(a.sigmas, b.sigmas) and torch.equal(a.timesteps, b.timesteps)
+    c = EulerDiscreteScheduler.from_config(dict(svd, sigma_max=80.0, timestep_spacing="trailing")).set_timesteps(10)
+    assert abs(float(c.sigmas[0]) - 80.0) < 1e-4 and c.init_noise_sigma == pytest.approx(80.0, rel=1e-6)
+    for bad in ({"prediction_type": "epsilon"}, {"use_karras_sigmas": False}, {"timestep_type": "discrete"},
+                {"_class_name": "DDIMScheduler"}):
+        with pytest.raises(NotImplementedError):
+            EulerDiscreteScheduler.from_config(dict(svd, **bad))
+    with pytest.raises(OSError):
+        EulerDiscreteScheduler.from_pretrained(str(tmp_path / "nowhere"))
