@@ -241,29 +241,28 @@ def test_reference_encode_video_image_equals_oracle_encode_image():
 
 
 @live
-def test_product_host_helpers_equal_reference_helpers():
+def test_product_host_helpers_equal_reference_helpers(ref):
     """Host-side glue of this repo's pipeline (no CUDA involved) against the reference's own helpers:
     `get_add_time_ids` (src/ctrlv/utils/util.py:147-170), `_encode_vae_condition`'s layout rules and
     `check_inputs` (pipeline_video_control.py:51-68)."""
     from types import SimpleNamespace
     from ctrlv_b200.pipeline import StableVideoControlPipeline as Mine
-    ref = _reference_functions("utils/util.py", {"get_add_time_ids", "get_model_attr"}, {"nn": torch.nn})
+    util = _reference_functions("utils/util.py", {"get_add_time_ids", "get_model_attr"}, {"nn": torch.nn})
     unet = SimpleNamespace(config=SimpleNamespace(addition_time_embed_dim=256),
                            add_embedding=SimpleNamespace(linear_1=SimpleNamespace(in_features=768)))
     me = Mine.__new__(Mine)
     me.unet = unet
     for fps, mb, na, bs in ((6, 127, 0.02, 1), (24, 40, 0.1, 3)):
-        want = ref["get_add_time_ids"](fps, mb, na, torch.float32, bs, unet)
+        want = util["get_add_time_ids"](fps, mb, na, torch.float32, bs, unet)
         got = me._get_add_time_ids(fps, mb, na, bs)
         assert got.dtype == want.dtype and torch.equal(got, want)
     unet.add_embedding.linear_1.in_features = 512  # mis-configured model: same exception type
     with pytest.raises(ValueError):
-        ref["get_add_time_ids"](6, 127, 0.02, torch.float32, 1, unet)
+        util["get_add_time_ids"](6, 127, 0.02, torch.float32, 1, unet)
     with pytest.raises(ValueError):
         me._get_add_time_ids(6, 127, 0.02, 1)
     # check_inputs: the reference's own method (through the shim) and ours reject the same calls
-    r = R.load_reference()
-    theirs = r.StableVideoControlPipeline.__new__(r.StableVideoControlPipeline)
+    theirs = ref.StableVideoControlPipeline.__new__(ref.StableVideoControlPipeline)
     img, cond = torch.zeros(1, 3, 64, 64), torch.zeros(1, 2, 4, 8, 8)
     for args in ((img, cond, 64, 64), (img, cond, 60, 64), (img, cond, 64, 36), (3.0, cond, 64, 64),
                  (img, [cond], 64, 64), (img, None, 64, 64)):
