@@ -255,6 +255,8 @@ def run_b200(a):
     # ---- device-resident timing: W warm-up steps, then exactly K steps
     for i in range(a.warmup):
         st.step(i % nsched)
+    if world > 1:  # warm-up of the job's one collective too (NCCL connects its all-gather channels lazily)
+        parallel.gather_latents(st.latents, world, world, rank)
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
