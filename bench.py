@@ -317,6 +317,9 @@ def run_b200(a):
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "profiles/r01_step_dram_traffic.json: ncu dram__bytes_read+write, cold caches, mean per igemm launch",
                 "peak_source": peak_src, "launches_per_step": int(gemm_n),
+                "timing": "CUDA events around every igemm launch of one eager (un-captured) step in this process, on the "
+                          "launching stream; the timed region replays the same launches from a CUDA graph, which "
+                          "cannot be event-timed per kernel",
                 "algorithmic_tflop_per_step": gemm_fl / 1e12, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
                 "whole_step_tflops": STEP_TFLOP * value / world if (T, h, w) == (14, 40, 64) else None}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
