@@ -5,7 +5,6 @@ Writes gpurun_out/config3.json.  Not a bench.py line: the headline metric stays 
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import sampling as S  # only for make_inputs (synthetic inputs of SURVEY §8d)
 from ctrlv_b200 import models, pipeline
 
 T, h, w, CLIPS, STEPS = 14, 40, 64, 8, 25
@@ -17,11 +16,15 @@ res = {"config": "8 clips x 25 steps, 14x320x512, CFG, one B200", "runs": []}
 for b in batches:
     st = pipeline.DenoiseStep(mu, mc, b, T, h, w, cfg=True, use_graph=True)
     st.set_schedule(sch.sigmas, sch.timesteps)
-    inp = S.make_inputs(T=T, h=h, w=w, batch=b)
-    st.image_latents.copy_(inp["image_latents"]); st.cond_em.copy_(inp["cond_em"])
-    st.ehs.copy_(inp["image_embeddings"].reshape(2 * b, -1)); st.added_time_ids.copy_(inp["added_time_ids"])
-    st.guidance.copy_(inp["guidance"])
-    lat0 = (inp["latents"] * sch.init_noise_sigma).cuda()
+    # synthetic inputs of SURVEY §8d (seed 1234, drawn on the CPU in fp32, uncond halves zero)
+    g = torch.Generator("cpu").manual_seed(1234)
+    lat0 = (torch.randn(b, T, 4, h, w, generator=g) * sch.init_noise_sigma).cuda()
+    il = torch.randn(b, 4, h, w, generator=g).unsqueeze(1).repeat(1, T, 1, 1, 1)
+    emb = torch.randn(b, 1024, generator=g)
+    cond = torch.randn(b, T, 4, h, w, generator=g)
+    st.image_latents.copy_(torch.cat([torch.zeros_like(il), il])); st.cond_em.copy_(torch.cat([torch.zeros_like(cond), cond]))
+    st.ehs.copy_(torch.cat([torch.zeros_like(emb), emb])); st.added_time_ids.copy_(torch.tensor([[6.0, 127.0, 0.02]] * (2 * b)))
+    st.guidance.copy_(torch.linspace(1.0, 3.0, T))
     st.latents.copy_(lat0); st.capture()
     for k in range(3):
         st.step(k)
