@@ -1,13 +1,16 @@
 """bench.py — Box2Video denoise-step throughput on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path (oracle)
+    python bench.py --gpus N --steps K --warmup W                     # this repo's sm_100a path (config 2)
+    python bench.py --impl reference --gpus N --steps K --warmup W    # reference CPU path (oracle, all frames)
+    python bench.py --config 3 [--cfg-split] --gpus N                 # fixed 8 clips x 25 steps over N GPUs
+    python bench.py --config 4                                        # SVD-XT step, 25 frames @576x1024
+    python bench.py --config 5                                        # per-block sweep, one JSON line per block
 
 A "step" is one Euler-EDM iteration of ControlNet + UNet under classifier-free guidance
-(pipeline_video_control.py:298-343) on one clip of 14 frames at 320x512 (latent 14x4x40x64, CFG
-batch 2), bf16, synthetic inputs, random-init weights of the full SVD architecture
-(BASELINE.json configs[1]).  For N > 1 every rank samples its own clip (sample-parallel, weak
-scaling); value = steps of all ranks / max-over-ranks device time.  One JSON line on rank 0.
+(pipeline_video_control.py:298-343), bf16, synthetic inputs, random-init weights of the full SVD
+architecture.  Default (BASELINE.json configs[1], "config 2"): one clip of 14 frames at 320x512 per
+GPU (latent 14x4x40x64, CFG batch 2); for N > 1 every rank samples its own clip (sample-parallel,
+weak scaling); value = steps of all ranks / max-over-ranks device time.  One JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -26,6 +29,8 @@ if ROOT not in sys.path:
 METRIC = "denoise_steps_per_s"
 UNIT = "steps/s"
 STEP_TFLOP = 29.14  # algorithmic work of one CFG step at 14x320x512
+TOTAL_CLIPS = 8     # BASELINE.json configs[2]
+SCHED_STEPS = 25
 
 
 def parse():
@@ -34,17 +39,30 @@ def parse():
     ap.add_argument("--steps", type=int, default=25)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=14)
-    ap.add_argument("--height", type=int, default=320)
-    ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configs[]: 2 = one clip/GPU (default, the metric's config), 3 = fixed 8 clips "
+                         "x 25 steps over N GPUs (strong scaling), 4 = SVD-XT 25x576x1024 step, 5 = per-block sweep")
+    ap.add_argument("--cfg-split", action="store_true",
+                    help="config 3: shard the two CFG branches of a clip group over a GPU pair (N even)")
+    ap.add_argument("--clip-offset", type=int, default=0,
+                    help="index of the first synthetic clip (seed 1234 + index): reproduces rank r's clip on one GPU")
+    ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU-baseline sample (0 = auto)")
-    return ap.parse_args()
+    ap.add_argument("--no-graph", action="store_true")
+    a = ap.parse_args()
+    dflt = (25, 576, 1024) if a.config == 4 else (14, 320, 512)
+    a.frames = a.frames or dflt[0]
+    a.height = a.height or dflt[1]
+    a.width = a.width or dflt[2]
+    return a
 
 
-def workload_name(a):
-    return (f"Box2Video CFG denoise step: SVD UNet (1.52B) + bbox ControlNet (0.68B), 1 clip x {a.frames} frames "
-            f"@{a.height}x{a.width} (latent {a.frames}x4x{a.height // 8}x{a.width // 8}), 25-step Euler-EDM schedule")
+def workload_name(a, clips=1):
+    return (f"Box2Video CFG denoise step: SVD UNet (1.52B) + bbox ControlNet (0.68B), {clips} clip{'s' if clips > 1 else ''} "
+            f"x {a.frames} frames @{a.height}x{a.width} (latent {a.frames}x4x{a.height // 8}x{a.width // 8}), "
+            f"{SCHED_STEPS}-step Euler-EDM schedule")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -121,72 +139,77 @@ def build_oracle_cpu():
     return fill(ou), fill(oc)
 
 
-def cpu_step_time(ou, oc, frames, h, w, repeats=1):
-    """Seconds for one CFG denoise step of the oracle on the host cores with `frames` frames."""
-    import torch
-    from oracle import sampling as S
-    inp = S.make_inputs(T=frames, h=h, w=w)
-    sch = S.EulerDiscreteSchedulerOracle()
-    sch.set_timesteps(25)
-    lat = inp["latents"] * sch.init_noise_sigma
-    gs = inp["guidance"].view(1, -1, 1, 1, 1)
-    best = None
-    with torch.no_grad():
-        for _ in range(repeats):
-            sch.step_index = 0
-            t0 = time.time()
-            S.denoise_step(ou, oc, sch, lat, sch.timesteps[0], inp["image_latents"], inp["image_embeddings"],
-                           inp["added_time_ids"], inp["cond_em"], gs)
-            dt = time.time() - t0
-            best = dt if best is None else min(best, dt)
-    return best
+class CpuStepper:
+    """The reference's loop body on the host cores: one CFG denoise step of the fp32 oracle on the FULL
+    configuration (all frames), stepping through the 25-step schedule like the GPU arm does."""
+
+    def __init__(self, a):
+        import torch
+        from oracle import sampling as S
+        self.torch, self.S = torch, S
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.ou, self.oc = build_oracle_cpu()
+        self.inp = S.make_inputs(T=a.frames, h=a.height // 8, w=a.width // 8)
+        self.sch = S.EulerDiscreteSchedulerOracle()
+        self.sch.set_timesteps(SCHED_STEPS)
+        self.lat = self.inp["latents"] * self.sch.init_noise_sigma
+        self.gs = self.inp["guidance"].view(1, -1, 1, 1, 1)
+
+    def step(self, i):
+        i = i % SCHED_STEPS
+        self.sch.step_index = i
+        t0 = time.time()
+        with self.torch.no_grad():
+            out = self.S.denoise_step(self.ou, self.oc, self.sch, self.lat, self.sch.timesteps[i],
+                                      self.inp["image_latents"], self.inp["image_embeddings"],
+                                      self.inp["added_time_ids"], self.inp["cond_em"], self.gs)
+        dt = time.time() - t0
+        if not bool(self.torch.isfinite(out).all()):
+            raise RuntimeError("oracle step produced non-finite latents")
+        return dt
 
 
-def cpu_baseline(a, budget_s=25.0):
-    import torch
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    ou, oc = build_oracle_cpu()
-    h, w = a.height // 8, a.width // 8
-    frames = a.cpu_frames
-    if frames <= 0:
-        t1 = cpu_step_time(ou, oc, 1, h, w)  # probe (also warms the thread pool / allocator)
-        frames = max(1, min(a.frames, int(budget_s / max(t1, 1e-3))))
-    dt = cpu_step_time(ou, oc, frames, h, w)
-    scale = frames / a.frames
-    return {"value": scale / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": (f"oracle fp32 (torch CPU, {cores} threads): 1 CFG step of ControlNet+UNet on {frames} of "
-                       f"{a.frames} frames @{a.height}x{a.width} in {dt:.1f} s, scaled by {frames}/{a.frames} to the full step")}
+def cpu_baseline(a):
+    """Reported beside the GPU number (not the target): ONE full step of the same workload, all frames."""
+    cs = CpuStepper(a)
+    dt = cs.step(0)
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cs.cores, "kind": "port",
+            "sample": (f"oracle fp32 (torch CPU, {cs.cores} threads): 1 full CFG step of ControlNet+UNet, all {a.frames} "
+                       f"frames @{a.height}x{a.width}, {dt:.1f} s (no scaling, no warm-up step)")}
 
 
 def run_reference(a):
+    """The reference's own CPU path for the same config: every step is a FULL step (all frames).  If the host
+    is so slow that W + K full steps would not end within ~13 min, fewer steps are timed (never fewer
+    frames) and `steps_measured` says how many."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import torch
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    ou, oc = build_oracle_cpu()
-    h, w = a.height // 8, a.width // 8
-    n = a.steps + a.warmup
-    t1 = cpu_step_time(ou, oc, 1, h, w)
-    budget = 150.0 / max(n, 1)  # keep the whole run within a few minutes
-    frames = max(1, min(a.frames, int(budget / max(t1, 1e-3))))
-    for _ in range(a.warmup):
-        cpu_step_time(ou, oc, frames, h, w)
+    cs = CpuStepper(a)
+    t_first = cs.step(0)  # also warms the thread pool / allocator
+    budget = 780.0
+    warm = max(0, a.warmup - 1)
+    steps = a.steps
+    if (warm + steps) * t_first > budget:
+        warm = 0
+        steps = max(1, min(a.steps, int(budget / t_first)))
+    for i in range(warm):
+        cs.step(1 + i)
     t0 = time.time()
-    for _ in range(a.steps):
-        cpu_step_time(ou, oc, frames, h, w)
-    dt = (time.time() - t0) / a.steps
-    value = (frames / a.frames) / dt
-    sample = (f"oracle fp32 (torch CPU, {cores} threads): each step = 1 CFG step of ControlNet+UNet on {frames} of "
-              f"{a.frames} frames @{a.height}x{a.width} ({dt:.2f} s), scaled by {frames}/{a.frames}")
+    for i in range(steps):
+        cs.step(a.warmup + i)
+    dt = (time.time() - t0) / steps
+    value = 1.0 / dt
+    sample = (f"oracle fp32 (torch CPU, {cs.cores} threads): {steps} timed full CFG steps of ControlNet+UNet, all "
+              f"{a.frames} frames @{a.height}x{a.width}, {dt:.2f} s/step (first step {t_first:.1f} s, {warm + 1} warm-up)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "steps_measured": steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "reference_path": "oracle/ (diffusers==0.27.2 restatement; "
-                       "the reference itself cannot be installed offline)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                       "the reference itself cannot be installed offline)", "frames_measured": a.frames,
+                       "extrapolated": False},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cs.cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -196,6 +219,59 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
+def fill_host_inputs(hb, st, sch, clip_ids):
+    """Synthetic inputs: clip c is drawn on the CPU in fp32 from seed 1234 + c, in a fixed
+    order, whatever rank or batch slot it lands in — so an N-GPU job and a 1-GPU run of the same clip agree."""
+    import torch
+    B, T, h, w = st.B, st.T, st.h, st.w
+    assert len(clip_ids) == B
+    for k in ("image_latents", "ehs", "cond_em"):
+        hb[k].zero_()  # uncond halves
+    for j, c in enumerate(clip_ids):
+        g = torch.Generator("cpu").manual_seed(1234 + c)
+        hb["latents"][j].copy_(torch.randn(T, 4, h, w, generator=g) * sch.init_noise_sigma)
+        hb["image_latents"][B + j].copy_(torch.randn(4, h, w, generator=g).unsqueeze(0).expand(T, 4, h, w))
+        hb["ehs"][B + j].copy_(torch.randn(st.ehs.shape[1], generator=g))
+        hb["cond_em"][B + j].copy_(torch.randn(T, 4, h, w, generator=g))
+    hb["added_time_ids"].copy_(torch.tensor([[6.0, 127.0, 0.02]] * (2 * B)))
+    hb["guidance"].copy_(torch.linspace(1.0, 3.0, T))
+
+
+def checksum(t):
+    """Order-independent bit-pattern checksum of an fp32 tensor (exact: equal tensors <=> equal sums of bits
+    is not guaranteed, but any changed element changes it with overwhelming probability)."""
+    import torch
+    return int(t.contiguous().view(torch.int32).to(torch.int64).sum().item())
+
+
+def class_rooflines(prof, peaks):
+    """Per-class achieved rates of one eager step (CUDA events around every launch of the class)."""
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    bw_peak = float(peaks.get("hbm_gbs", 6551.0))
+    out = {}
+
+    def agg(ops_):
+        n = sum(v[0] for k, v in prof.items() if k[0] in ops_)
+        ms = sum(v[1] for k, v in prof.items() if k[0] in ops_)
+        fl = sum(v[2] for k, v in prof.items() if k[0] in ops_)
+        by = sum(v[3] for k, v in prof.items() if k[0] in ops_)
+        return n, ms, fl, by
+    n, ms, fl, _ = agg(("attn_spatial",))
+    if ms > 0:
+        out["attention_spatial"] = {"bound": "tensor", "kernel": "ctrlv::attn2_kernel / attn_kernel<0>", "launches": n,
+                                    "ms_per_step": ms, "achieved": fl / ms / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
+                                    "frac": fl / ms / 1e9 / tf_peak}
+    for name, ops_, kern in (("groupnorm", ("groupnorm",), "ctrlv::gn_stats_kernel + gn_apply_kernel"),
+                             ("layernorm", ("layernorm",), "ctrlv::layernorm_kernel"),
+                             ("attention_temporal", ("attn_temporal",), "ctrlv::attn_kernel<1>")):
+        n, ms, _, by = agg(ops_)
+        if ms > 0:
+            out[name] = {"bound": "hbm", "kernel": kern, "launches": n, "ms_per_step": ms, "achieved": by / ms / 1e6,
+                         "peak": bw_peak, "unit": "GB/s", "frac": by / ms / 1e6 / bw_peak,
+                         "algorithmic_bytes_per_step": by}
+    return out
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -209,20 +285,33 @@ def run_b200(a):
 
     T, h, w = a.frames, a.height // 8, a.width // 8
     unet = models.UNetSpatioTemporalConditionModel(seed=0)
-    ctrl = models.ControlNetModel(seed=1)
-    sch = pipeline.EulerDiscreteScheduler().set_timesteps(25)
-    st = pipeline.DenoiseStep(unet, ctrl, 1, T, h, w, cfg=True, conditioning_scale=1.0, use_graph=True)
+    ctrl = models.ControlNetModel(seed=1, zero_conv_std=0.02)  # non-zero zero-convs: the residual path carries signal
+    sch = pipeline.EulerDiscreteScheduler().set_timesteps(SCHED_STEPS)
+
+    # ---- work partition
+    pair = None
+    if a.config == 3:
+        scaling = "strong"
+        if a.cfg_split:
+            if world % 2:
+                raise SystemExit("--cfg-split needs an even number of GPUs")
+            pair = parallel.CfgPair(rank, world)
+            clip_ids = parallel.shard_clips(TOTAL_CLIPS, world // 2, pair.pair)
+        else:
+            clip_ids = parallel.shard_clips(TOTAL_CLIPS, world, rank)
+        # all local clips are packed into one step (CFG batch 2 x clips): same kernels, more rows per launch
+        clip_ids = [a.clip_offset + c for c in clip_ids]
+        n_job_steps = SCHED_STEPS
+    else:
+        scaling = "weak"
+        clip_ids = [a.clip_offset + rank]
+        n_job_steps = a.steps
+    Bc = len(clip_ids)
+    st = pipeline.DenoiseStep(unet, ctrl, Bc, T, h, w, cfg=True, conditioning_scale=1.0, use_graph=not a.no_graph,
+                              cfg_branch=pair.branch if pair else None, exchange=pair.exchange if pair else None)
     st.set_schedule(sch.sigmas, sch.timesteps)
-    # synthetic inputs: seed 1234 + rank, drawn on the CPU in fp32
-    g = torch.Generator("cpu").manual_seed(1234 + rank)
     hb = st.make_host_buffers()
-    hb["latents"].copy_(torch.randn(st.latents.shape, generator=g) * sch.init_noise_sigma)
-    il = torch.randn(1, 4, h, w, generator=g)
-    hb["image_latents"].zero_(); hb["image_latents"][1:].copy_(il.unsqueeze(1).expand(1, T, 4, h, w))
-    hb["ehs"].zero_(); hb["ehs"][1:].copy_(torch.randn(1, st.ehs.shape[1], generator=g))
-    hb["cond_em"].zero_(); hb["cond_em"][1:].copy_(torch.randn(1, T, 4, h, w, generator=g))
-    hb["added_time_ids"].copy_(torch.tensor([[6.0, 127.0, 0.02]] * 2))
-    hb["guidance"].copy_(torch.linspace(1.0, 3.0, T))
+    fill_host_inputs(hb, st, sch, clip_ids)
     for k in st.HOST_INPUTS:
         getattr(st, k).copy_(hb[k])
     st.capture()
@@ -233,39 +322,48 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # count this repo's kernel launches per step (eager pass with the per-call hook)
+    # ---- one eager step with CUDA events around every launch: launch count (the library's own counter)
+    # and per-class achieved rates
     ops.PROFILE = {}
     st._graph, gsave = None, st._graph
     lat_keep = st.latents.clone()
+    n0 = lib.ctrlv_launch_count()
     st.step(0)
+    launches_per_step = int(lib.ctrlv_launch_count() - n0)
     ops.profile_flush()
     prof = ops.PROFILE
     ops.PROFILE = None
     st._graph = gsave
     st.latents.copy_(lat_keep)
-    # launches: every profiled op is one kernel except groupnorm (2); plus the un-profiled glue ops
-    n_prof = sum(v[0] * {"groupnorm": 2, "upconv3x3": 4}.get(k[0], 1) for k, v in prof.items())
-    glue = 2 + 2 * (2 + 4 + 2) + 13  # prep + cfg_euler, per-model embeds (sinusoid x2, MLP x4, aux x2), axpby
-    launches_per_step = int(n_prof + glue)
-    gemm_ms = sum(v[1] for k, v in prof.items() if k[0] in ("linear", "conv3x3", "conv_t3", "upconv3x3"))
-    gemm_fl = sum(v[2] for k, v in prof.items() if k[0] in ("linear", "conv3x3", "conv_t3", "upconv3x3"))
-    gemm_n = sum(v[0] * (4 if k[0] == "upconv3x3" else 1) for k, v in prof.items()
-                 if k[0] in ("linear", "conv3x3", "conv_t3", "upconv3x3"))
+    gemm_ops = ("linear", "conv3x3", "conv_t3", "upconv3x3")
+    gemm_ms = sum(v[1] for k, v in prof.items() if k[0] in gemm_ops)
+    gemm_fl = sum(v[2] for k, v in prof.items() if k[0] in gemm_ops)
+    gemm_n = sum(v[0] * (4 if k[0] == "upconv3x3" else 1) for k, v in prof.items() if k[0] in gemm_ops)
 
-    # ---- device-resident timing: W warm-up steps, then exactly K steps
+    n_all = TOTAL_CLIPS if a.config == 3 else world
+    n_groups = (world // 2) if pair else world
+
+    def collect():
+        if pair:  # both ranks of a pair hold the same latents: gather one copy per pair
+            bufs = [torch.empty_like(st.latents) for _ in range(world)]
+            dist.all_gather(bufs, st.latents.contiguous())
+            return torch.cat(bufs[0::2])
+        return parallel.gather_latents(st.latents, n_all, world, rank)
+
+    # ---- device-resident timing: W warm-up steps, then exactly K steps (config 3: the whole 25-step job)
     for i in range(a.warmup):
         st.step(i % nsched)
-    if world > 1:  # warm-up of the job's one collective too (NCCL connects its all-gather channels lazily)
-        parallel.gather_latents(st.latents, world, world, rank)
+    if world > 1:  # warm-up of the job's collective too (NCCL connects its channels lazily)
+        collect()
+    st.latents.copy_(hb["latents"].to("cuda"))
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(a.steps):
+    for i in range(n_job_steps):
         st.step(i % nsched)
-    if world > 1:  # collect the clips' latents (the path's only collective)
-        parallel.gather_latents(st.latents, world, world, rank)
+    gathered = collect() if world > 1 else st.latents  # collect the clips' latents (the path's only collective)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -274,14 +372,26 @@ def run_b200(a):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    value = world * a.steps / (ms / 1e3)
+    # N-GPU correctness evidence: this rank's own latents sit bitwise in its slot of the gathered tensor, and
+    # every clip has a checksum that a 1-GPU run of the same clip (--clip-offset) must reproduce
+    gather_ok, sums = None, None
+    if world > 1:
+        mine = (pair.pair if pair else rank)
+        lo = sum(len(parallel.shard_clips(n_all, n_groups, r)) for r in range(mine))
+        ok = torch.tensor([1 if torch.equal(gathered[lo:lo + Bc], st.latents) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gather_ok = bool(ok.item())
+    final = gathered if world > 1 else st.latents
+    sums = [checksum(final[j]) for j in range(final.shape[0])]
+    finite = bool(torch.isfinite(final).all())
 
     # ---- end to end: host buffers in, host latents out, every step
+    fill_host_inputs(hb, st, sch, clip_ids)
     for i in range(min(a.warmup, 3)):
         st.step_host(i % nsched, hb)
     barrier()
     e0.record()
-    for i in range(a.steps):
+    for i in range(n_job_steps):
         st.step_host(i % nsched, hb)
         hb["latents"].copy_(hb["latents_out"])  # next step consumes the result, like the reference loop
     e1.record()
@@ -290,7 +400,7 @@ def run_b200(a):
     barrier()
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * a.steps / (float(ms2.item()) / 1e3)
+    ms2 = float(ms2.item())
     h2d, d2h = st.host_bytes_per_step()
 
     if world > 1:
@@ -305,36 +415,152 @@ def run_b200(a):
         pass
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    # DRAM bytes per igemm launch (average over the step's 429 launches) from the committed ncu pass
-    traffic = None
-    if (T, h, w) == (14, 40, 64):
-        try:
-            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r01_step_dram_traffic.json")))
-                            ["igemm_dram_bytes_per_launch"])
-        except Exception:
-            traffic = None
+    # DRAM bytes per igemm launch (average over the step's launches) from the committed ncu pass of the same step
+    traffic, traffic_src = None, None
+    if (T, h, w, Bc) == (14, 40, 64, 1):
+        for name in ("r02_step_dram_traffic.json", "r01_step_dram_traffic.json"):
+            try:
+                traffic = float(json.load(open(os.path.join(ROOT, "profiles", name)))["igemm_dram_bytes_per_launch"])
+                traffic_src = f"profiles/{name}: ncu dram__bytes_read+write, cold caches, mean per igemm launch"
+                break
+            except Exception:
+                continue
     roofline = {"bound": "tensor", "kernel": "ctrlv::igemm_kernel (tcgen05 implicit GEMM: Linear / 3x3 / temporal conv)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "profiles/r01_step_dram_traffic.json: ncu dram__bytes_read+write, cold caches, mean per igemm launch",
-                "peak_source": peak_src, "launches_per_step": int(gemm_n),
+                "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": int(gemm_n),
                 "timing": "CUDA events around every igemm launch of one eager (un-captured) step in this process, on the "
                           "launching stream; the timed region replays the same launches from a CUDA graph, which "
                           "cannot be event-timed per kernel",
                 "algorithmic_tflop_per_step": gemm_fl / 1e12, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
-                "whole_step_tflops": STEP_TFLOP * value / world if (T, h, w) == (14, 40, 64) else None}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "classes": class_rooflines(prof, peaks)}
+    if a.config == 3:
+        metric, unit = "clips_per_min", "clips/min"
+        value = TOTAL_CLIPS * 60e3 / ms
+        e2e_value = TOTAL_CLIPS * 60e3 / ms2
+        steps_done = n_job_steps
+        work = workload_name(a, TOTAL_CLIPS) + f"; whole job = {TOTAL_CLIPS} clips x {SCHED_STEPS} steps"
+        par = (f"cfg-branch pairs x{world // 2} ({Bc} clips per pair, one all-gather of the model output per step)"
+               if pair else f"sample-parallel x{world} ({Bc} clips packed per GPU)")
+    else:
+        metric, unit = METRIC, UNIT
+        value = world * a.steps / (ms / 1e3)
+        e2e_value = world * a.steps / (ms2 / 1e3)
+        steps_done = a.steps
+        work = workload_name(a)
+        par = f"sample-parallel x{world}"
+        if (T, h, w) == (14, 40, 64):
+            roofline["whole_step_tflops"] = STEP_TFLOP * value / world
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps_done, "warmup": a.warmup,
+            "ms_per_step": ms / steps_done, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(a), "clips_per_gpu": 1, "cfg_batch": 2, "parallelism": f"sample-parallel x{world}",
-                       "weights": "random-init, full SVD architecture", "l2_policy": "inputs+weights (4.4 GB bf16) exceed the 126 MB L2; no flush",
-                       "clips_per_min_at_25_steps": value * 60.0 / 25.0, "cuda_graph": True},
+            "config": {"workload": work, "baseline_config": a.config, "clips_per_gpu": Bc, "cfg_batch": 2 * Bc,
+                       "parallelism": par, "weights": "random-init, full SVD architecture",
+                       "l2_policy": "inputs+weights (4.4 GB bf16) exceed the 126 MB L2; no flush",
+                       "cuda_graph": not a.no_graph, "first_clip": a.clip_offset},
             "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches_per_step * a.steps,
-            "roofline": roofline}
-    if world == 1 and not a.no_cpu_baseline:
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_per_step * steps_done, "launches_per_step": launches_per_step,
+            "launch_count_source": "ctrlv_launch_count() around one eager step (the graph replays the same launches)",
+            "roofline": roofline,
+            "result": {"finite": finite, "gather_ok": gather_ok, "clip_checksums": sums}}
+    if a.config == 2:
+        line["config"]["clips_per_min_at_25_steps"] = value * 60.0 / SCHED_STEPS
+    if world == 1 and not a.no_cpu_baseline and a.config == 2:
         line["cpu_baseline"] = cpu_baseline(a)
     print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# config 5: per-block microbenchmark sweep (one JSON line per block)
+# ------------------------------------------------------------------------------------------------
+def run_sweep(a):
+    import torch
+    from types import SimpleNamespace
+    from ctrlv_b200 import _lib, models, ops
+    lib = _lib.load(build_if_missing=False)
+    if lib.ctrlv_device_check() != 0:
+        raise RuntimeError(lib.ctrlv_last_error().decode())
+    BF, dev = torch.bfloat16, "cuda"
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf, peak_bw = float(peaks.get("bf16_tflops_sustained", 1400.0)), float(peaks.get("hbm_gbs", 6551.0))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2: written between timed calls
+
+    def timeit(fn, iters=a.steps if a.steps < 25 else 10):
+        for _ in range(max(3, a.warmup)):
+            fn()
+        tot = 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(iters):
+            flush.zero_()
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / iters
+
+    def rec(name, ms, bound, flops=0.0, nbytes=0.0):
+        r = {"metric": "block_time", "block": name, "value": round(ms * 1e3, 2), "unit": "us", "higher_is_better": False,
+             "n_gpus": 1, "dtype": "bf16", "data": "synthetic", "config": {"workload": "per-block sweep (BASELINE config 5)",
+                                                                      "l2_policy": "256 MB flush between timed calls"}}
+        if bound == "tensor":
+            r["roofline"] = {"bound": "tensor", "achieved": flops / ms / 1e9, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": flops / ms / 1e9 / peak_tf}
+        else:
+            r["roofline"] = {"bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": peak_bw, "unit": "GB/s",
+                             "frac": nbytes / ms / 1e6 / peak_bw}
+        print(json.dumps(r), flush=True)
+
+    sd = models.random_state_dict(dict(models.SVD_CONFIG), False, seed=0)
+    for (T, h, w) in ((14, 40, 64), (25, 72, 128)):
+        B = 2
+        tag = f"T{T}_{h * 8}x{w * 8}"
+        emb = torch.randn(B, 1280, device=dev)
+        ehs = torch.randn(B, 1024, device=dev)
+        levels = (("down_blocks.0.resnets.1", "down_blocks.0.attentions.1", 320, 5),
+                  ("down_blocks.1.resnets.1", "down_blocks.1.attentions.1", 640, 10),
+                  ("down_blocks.2.resnets.1", "down_blocks.2.attentions.1", 1280, 20))
+        for lvl, (pfx_r, pfx_a, C, heads) in enumerate(levels):
+            hh, ww = h >> lvl, w >> lvl
+            S, F_ = hh * ww, B * T
+            M = F_ * S
+            g = (B, T, hh, ww)
+            qkv = torch.randn(M, 3 * C, device=dev).to(BF)
+            out = torch.empty(M, C, device=dev, dtype=BF)
+            ms = timeit(lambda: ops.attn_spatial(qkv, F_, S, heads, out=out))
+            rec(f"{tag} spatial_attention S={S} heads={heads}", ms, "tensor", flops=4.0 * F_ * heads * S * S * 64)
+            ms = timeit(lambda: ops.attn_temporal(qkv, B, T, S, heads, out=out))
+            rec(f"{tag} temporal_attention S={S} heads={heads} T={T}", ms, "hbm", nbytes=8.0 * M * C)
+            del qkv, out
+            rb = models._ResBlock(sd, pfx_r, 1e-6)
+            tr = models._Transformer(sd, pfx_a, heads, "s_major")
+            temb_w = torch.cat([rb.temb.w, rb.ttemb.w]).contiguous()
+            temb_b = torch.cat([rb.temb.b, rb.ttemb.b]).contiguous()
+            rb.temb_off, rb.ttemb_off = 0, C
+            ctx_w = models._w(torch.cat([tr.attn2.w, tr.tattn2.w]))
+            ctx_b = models._f(torch.cat([tr.attn2.b, tr.tattn2.b]))
+            tr.attn2.off, tr.tattn2.off = 0, C
+            ctx = ops.small_linear(ehs, ctx_w, ctx_b)
+            aux = SimpleNamespace(temb=ops.small_linear(emb, temb_w, temb_b, act_in=True), ctx=ctx, ctx_all=ctx,
+                                  vB=ctx.shape[0], b0=0)
+            x = torch.randn(M, C, device=dev).to(BF)
+            ms = timeit(lambda: rb(x, aux, g))
+            rec(f"{tag} SpatioTemporalResBlock C={C} {hh}x{ww} (2 conv3x3 + 2 conv(3,1,1) + 4 GroupNorm)", ms, "tensor",
+                flops=2.0 * M * (18 * C * C + 6 * C * C))
+            ms = timeit(lambda: ops.conv3x3(x, F_, hh, ww, rb.conv1_w, bias=rb.conv1_b))
+            rec(f"{tag} conv3x3 C={C} {hh}x{ww}", ms, "tensor", flops=2.0 * M * 9 * C * C)
+            ms = timeit(lambda: ops.conv_t3(x, B, T, S, rb.tconv1_w, bias=rb.tconv1_b))
+            rec(f"{tag} conv(3,1,1) C={C} {hh}x{ww}", ms, "tensor", flops=2.0 * M * 3 * C * C)
+            ms = timeit(lambda: ops.groupnorm(x, F_, S, rb.norm2.g, rb.norm2.b, 1e-6, True))
+            rec(f"{tag} GroupNorm+SiLU C={C} {hh}x{ww}", ms, "hbm", nbytes=4.0 * M * C)
+            ms = timeit(lambda: tr(x, aux, g))
+            fl = (2.0 * M * C * C * 14 + 3 * 2.0 * M * 12 * C * C + 4.0 * F_ * heads * S * S * 64
+                  + 4.0 * B * S * heads * T * T * 64)
+            rec(f"{tag} TransformerSpatioTemporalModel C={C} S={S}", ms, "tensor", flops=fl)
+            del x, rb, tr
     return 0
 
 
@@ -342,6 +568,8 @@ def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
+    if a.config == 5:
+        return run_sweep(a)
     return run_b200(a)
 
 

@@ -81,8 +81,10 @@ SIGNATURES = {
     "ctrlv_last_error": (C.c_char_p, []),
     "ctrlv_version": (C.c_char_p, []),
     "ctrlv_device_check": (_I, []),
+    "ctrlv_launch_count": (_L, []),
     "ctrlv_igemm": (_I, [C.POINTER(IgemmDesc), _P]),
     "ctrlv_igemm_plan": (_I, [C.POINTER(IgemmDesc), _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ctrlv_igemm_override": (_I, [_I, _I, _I]),
     "ctrlv_linear": (_I, [_P, _L, _I, _I, _P, _I, C.POINTER(Epilogue), _P]),
     "ctrlv_conv3x3": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I,
                            C.POINTER(Epilogue), _P]),

@@ -1,5 +1,6 @@
 // Library plumbing: thread-local error string, device check, TMA tensor-map encoding through
 // the driver entry point (no link-time dependency on libcuda).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,9 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 bool pdl_enabled() {
   static int v = -1;
@@ -83,6 +87,8 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 }  // namespace ctrlv
 
 extern "C" const char* ctrlv_last_error(void) { return ctrlv::g_err; }
+
+extern "C" int64_t ctrlv_launch_count(void) { return (int64_t)ctrlv::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* ctrlv_version(void) { return "ctrlv_b200 0.1 (sm_100a)"; }
 

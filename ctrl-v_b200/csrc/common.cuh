@@ -46,6 +46,9 @@ void set_last_error(const char* fmt, ...);
 // pdl_trigger() on entry so its successor may be scheduled while it drains, and pdl_wait() before
 // its first access to global memory (full completion + visibility of the predecessor).
 bool pdl_enabled();
+// every kernel launch of the library is counted (ctrlv_launch_count(): the number a caller reports as
+// "launches of this library" is measured, not derived)
+void count_launch();
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
@@ -61,6 +64,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  count_launch();
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

@@ -619,14 +619,17 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
   }
 }
 
-static bool g_attn_init = false;
+static bool g_attn_init[64] = {false};  // per device ordinal
 static int attn_init() {
-  if (g_attn_init) return CTRLV_OK;
+  int dev = 0;
+  CTRLV_CUDA(cudaGetDevice(&dev));
+  CTRLV_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+  if (g_attn_init[dev]) return CTRLV_OK;
   const int smem = 6 * kTile + 1024;
   CTRLV_CUDA(cudaFuncSetAttribute(attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CTRLV_CUDA(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CTRLV_CUDA(cudaFuncSetAttribute(attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2Smem));
-  g_attn_init = true;
+  g_attn_init[dev] = true;
   return CTRLV_OK;
 }
 
@@ -656,9 +659,7 @@ extern "C" int ctrlv_attn_spatial(const void* qkv, int32_t frames, int32_t S, in
   rc = encode_tmap_bf16(&p.tm, qkv, 3, dims, strides, box, true);
   if (rc) return rc;
   // long sequences: two-tile kernel with P in TMEM; short ones: one tile per CTA, 2 CTAs per SM
-  const char* v = getenv("CTRLV_ATTN_V");
-  const int ver = v ? atoi(v) : (S >= 160 ? 2 : 1);
-  if (ver == 2) {
+  if (S >= 160) {
     dim3 grid2((S + 255) / 256, heads, frames);
     CTRLV_CUDA(launch_pdl(attn2_kernel, grid2, dim3(kAttn2Threads), (size_t)kAttn2Smem, stream, p));
     return CTRLV_OK;

@@ -27,10 +27,6 @@ constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
 constexpr int kMaxEpiWarps = 16;  // epilogue warps: 12 (3 per TMEM lane quarter) or 16 (4 per quarter)
 
-// developer trace: clock64 stamps of CTA 0 (8 slots per tile), read back with ctrlv_debug_trace_read
-__device__ long long g_trace[8 * 64];
-#define TRACE(it, k) do { if (p.trace && blockIdx.x == 0 && (it) < 64) g_trace[(it) * 8 + (k)] = clock64(); } while (0)
-
 struct IgemmSeg {
   int map, c0, nchunk, dx, dy, dz;
 };
@@ -49,8 +45,6 @@ struct IgemmParams {
   int bres;       // 1: weight-stationary — the CTA's whole B tile (all K) stays resident in smem
   int bres_off;   // byte offset of the resident B region (after the A ring)
   int m_tiles;    // tiles_x * tiles_y * tiles_z
-  int trace;
-  int dbg;  // developer experiments: bit0 skip MMA issue, bit1 skip TMA loads
   ctrlv_epilogue ep;
 };
 
@@ -529,25 +523,33 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
-static int g_max_smem = 0;
+// per-device launch limits (one process may drive several devices: nothing is cached across devices)
+struct DevProps { int sms; int max_smem; };
+static DevProps g_props[64];  // indexed by device ordinal; sms == 0: not initialised yet
 
-static int device_props() {
-  if (g_num_sms) return CTRLV_OK;
+static int device_props(const DevProps** out) {
   int dev = 0;
   CTRLV_CUDA(cudaGetDevice(&dev));
-  int sms = 0, smem = 0;
-  CTRLV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CTRLV_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  cudaFuncAttributes fa;
-  CTRLV_CUDA(cudaFuncGetAttributes(&fa, igemm_kernel<1, 12>));
-  smem -= (int)fa.sharedSizeBytes;  // static shared memory (barriers, epilogue tiles) counts against the limit
-  CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<1, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  g_max_smem = smem;
-  g_num_sms = sms;
+  CTRLV_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+  DevProps& dp = g_props[dev];
+  if (dp.sms == 0) {
+    int sms = 0, smem = 0;
+    CTRLV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CTRLV_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cudaFuncAttributes fa;
+    CTRLV_CUDA(cudaFuncGetAttributes(&fa, igemm_kernel<1, 12>));
+    smem -= (int)fa.sharedSizeBytes;  // static shared memory (barriers, epilogue tiles) counts against the limit
+    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<1, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dp.max_smem = smem;
+    dp.sms = sms;
+  }
+  *out = &dp;
   return CTRLV_OK;
 }
+
+// tile-plan overrides for tuning sweeps (ctrlv_igemm_override; 0 = heuristic)
+static int g_force_bn = 0, g_force_cg = 0, g_force_stages = 0;
 
 // choose the (bx, by, bz) row box (<= 128 rows) that wastes the fewest MMA rows
 static void choose_box(int X, int Y, int Z, int* bx, int* by, int* bz) {
@@ -599,8 +601,10 @@ static int choose_cg(int BN, int N, int tiles_m, int kblocks) {
 }
 
 static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
-  int rc = device_props();
+  const DevProps* dp = nullptr;
+  int rc = device_props(&dp);
   if (rc) return rc;
+  const int g_num_sms = dp->sms, g_max_smem = dp->max_smem;
   CTRLV_CHECK_ARG(d != nullptr, "igemm: null descriptor");
   CTRLV_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= CTRLV_MAX_SRC, "igemm: nsrc=%d out of range", d->nsrc);
   CTRLV_CHECK_ARG(d->nseg >= 1 && d->nseg <= CTRLV_MAX_SEG, "igemm: nseg=%d out of range", d->nseg);
@@ -633,32 +637,10 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   const int kblocks_pre = kblocks;
   p.N = d->N;
   p.BN = d->bn > 0 ? d->bn : choose_bn(d->N, (long long)p.tiles_x * p.tiles_y * p.tiles_z, g_num_sms);
-  if (const char* e = getenv("CTRLV_DEBUG_BN")) p.BN = atoi(e);  // developer override
+  if (g_force_bn) p.BN = g_force_bn;
   if (p.BN == 0) {
     // ragged N: largest 32-multiple tile, TMA zero-fills the weight rows past N
     p.BN = d->N >= 256 ? 256 : ((d->N + 31) / 32) * 32;
-  }
-  // weight-stationary candidates (short K, many m-tiles): the widest n-tile whose whole [BN x K]
-  // weight slab plus >= 5 A stages fits in shared memory
-  int bres_bn = 0;
-  {
-    const long long room_total = (long long)g_max_smem - 2048;
-    const long long m_tiles_pre = (long long)p.tiles_x * p.tiles_y * p.tiles_z;
-    // (measured neutral on B200 for this path's shapes — the short-K GEMMs are bound by the MMA
-    //  issue/epilogue chain, not by weight re-fetch — so it is opt-in: CTRLV_BRES=1)
-    bool want = kblocks <= 10 && m_tiles_pre >= 2LL * g_num_sms && d->bn == 0 && !getenv("CTRLV_DEBUG_BN");
-    {
-      const char* e = getenv("CTRLV_BRES");
-      want = want && e != nullptr && atoi(e) != 0;
-    }
-    if (want) {
-      const int cands[] = {256, 192, 160, 128, 96};
-      for (int bn : cands) {
-        if (d->N % bn != 0 || g_num_sms / (d->N / bn) < 1) continue;
-        if ((long long)kblocks * bn * kBK * 2 + 5LL * kBM * kBK * 2 <= room_total) { bres_bn = bn; break; }
-      }
-    }
-    if (bres_bn) p.BN = bres_bn;
   }
   CTRLV_CHECK_ARG(p.BN % 32 == 0 && p.BN >= 32 && p.BN <= 256, "igemm: bad n-tile %d", p.BN);
   p.tiles_n = (d->N + p.BN - 1) / p.BN;
@@ -668,7 +650,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   // ring.  Measured on this path's shapes (profiles/r01_cg2_vs_cg1.txt): +15-19 % on the 3x3 convs,
   // a win for K >= 1280 and for wide-N K = 640, a loss for K = 320 and tiny M.
   p.cg = choose_cg(p.BN, d->N, tiles_m, kblocks_pre);
-  if (const char* e = getenv("CTRLV_DEBUG_CG")) p.cg = atoi(e);  // developer override
+  if (g_force_cg) p.cg = g_force_cg;
   p.tiles_total = ((tiles_m + p.cg - 1) / p.cg) * p.tiles_n;
   if (d->out_X > 0) {
     CTRLV_CHECK_ARG(d->out_Y > 0 && d->out_mul_x >= 1 && d->out_mul_y >= 1 && d->out_off_x >= 0 && d->out_off_y >= 0 &&
@@ -705,24 +687,13 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   p.a_bytes = 64 * p.bx * p.by * p.bz * 2;
   p.stage_bytes = kBM * kBK * 2 + (p.BN / p.cg) * kBK * 2;
   p.m_tiles = tiles_m;
-  p.trace = getenv("CTRLV_DEBUG_TRACE") ? 1 : 0;
-  if (const char* e = getenv("CTRLV_DEBUG_DBG")) p.dbg = atoi(e);
-  if (bres_bn && p.cg == 1) {
-    const long long room = (long long)g_max_smem - 2048 - (long long)kblocks * p.BN * kBK * 2;
-    p.bres = 1;
-    p.stage_bytes = kBM * kBK * 2;
-    int st = (int)(room / p.stage_bytes);
-    if (st > kMaxStages) st = kMaxStages;
-    p.bres_off = st * p.stage_bytes;
-  }
   int stages = p.bres ? p.bres_off / p.stage_bytes : (g_max_smem - 2048) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (const char* e = getenv("CTRLV_DEBUG_STAGES")) stages = atoi(e);  // developer override
+  if (g_force_stages) stages = g_force_stages;
   CTRLV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for 2 stages");
   p.stages = stages;
   p.tmem_cols = 2 * p.BN <= 128 ? 128 : (2 * p.BN <= 256 ? 256 : 512);
-  p.ep = d->ep;
-  if (p.ep.s_acc == 0.0f && p.ep.res1 == nullptr && p.ep.res2 == nullptr) p.ep.s_acc = 1.0f;
+  p.ep = d->ep;  // s_acc is taken literally: 0 gives out = s_res1*res1 + s_res2*res2 (conditioning_scale = 0)
   CTRLV_CHECK_ARG(p.ep.out != nullptr || p.ep.out_f32 != nullptr, "igemm: no output");
   if (p.ep.geglu) CTRLV_CHECK_ARG(d->N % 64 == 0, "igemm: GEGLU needs N %% 64 == 0");
   if (p.ep.rb_mode != 0)
@@ -763,6 +734,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
+    count_launch();
     CTRLV_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<2, 12>, p));
   }
   return CTRLV_OK;
@@ -772,10 +744,11 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
 
 using namespace ctrlv;
 
-// developer hook (not part of the public header): copy the trace stamps of the last traced launch
-extern "C" int ctrlv_debug_trace_read(long long* out, int n) {
-  CTRLV_CUDA(cudaDeviceSynchronize());
-  CTRLV_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * (n < 8 * 64 ? n : 8 * 64)));
+extern "C" int ctrlv_igemm_override(int32_t bn, int32_t cta_group, int32_t stages) {
+  CTRLV_CHECK_ARG((bn == 0 || (bn % 32 == 0 && bn >= 32 && bn <= 256)) && cta_group >= 0 && cta_group <= 2 &&
+                      stages >= 0 && stages <= kMaxStages && stages != 1,
+                  "igemm_override: bn=%d cta_group=%d stages=%d", bn, cta_group, stages);
+  g_force_bn = bn; g_force_cg = cta_group; g_force_stages = stages;
   return CTRLV_OK;
 }
 

@@ -284,12 +284,12 @@ extern "C" int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, i
   const int nthreads = (nwork + 31) / 32 * 32;
   // Both kernels do uniform work per block: size each grid to ONE full wave of resident blocks
   // (a 1.04-wave grid costs two waves).  Statistics splits and apply blocks are independent.
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    CTRLV_CUDA(cudaGetDevice(&dev));
-    CTRLV_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static int n_sm_of[64] = {0};  // per device ordinal
+  int dev = 0;
+  CTRLV_CUDA(cudaGetDevice(&dev));
+  CTRLV_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+  if (n_sm_of[dev] == 0) CTRLV_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
+  const int n_sm = n_sm_of[dev];
   const size_t st_smem = ((size_t)nwork * 8 + (size_t)vpr * 8) * sizeof(float);
   int occ_stats = 1, occ_apply = 1;
   CTRLV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_stats, gn_stats_kernel, nthreads, st_smem));

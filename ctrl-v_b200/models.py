@@ -173,11 +173,12 @@ def param_spec(cfg: dict, controlnet: bool) -> "OrderedDict[str, tuple]":
 
 
 def random_state_dict(cfg: dict, controlnet: bool, seed: int = 0, device="cuda",
-                      dtype=BF16, zero_conv_std: float = 0.02) -> Dict[str, torch.Tensor]:
+                      dtype=BF16, zero_conv_std: float = 0.0) -> Dict[str, torch.Tensor]:
     """Random-init weights with PyTorch's default layer statistics (uniform(+-1/sqrt(fan_in)),
     norm affine = (1, 0), mix_factor = 0.5), drawn directly on the device.  The ControlNet
-    zero-convs get N(0, zero_conv_std^2) instead of zeros so that the injection path carries
-    signal."""
+    zero-convs are zeros like the reference's `zero_module` (controlnet.py:149-184), so a fresh or
+    `from_unet` ControlNet is a no-op on the UNet; benchmarks and parity code pass
+    `zero_conv_std=0.02` so that the injection path carries signal."""
     g = torch.Generator(device=device).manual_seed(seed)
     sd = {}
     spec = param_spec(cfg, controlnet)
@@ -187,7 +188,8 @@ def random_state_dict(cfg: dict, controlnet: bool, seed: int = 0, device="cuda",
         elif len(shape if name.endswith("weight") else spec[name[:-4] + "weight"]) == 1:  # norm affine
             t = torch.ones(shape, device=device) if name.endswith("weight") else torch.zeros(shape, device=device)
         elif name.startswith("controlnet_"):
-            t = torch.randn(shape, device=device, generator=g) * zero_conv_std
+            t = (torch.randn(shape, device=device, generator=g) * zero_conv_std if zero_conv_std
+                 else torch.zeros(shape, device=device))
         else:
             wshape = shape if name.endswith("weight") else spec[name[:-4] + "weight"]
             fan_in = 1
@@ -202,12 +204,12 @@ def random_state_dict(cfg: dict, controlnet: bool, seed: int = 0, device="cuda",
 # ------------------------------------------------------------------------------------------------
 # weight packing
 # ------------------------------------------------------------------------------------------------
-def _w(t):  # matrix operand
-    return t.detach().to(device="cuda", dtype=BF16).contiguous()
+def _w(t):  # matrix operand (converted where it lives, then one plain copy to the GPU)
+    return t.detach().to(dtype=BF16).contiguous().to("cuda")
 
 
 def _f(t):  # fp32 vector
-    return t.detach().to(device="cuda", dtype=torch.float32).contiguous()
+    return t.detach().to(dtype=torch.float32).contiguous().to("cuda")
 
 
 def _conv9(w):  # [Cout, Cin, 3, 3] -> [Cout, 9*Cin], tap-major
@@ -429,7 +431,7 @@ class _PackedModel(torch.nn.Module):
     is_controlnet = False
 
     def __init__(self, state_dict: Optional[Dict[str, torch.Tensor]] = None,
-                 time_context_order: str = "s_major", seed: int = 0, **overrides):
+                 time_context_order: str = "s_major", seed: int = 0, zero_conv_std: float = 0.0, **overrides):
         super().__init__()
         cfg = dict(SVD_CONFIG)
         if self.is_controlnet:
@@ -450,8 +452,9 @@ class _PackedModel(torch.nn.Module):
         self.time_context_order = time_context_order
         self.dtype = BF16
         self._sd: Dict[str, torch.Tensor] = {}
+        self._version = 0  # bumped by every (re)pack: cached CUDA graphs hold raw pointers of the packed weights
         if state_dict is None:
-            state_dict = random_state_dict(cfg, self.is_controlnet, seed=seed)
+            state_dict = random_state_dict(cfg, self.is_controlnet, seed=seed, zero_conv_std=zero_conv_std)
         self.load_state_dict(state_dict)
         # `add_embedding.linear_1.in_features` is read by ctrlv.utils.util:161
         self.add_embedding = SimpleNamespace(linear_1=SimpleNamespace(
@@ -459,7 +462,7 @@ class _PackedModel(torch.nn.Module):
 
     # ---- state dict with diffusers key names -------------------------------------------------
     def state_dict(self, *a, **k):
-        return OrderedDict(self._sd)
+        return OrderedDict((n, v.to("cuda")) for n, v in self._sd.items())
 
     def load_state_dict(self, sd, strict: bool = True):
         spec = param_spec(self.cfg, self.is_controlnet)
@@ -467,12 +470,16 @@ class _PackedModel(torch.nn.Module):
         unexpected = [k for k in sd if k not in spec]
         if strict and (missing or unexpected):
             raise RuntimeError(f"load_state_dict: missing {missing[:5]} unexpected {unexpected[:5]}")
+        big = sum(int(v.numel()) for v in sd.values()) > 100_000_000
         for k, shape in spec.items():
             if k in sd:
                 if tuple(sd[k].shape) != tuple(shape):
                     raise RuntimeError(f"size mismatch for {k}: {tuple(sd[k].shape)} vs {shape}")
-                self._sd[k] = sd[k].detach().to("cuda")
+                # small models are packed where their tensors live (permutes, concatenations, LayerNorm folds
+                # on the host, only the packed matrices are copied over); big ones are packed on the GPU
+                self._sd[k] = sd[k].detach().to("cuda") if big else sd[k].detach()
         self._pack()
+        self._version += 1
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
     # ---- diffusers-format checkpoints --------------------------------------
@@ -513,7 +520,7 @@ class _PackedModel(torch.nn.Module):
         sd, cfg = self._sd, self.cfg
         c0 = cfg["block_out_channels"][0]
         cin = cfg["in_channels"]
-        w = torch.zeros(c0, 3, 3, 64, device="cuda", dtype=torch.float32)
+        w = torch.zeros(c0, 3, 3, 64, device=sd["conv_in.weight"].device, dtype=torch.float32)
         w[..., :cin] = sd["conv_in.weight"].float().permute(0, 2, 3, 1)
         b = sd["conv_in.bias"].float()
         if self.is_controlnet:  # conv_in(sample) + control_conv_in(cond) == one conv on [sample | cond]
@@ -761,9 +768,9 @@ class UNetSpatioTemporalConditionModel(_PackedModel):
         self.norm_out = _Norm(sd, "conv_norm_out")
         oc = cfg["out_channels"]
         assert oc <= 32
-        w = torch.zeros(32, 9 * boc[0], device="cuda", dtype=torch.float32)
+        w = torch.zeros(32, 9 * boc[0], device=sd["conv_out.weight"].device, dtype=torch.float32)
         w[:oc] = _conv9(sd["conv_out.weight"].float())
-        b = torch.zeros(32, device="cuda", dtype=torch.float32)
+        b = torch.zeros(32, device=sd["conv_out.weight"].device, dtype=torch.float32)
         b[:oc] = sd["conv_out.bias"].float()
         self.conv_out_w, self.conv_out_b = _w(w), _f(b)
         res, att = self._all_blocks()

@@ -25,13 +25,13 @@ PROFILE = None
 _prof_pending = []
 
 
-def _prof(op, key, flops=0.0):
+def _prof(op, key, flops=0.0, nbytes=0.0):
     if PROFILE is None:
         return None
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    _prof_pending.append((op, key, flops, e0, e1))
+    _prof_pending.append((op, key, flops, nbytes, e0, e1))
     return e1
 
 
@@ -42,9 +42,9 @@ def _prof_end(tok):
 
 def profile_flush():
     torch.cuda.synchronize()
-    for op, key, flops, e0, e1 in _prof_pending:
-        r = PROFILE.setdefault((op, key), [0, 0.0, 0.0])
-        r[0] += 1; r[1] += e0.elapsed_time(e1); r[2] += flops
+    for op, key, flops, nbytes, e0, e1 in _prof_pending:
+        r = PROFILE.setdefault((op, key), [0, 0.0, 0.0, 0.0])  # calls, ms, algorithmic flops, algorithmic bytes
+        r[0] += 1; r[1] += e0.elapsed_time(e1); r[2] += flops; r[3] += nbytes
     _prof_pending.clear()
 
 
@@ -183,7 +183,7 @@ def groupnorm(x: torch.Tensor, n_units: int, rows_per_unit: int, gamma: torch.Te
         out = torch.empty((x.shape[0], C0 + C1), dtype=BF16, device="cuda")
     if ws is None:
         ws = _gn_workspace(n_units)
-    tok = _prof("groupnorm", (n_units, rows_per_unit, C0 + C1))
+    tok = _prof("groupnorm", (n_units, rows_per_unit, C0 + C1), nbytes=4.0 * x.shape[0] * (C0 + C1))
     check(lib().ctrlv_groupnorm(x.data_ptr(), C0, _p(src1), C1, n_units, rows_per_unit, gamma.data_ptr(),
                                 beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), ws.data_ptr(),
                                 _stream()), "ctrlv_groupnorm")
@@ -204,7 +204,7 @@ def layernorm(x: torch.Tensor, gamma: Optional[torch.Tensor] = None, beta: Optio
         out = torch.empty((M, Cc), dtype=BF16, device="cuda")
     if rowbias is not None:
         _req(rowbias, torch.float32, "rowbias")
-    tok = _prof("layernorm", (M, Cc))
+    tok = _prof("layernorm", (M, Cc), nbytes=4.0 * M * Cc)
     check(lib().ctrlv_layernorm(x.data_ptr(), x.stride(0), M, Cc, _p(gamma), _p(beta), eps,
                                 _p(rowbias), rowbias.stride(0) if rowbias is not None else 0, rb_div,
                                 rb_mod, out.data_ptr(), _stream()), "ctrlv_layernorm")
@@ -219,7 +219,7 @@ def attn_spatial(qkv: torch.Tensor, frames: int, S: int, heads: int, scale: Opti
     assert qkv.is_contiguous() and qkv.shape == (frames * S, 3 * Cc), (qkv.shape, frames, S, heads)
     if out is None:
         out = torch.empty((frames * S, Cc), dtype=BF16, device="cuda")
-    tok = _prof("attn_spatial", (frames, S, heads), 4.0 * frames * heads * S * S * 64)
+    tok = _prof("attn_spatial", (frames, S, heads), 4.0 * frames * heads * S * S * 64, nbytes=8.0 * frames * S * Cc)
     check(lib().ctrlv_attn_spatial(qkv.data_ptr(), frames, S, heads, scale if scale is not None else 0.125,
                                    out.data_ptr(), _stream()), "ctrlv_attn_spatial")
     _prof_end(tok)
@@ -233,7 +233,7 @@ def attn_temporal(qkv: torch.Tensor, B: int, T: int, S: int, heads: int, scale: 
     assert qkv.is_contiguous() and qkv.shape == (B * T * S, 3 * Cc)
     if out is None:
         out = torch.empty((B * T * S, Cc), dtype=BF16, device="cuda")
-    tok = _prof("attn_temporal", (B, T, S, heads), 4.0 * B * S * heads * T * T * 64)
+    tok = _prof("attn_temporal", (B, T, S, heads), 4.0 * B * S * heads * T * T * 64, nbytes=8.0 * B * T * S * Cc)
     check(lib().ctrlv_attn_temporal(qkv.data_ptr(), B, T, S, heads, scale if scale is not None else 0.125,
                                     out.data_ptr(), _stream()), "ctrlv_attn_temporal")
     _prof_end(tok)
@@ -433,7 +433,7 @@ def pack_upconv3x3(w: torch.Tensor, device="cuda", dtype=BF16) -> torch.Tensor:
                             acc += w[:, :, a, b]
                     blocks.append(acc)
             out[py * 2 + px] = torch.cat(blocks, dim=1)
-    return out.to(device=device, dtype=dtype).contiguous()
+    return out.to(dtype=dtype).contiguous().to(device)
 
 
 def upsample2x_conv3x3(x: torch.Tensor, frames: int, H: int, W: int, wp: torch.Tensor,

@@ -280,7 +280,8 @@ class StableVideoControlPipeline:
         self.unet, self.controlnet = unet, controlnet
         self.scheduler = scheduler if scheduler is not None else EulerDiscreteScheduler()
         self.vae_scale_factor = (2 ** (len(vae.config.block_out_channels) - 1)) if vae is not None else 8
-        self._steps: Dict[tuple, DenoiseStep] = {}
+        self._steps: Dict[tuple, DenoiseStep] = {}  # insertion-ordered: least recently used first
+        self.max_cached_steps = 4
         self._guidance_scale = 1.0
 
     @classmethod
@@ -369,6 +370,33 @@ class StableVideoControlPipeline:
                                       "`image_encoder` (ctrlv_b200.clip.CLIPVisionModelWithProjection)")
         return self.image_encoder.encode_image(self._image_to_tensor01(image))
 
+    @staticmethod
+    def _duplicate_conditioning(image_embeddings, image_latents, batch_size, nvp):
+        """Per-prompt duplication for `num_videos_per_prompt` > 1, in the orders the reference's helpers
+        use: the bbox-frame latents (`_encode_vae_condition`, pipeline_video_control.py:90) and the image
+        latents (diffusers-0.27.2 `_encode_vae_image`: `.repeat(num_videos_per_prompt, 1, 1, 1)`) are
+        TILED, so sample j carries image j % batch and bbox frames j % batch; only the CLIP embedding
+        (`_encode_image`: `repeat(1, n, 1).view(b * n, ...)`) is interleaved.  For batch > 1 and n > 1 the
+        reference therefore pairs embedding j // n with latents j % batch; that quirk is kept so that the
+        drop-in samples what the reference samples."""
+        emb = image_embeddings.to("cuda", torch.float32).reshape(batch_size, -1).repeat_interleave(nvp, 0)
+        il = image_latents.to("cuda", torch.float32).repeat(nvp, 1, 1, 1)
+        return emb, il
+
+    def _denoise_step(self, key, make):
+        """Cached `DenoiseStep` per (shape, mode, weight versions).  A captured graph holds raw pointers
+        of the packed weights, so the versions of both networks are part of the key (a `load_state_dict`
+        repacks and frees the old buffers); the cache is a small LRU because every entry owns a full
+        activation pool."""
+        key = key + (self.unet._version, self.controlnet._version if self.controlnet is not None else -1)
+        st = self._steps.pop(key, None)
+        if st is None:
+            st = make()
+            while len(self._steps) >= self.max_cached_steps:
+                self._steps.pop(next(iter(self._steps)))
+        self._steps[key] = st  # most recently used last
+        return st
+
     def _get_add_time_ids(self, fps, motion_bucket_id, noise_aug_strength, batch_size):  # :247-255
         add_time_ids = [fps, motion_bucket_id, noise_aug_strength]
         passed = self.unet.config.addition_time_embed_dim * len(add_time_ids)
@@ -455,8 +483,7 @@ class StableVideoControlPipeline:
         h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
         B = batch_size * nvp
         # :220 uncond image embedding = zeros; :235-245 uncond image latents = zeros
-        emb = image_embeddings.to("cuda", torch.float32).reshape(batch_size, -1).repeat_interleave(nvp, 0)
-        il = image_latents.to("cuda", torch.float32).repeat_interleave(nvp, 0)
+        emb, il = self._duplicate_conditioning(image_embeddings, image_latents, batch_size, nvp)
         if do_cfg:
             emb = torch.cat([torch.zeros_like(emb), emb])
             il = torch.cat([torch.zeros_like(il), il])
@@ -475,14 +502,14 @@ class StableVideoControlPipeline:
         cond_em = self._encode_vae_condition(cond_images, nvp, do_cfg)
         guidance = torch.linspace(min_guidance_scale, max_guidance_scale, num_frames)  # :287
 
-        key = (B, num_frames, h, w, do_cfg, float(control_condition_scale), num_inference_steps, use_graph)
-        st = self._steps.get(key)
-        if st is None:
+        def make():
             st = DenoiseStep(self.unet, self.controlnet, B, num_frames, h, w, do_cfg,
                              control_condition_scale, use_graph)
             st.set_schedule(self.scheduler.sigmas, timesteps)
             st.capture()
-            self._steps[key] = st
+            return st
+        st = self._denoise_step((B, num_frames, h, w, do_cfg, float(control_condition_scale), num_inference_steps,
+                                 use_graph), make)
         st.latents.copy_(latents)
         st.image_latents.copy_(il)
         st.cond_em.copy_(cond_em)
@@ -548,8 +575,7 @@ class VideoDiffusionPipeline(StableVideoControlPipeline):
         do_cfg = self.do_classifier_free_guidance
         h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
         B = batch_size * nvp
-        emb = image_embeddings.to("cuda", torch.float32).reshape(batch_size, -1).repeat_interleave(nvp, 0)
-        il = image_latents.to("cuda", torch.float32).repeat_interleave(nvp, 0)
+        emb, il = self._duplicate_conditioning(image_embeddings, image_latents, batch_size, nvp)
         if do_cfg:
             emb = torch.cat([torch.zeros_like(emb), emb])
             il = torch.cat([torch.zeros_like(il), il])
@@ -569,13 +595,12 @@ class VideoDiffusionPipeline(StableVideoControlPipeline):
         latents = latents.to("cuda", torch.float32) * self.scheduler.init_noise_sigma
         guidance = torch.linspace(min_guidance_scale, max_guidance_scale, num_frames)  # :249
 
-        key = (B, num_frames, h, w, do_cfg, num_inference_steps, use_graph)
-        st = self._steps.get(key)
-        if st is None:
+        def make():
             st = DenoiseStep(self.unet, None, B, num_frames, h, w, do_cfg, 1.0, use_graph)
             st.set_schedule(self.scheduler.sigmas, timesteps)
             st.capture()
-            self._steps[key] = st
+            return st
+        st = self._denoise_step((B, num_frames, h, w, do_cfg, num_inference_steps, use_graph), make)
         st.latents.copy_(latents)
         st.image_latents.copy_(il)
         st.ehs.copy_(emb)

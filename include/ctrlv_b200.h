@@ -35,6 +35,8 @@ extern "C" {
 const char* ctrlv_last_error(void);
 /* Library version string and the SM architecture it was compiled for ("sm_100a"). */
 const char* ctrlv_version(void);
+/* Number of kernels this library has launched (or recorded into a stream capture) in this process. */
+int64_t ctrlv_launch_count(void);
 /* 0 if the current device can run the kernels (compute capability 10.x), negative otherwise. */
 int ctrlv_device_check(void);
 
@@ -58,7 +60,9 @@ typedef struct ctrlv_epilogue {
   int32_t ld_rowbias;
   int32_t rb_mode, rb_div, rb_mod, rb_B;
   int32_t geglu;     /* 1: N/2 outputs per row */
-  float s_acc;       /* scale of the accumulator term */
+  float s_acc;       /* scale of the accumulator term, taken literally: set it to 1.0f for a plain
+                        product (a zero-initialised struct multiplies the product by 0, which is what
+                        conditioning_scale = 0 asks for, controlnet.py:343-344) */
   const void* res1;  /* bf16 [M][ld_res1] or NULL */
   int32_t ld_res1;
   float s_res1;
@@ -113,6 +117,10 @@ int ctrlv_igemm(const ctrlv_igemm_desc* desc, void* stream);
  * launcher picks for `desc` on a device with `num_sms` SMs — lets host tests pin the tiling heuristics. */
 int ctrlv_igemm_plan(const ctrlv_igemm_desc* desc, int32_t num_sms, int32_t* box_xyz, int32_t* bn,
                      int32_t* cta_group);
+
+/* Tuning hook for tile sweeps (process-global, not for production use): force the n-tile width, the
+ * cta_group and the pipeline depth of every following ctrlv_igemm launch; 0 = the launcher's heuristic. */
+int ctrlv_igemm_override(int32_t bn, int32_t cta_group, int32_t stages);
 
 /* nn.Linear (diffusers Attention.to_q/k/v/to_out, FeedForward, proj_in/out, 1x1 convs incl. the
  * ControlNet zero-convs controlnet.py:148-185,331-339):  out[M][N] = A[M][K] * W[N][K]^T. */

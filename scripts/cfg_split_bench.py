@@ -12,7 +12,7 @@ rank, world, local = parallel.init_from_env("nccl")
 torch.cuda.set_device(local)
 T, h, w, steps = 14, 40, 64, 25
 unet = models.UNetSpatioTemporalConditionModel(seed=0)
-ctrl = models.ControlNetModel(seed=1)
+ctrl = models.ControlNetModel(seed=1, zero_conv_std=0.02)
 sch = pipeline.EulerDiscreteScheduler().set_timesteps(25)
 pair = parallel.CfgPair(rank, world)
 g = torch.Generator("cpu").manual_seed(1234 + pair.pair)

@@ -10,7 +10,7 @@ from ctrlv_b200 import models, pipeline
 T, h, w, CLIPS, STEPS = 14, 40, 64, 8, 25
 batches = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["1", "2", "4"])]
 mu = models.UNetSpatioTemporalConditionModel(seed=0)
-mc = models.ControlNetModel(seed=1)
+mc = models.ControlNetModel(seed=1, zero_conv_std=0.02)
 sch = pipeline.EulerDiscreteScheduler().set_timesteps(STEPS)
 res = {"config": "8 clips x 25 steps, 14x320x512, CFG, one B200", "runs": []}
 for b in batches:

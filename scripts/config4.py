@@ -10,7 +10,7 @@ torch.backends.cuda.matmul.allow_tf32 = False; torch.backends.cudnn.allow_tf32 =
 dev = "cuda"; T, h, w = 25, 72, 128
 cfg = dict(models.SVD_CONFIG)
 sd_u = models.random_state_dict(cfg, False, seed=0, dtype=torch.float32)
-sd_c = models.random_state_dict(cfg, True, seed=1, dtype=torch.float32)
+sd_c = models.random_state_dict(cfg, True, seed=1, dtype=torch.float32, zero_conv_std=0.02)
 mu = models.UNetSpatioTemporalConditionModel(state_dict=sd_u); mc = models.ControlNetModel(state_dict=sd_c)
 inp = S.make_inputs(T=T, h=h, w=w, device=dev)
 sch = S.EulerDiscreteSchedulerOracle(); sch.set_timesteps(25)

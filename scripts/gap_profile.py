@@ -6,7 +6,7 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 from ctrlv_b200 import models, pipeline
 T, h, w = 14, 40, 64
-mu = models.UNetSpatioTemporalConditionModel(seed=0); mc = models.ControlNetModel(seed=1)
+mu = models.UNetSpatioTemporalConditionModel(seed=0); mc = models.ControlNetModel(seed=1, zero_conv_std=0.02)
 sch = pipeline.EulerDiscreteScheduler().set_timesteps(25)
 st = pipeline.DenoiseStep(mu, mc, 1, T, h, w, cfg=True, use_graph=True)
 st.set_schedule(sch.sigmas, sch.timesteps)

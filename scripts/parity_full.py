@@ -21,7 +21,7 @@ def main(steps=25, T=14, h=40, w=64):
     log("building weights on GPU (product random init), loading into oracle modules")
     cfg = dict(models.SVD_CONFIG)
     sd_u = models.random_state_dict(cfg, False, seed=0, dtype=torch.float32)
-    sd_c = models.random_state_dict(cfg, True, seed=1, dtype=torch.float32)
+    sd_c = models.random_state_dict(cfg, True, seed=1, dtype=torch.float32, zero_conv_std=0.02)
     with torch.device("meta"):
         ou = O.UNetSpatioTemporalConditionModel(); oc = O.ControlNetModel()
     ou.load_state_dict(sd_u, assign=True); oc.load_state_dict(sd_c, assign=True)

@@ -5,7 +5,7 @@ import torch
 from ctrlv_b200 import models, pipeline, ops
 T = int(os.environ.get("T", 14)); h = int(os.environ.get("H", 40)); w = int(os.environ.get("W", 64))
 mu = models.UNetSpatioTemporalConditionModel(seed=0)
-mc = models.ControlNetModel(seed=1)
+mc = models.ControlNetModel(seed=1, zero_conv_std=0.02)
 sch = pipeline.EulerDiscreteScheduler().set_timesteps(25)
 st = pipeline.DenoiseStep(mu, mc, 1, T, h, w, cfg=True, use_graph=False)
 st.set_schedule(sch.sigmas, sch.timesteps)

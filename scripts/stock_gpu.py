@@ -10,7 +10,7 @@ dev = "cuda"
 T = int(os.environ.get("T", 14)); h = int(os.environ.get("H", 40)); w = int(os.environ.get("W", 64))
 cfg = dict(models.SVD_CONFIG)
 sd_u = models.random_state_dict(cfg, False, seed=0, dtype=torch.bfloat16)
-sd_c = models.random_state_dict(cfg, True, seed=1, dtype=torch.bfloat16)
+sd_c = models.random_state_dict(cfg, True, seed=1, dtype=torch.bfloat16, zero_conv_std=0.02)
 with torch.device("meta"):
     ou = O.UNetSpatioTemporalConditionModel(); oc = O.ControlNetModel()
 ou.load_state_dict(sd_u, assign=True); oc.load_state_dict(sd_c, assign=True)

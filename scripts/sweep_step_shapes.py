@@ -6,7 +6,7 @@ import torch
 from ctrlv_b200 import models, pipeline, ops
 BF = torch.bfloat16; dev = "cuda"
 T, h, w = 14, 40, 64
-mu = models.UNetSpatioTemporalConditionModel(seed=0); mc = models.ControlNetModel(seed=1)
+mu = models.UNetSpatioTemporalConditionModel(seed=0); mc = models.ControlNetModel(seed=1, zero_conv_std=0.02)
 sch = pipeline.EulerDiscreteScheduler().set_timesteps(25)
 st = pipeline.DenoiseStep(mu, mc, 1, T, h, w, cfg=True, use_graph=False, two_streams=False)
 st.set_schedule(sch.sigmas, sch.timesteps)
@@ -61,17 +61,17 @@ for (op, key), cnt in sorted(keys.items(), key=lambda kv: str(kv[0])):
         fn, N = make(op, key)
     except Exception as e:
         print("skip", op, key, e); continue
-    os.environ.pop("CTRLV_DEBUG_BN", None); os.environ.pop("CTRLV_DEBUG_CG", None)
+    ops.lib().ctrlv_igemm_override(0, 0, 0)
     base = t(fn); best = (base, "auto"); alt = {}
     for cg in (1, 2):
         for bn in (64, 96, 128, 160, 192, 256):
             if bn > N or (N % bn): continue
-            os.environ["CTRLV_DEBUG_BN"] = str(bn); os.environ["CTRLV_DEBUG_CG"] = str(cg)
+            ops.lib().ctrlv_igemm_override(bn, cg, 0)
             try: v = t(fn, 3)
             except Exception: v = float("nan")
             alt[f"cg{cg}/bn{bn}"] = v
             if v == v and v < best[0]: best = (v, f"cg{cg}/bn{bn}")
-    os.environ.pop("CTRLV_DEBUG_BN", None); os.environ.pop("CTRLV_DEBUG_CG", None)
+    ops.lib().ctrlv_igemm_override(0, 0, 0)
     tot_auto += base * cnt; tot_best += best[0] * cnt
     rows.append(dict(op=op, key=list(key), count=cnt, auto_us=base, best=best[1], best_us=best[0], alt=alt))
     print(f"{op:9s} {str(key):48s} n={cnt:3.0f} auto {base:7.1f}  best {best[1]:10s} {best[0]:7.1f}  gain/step {(base-best[0])*cnt:7.1f} us", flush=True)

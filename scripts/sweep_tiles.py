@@ -1,5 +1,4 @@
-"""Sweep n-tile width and cta_group for the mid-size GEMM shapes (developer overrides CTRLV_DEBUG_BN /
-CTRLV_DEBUG_CG are read per launch) against the heuristic's own choice."""
+"""Sweep n-tile width and cta_group for the mid-size GEMM shapes (tile-plan overrides through ctrlv_igemm_override) against the heuristic's own choice."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,7 +16,7 @@ def t(fn, n=7):
         ts.append(e0.elapsed_time(e1) * 1e3)
     return sorted(ts)[len(ts) // 2]
 def sweep(name, fn, N):
-    os.environ.pop("CTRLV_DEBUG_BN", None); os.environ.pop("CTRLV_DEBUG_CG", None)
+    ops.lib().ctrlv_igemm_override(0, 0, 0)
     base = t(fn)
     best = (base, "auto")
     line = [f"auto {base:6.1f}"]
@@ -25,14 +24,14 @@ def sweep(name, fn, N):
         for bn in (64, 96, 128, 160, 192, 256):
             if N % bn and bn != 256: continue
             if bn > N: continue
-            os.environ["CTRLV_DEBUG_BN"] = str(bn); os.environ["CTRLV_DEBUG_CG"] = str(cg)
+            ops.lib().ctrlv_igemm_override(bn, cg, 0)
             try:
                 v = t(fn)
             except Exception as e:
                 v = float("nan")
             line.append(f"cg{cg}/bn{bn} {v:6.1f}")
             if v == v and v < best[0]: best = (v, f"cg{cg}/bn{bn}")
-    os.environ.pop("CTRLV_DEBUG_BN", None); os.environ.pop("CTRLV_DEBUG_CG", None)
+    ops.lib().ctrlv_igemm_override(0, 0, 0)
     print(f"{name:34s} best {best[1]:10s} {best[0]:6.1f} us  ({100*(base-best[0])/base:4.1f}% vs auto) | " + "  ".join(line), flush=True)
 def lin(M, K, N, res=False, geglu=False):
     a = torch.randn(M, K, device=dev).to(BF); w = (torch.randn(N, K, device=dev) / K ** 0.5).to(BF); b = torch.randn(N, device=dev)

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from tests.golden import ref_shim as R  # noqa: E402
 from oracle import svd_oracle as O  # noqa: E402
 
-T, H, W, STEPS = 4, 8, 8, 5
+T, H, W, STEPS = 4, 8, 8, 25  # the reference default schedule (pipeline_video_control.py:112)
 XDIM = O.TINY_CONFIG["cross_attention_dim"]
 
 

@@ -80,21 +80,93 @@ def test_residuals_in_reference_layout_are_accepted(tiny):
 
 
 def test_zero_init_controlnet_is_a_noop_and_from_unet(tiny):
+    """controlnet.py:149-184: the zero-convs are `zero_module`s, so a fresh `from_unet` ControlNet (and a
+    fresh constructor) leaves the UNet untouched — no hand-zeroing of weights."""
     from ctrlv_b200 import models
+    from oracle import svd_oracle as O
     ou, oc, mu, mc = tiny
-    c0 = models.ControlNetModel.from_unet(mu)
-    sd = c0.state_dict()
-    for k in sd:
-        if k.startswith("controlnet_"):
-            sd[k] = torch.zeros_like(sd[k])
-    c0.load_state_dict(sd)
     inp, x = _inputs(2, 8, 8, 3.0)
     t = torch.tensor(0.27, device=dev)
-    d, m = c0(x, t, inp["image_embeddings"], inp["added_time_ids"], control_cond=inp["cond_em"], return_dict=False)
-    assert all(float(r.abs().max()) == 0.0 for r in d) and float(m.abs().max()) == 0.0
     y0 = mu(x, t, inp["image_embeddings"], inp["added_time_ids"], return_dict=False)[0]
-    y1 = mu(x, t, inp["image_embeddings"], inp["added_time_ids"], d, m, return_dict=False)[0]
-    assert torch.equal(y0, y1)
+    for c0 in (models.ControlNetModel.from_unet(mu), models.ControlNetModel(seed=3, **O.TINY_CONFIG)):
+        d, m = c0(x, t, inp["image_embeddings"], inp["added_time_ids"], control_cond=inp["cond_em"], return_dict=False)
+        assert all(float(r.abs().max()) == 0.0 for r in d) and float(m.abs().max()) == 0.0
+        y1 = mu(x, t, inp["image_embeddings"], inp["added_time_ids"], d, m, return_dict=False)[0]
+        assert torch.equal(y0, y1)
+    c1 = models.ControlNetModel.from_unet(mu)
+    su, sc = mu.state_dict(), c1.state_dict()
+    assert all(torch.equal(sc[k].to(dev), su[k].to(dev)) for k in sc if k in su)  # encoder weights copied
+    c2 = models.ControlNetModel(seed=3, zero_conv_std=0.02, **O.TINY_CONFIG)      # opt-in: residual path carries signal
+    d, m = c2(x, t, inp["image_embeddings"], inp["added_time_ids"], control_cond=inp["cond_em"], return_dict=False)
+    assert float(m.abs().max()) > 0.0
+
+
+def test_conditioning_scale_zero_switches_the_controlnet_off(tiny):
+    """controlnet.py:343-344 multiplies the residuals by `conditioning_scale`: 0 gives all-zero residuals and
+    the UNet output of the plain (no-ControlNet) forward — the no-control ablation."""
+    from ctrlv_b200 import pipeline
+    from oracle import sampling as S
+    ou, oc, mu, mc = tiny
+    inp, x = _inputs(2, 8, 8, 3.0)
+    t = torch.tensor(0.27, device=dev)
+    d, m = mc(x, t, inp["image_embeddings"], inp["added_time_ids"], control_cond=inp["cond_em"],
+              conditioning_scale=0.0, return_dict=False)
+    assert all(float(r.abs().max()) == 0.0 for r in d) and float(m.abs().max()) == 0.0
+    d1, m1 = mc(x, t, inp["image_embeddings"], inp["added_time_ids"], control_cond=inp["cond_em"], return_dict=False)
+    assert float(m1.abs().max()) > 0.0
+    y0 = mu(x, t, inp["image_embeddings"], inp["added_time_ids"], return_dict=False)[0]
+    y = mu(x, t, inp["image_embeddings"], inp["added_time_ids"], d, m, return_dict=False)[0]
+    assert torch.equal(y, y0)
+    # the pipeline's control_condition_scale = 0 equals a pipeline without a ControlNet
+    T, h, w = 2, 8, 8
+    kw = dict(cond_images=inp["cond_em_cond"], height=h * 8, width=w * 8, num_frames=T, num_inference_steps=3,
+              latents=inp["latents"].clone(), output_type="latent", image_embeddings=inp["image_embeds_cond"],
+              image_latents=inp["image_latents_cond"])
+    a = pipeline.StableVideoControlPipeline(unet=mu, controlnet=mc)(control_condition_scale=0.0, **kw).frames
+    b = pipeline.StableVideoControlPipeline(unet=mu, controlnet=None)(**kw).frames
+    c = pipeline.StableVideoControlPipeline(unet=mu, controlnet=mc)(control_condition_scale=1.0, **kw).frames
+    assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+def test_reloading_weights_invalidates_cached_graphs(tiny):
+    """A captured step graph holds raw pointers into the packed weights; `load_state_dict` repacks, so the
+    pipeline must not replay a graph captured before it."""
+    from ctrlv_b200 import models, pipeline
+    from oracle import svd_oracle as O
+    ou, oc, mu, mc = tiny
+    mu2 = models.UNetSpatioTemporalConditionModel(state_dict=mu.state_dict(), **O.TINY_CONFIG)
+    inp, _ = _inputs(2, 8, 8, 3.0)
+    kw = dict(cond_images=inp["cond_em_cond"], height=64, width=64, num_frames=2, num_inference_steps=3,
+              latents=inp["latents"].clone(), output_type="latent", image_embeddings=inp["image_embeds_cond"],
+              image_latents=inp["image_latents_cond"])
+    pipe = pipeline.StableVideoControlPipeline(unet=mu2, controlnet=mc)
+    a = pipe(**kw).frames
+    sd = {k: (v * 1.5 if k == "conv_out.weight" else v) for k, v in mu2.state_dict().items()}
+    mu2.load_state_dict(sd)
+    junk = [torch.randn(1 << 20, device=dev) for _ in range(8)]  # recycle the freed blocks
+    b = pipe(**kw).frames
+    fresh = pipeline.StableVideoControlPipeline(unet=mu2, controlnet=mc)(**kw).frames
+    assert torch.equal(b, fresh) and not torch.equal(a, b)
+    assert len(pipe._steps) == 2
+    pipe.max_cached_steps = 2
+    pipe(**dict(kw, num_inference_steps=4)); pipe(**dict(kw, num_inference_steps=5))
+    assert len(pipe._steps) == 2  # LRU bound
+    del junk
+
+
+def test_num_videos_per_prompt_duplication_orders():
+    """pipeline_video_control.py:90 tiles the bbox-frame latents; diffusers-0.27.2 `_encode_vae_image` tiles the
+    image latents and `_encode_image` interleaves the embeddings."""
+    from ctrlv_b200.pipeline import StableVideoControlPipeline as P
+    emb = torch.arange(2.0).view(2, 1, 1).repeat(1, 1, 4)
+    il = torch.arange(2.0).view(2, 1, 1, 1).repeat(1, 4, 2, 2)
+    e, l = P._duplicate_conditioning(emb, il, 2, 3)
+    assert e[:, 0].tolist() == [0, 0, 0, 1, 1, 1] and l[:, 0, 0, 0].tolist() == [0, 1, 0, 1, 0, 1]
+    pipe = P.__new__(P)
+    pipe.vae = None
+    cond = torch.arange(2.0).view(2, 1, 1, 1, 1).repeat(1, 2, 4, 2, 2)
+    ce = pipe._encode_vae_condition(cond, 3, True)
+    assert ce[6:, 0, 0, 0, 0].tolist() == l[:, 0, 0, 0].tolist() and float(ce[:6].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("order", ["s_major", "b_major"])
@@ -120,7 +192,7 @@ def test_pipeline_loop_matches_oracle_loop(order):
         torch.cuda.synchronize()
         res[use_graph] = out.frames.clone()
         # teacher-forced per-step error: restart each step from the oracle's state
-        st = next(s for k, s in pipe._steps.items() if k[-1] == use_graph)
+        st = next(s for s in pipe._steps.values() if s.use_graph == use_graph)
         sch = S.EulerDiscreteSchedulerOracle(); sch.set_timesteps(steps)
         prevs = [inp["latents"] * sch.init_noise_sigma] + trace[:-1]
         for i in range(steps):
@@ -210,7 +282,7 @@ def test_full_size_single_step(T, h, w):
     torch.backends.cudnn.allow_tf32 = False
     cfg = dict(models.SVD_CONFIG)
     sd_u = models.random_state_dict(cfg, False, seed=0, dtype=torch.float32)
-    sd_c = models.random_state_dict(cfg, True, seed=1, dtype=torch.float32)
+    sd_c = models.random_state_dict(cfg, True, seed=1, dtype=torch.float32, zero_conv_std=0.02)
     with torch.device("meta"):
         ou = O.UNetSpatioTemporalConditionModel(); oc = O.ControlNetModel()
     ou.load_state_dict(sd_u, assign=True); oc.load_state_dict(sd_c, assign=True)
