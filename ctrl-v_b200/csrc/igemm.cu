@@ -11,9 +11,12 @@
 // * tcgen05.mma (cta_group::1, M=128, N=BN, K=16) issued by one thread, fp32 accumulators in
 //   TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the main loop of
 //   tile i+1.  Persistent CTAs (one per SM), static round-robin tile schedule.
-// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..17 = epilogue
-//   (each owns the TMEM lane quarter warp_id % 4, one accumulator row per thread; the four warps
-//   of a quarter split the 32-column chunks so global-load latency of residuals is overlapped).
+// * Warp roles (16 warps = 4 warpgroups): warpgroup 0 = {TMA producer, MMA issuer (+ TMEM alloc), two
+//   idle warps}, warpgroups 1-3 = 12 epilogue warps (each owns the TMEM lane quarter warp_id % 4, one
+//   accumulator row per thread; the three warps of a quarter split the 32-column chunks).  After the
+//   set-up barrier warpgroup 0 shrinks to 40 registers per thread and the epilogue warpgroups grow to
+//   152 (setmaxnreg): the epilogue holds an accumulator chunk, a prefetched residual chunk and its
+//   row bookkeeping in registers without spilling.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -25,7 +28,9 @@ namespace ctrlv {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
-constexpr int kMaxEpiWarps = 16;  // epilogue warps: 12 (3 per TMEM lane quarter) or 16 (4 per quarter)
+constexpr int kEpiWarps = 12;     // epilogue warps: 3 per TMEM lane quarter
+constexpr int kFirstEpiWarp = 4;  // warps 0-3: TMA producer, MMA issuer, two idle (one warpgroup)
+constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;
 
 struct IgemmSeg {
   int map, c0, nchunk, dx, dy, dz;
@@ -80,29 +85,55 @@ struct EpRows {  // per (tile, warp): the rows this lane touches in the transpos
   }
 };
 
+// Prefetch loads are volatile asm: the compiler may not sink them below the (volatile) accumulator wait,
+// so their latency overlaps the MMA instead of sitting on the epilogue's critical path.
+__device__ __forceinline__ float ldg_f32_early(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_v4_early(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 template <int NV>
 struct ResPrefetch {
   static constexpr int CPR = NV / 8;
   uint4 r1[CPR];  // transposed mapping: piece (lane % CPR) of rows lane / CPR + RPI * i
-  float bv;       // lane j: bias[n0 + j] (+ the warp-uniform rowbias row), redistributed through smem
   bool full;      // warp-uniform: the whole chunk lies inside the stored columns
   __device__ __forceinline__ void issue(const ctrlv_epilogue& ep, const EpRows<NV>& rows, int o0, int n_store,
-                                        int n0, int N, const float* rb_uniform) {
+                                        int n0, int N) {
     const int lane = threadIdx.x & 31;
-    const int nl = n0 + lane;
-    bv = 0.f;
-    if (nl < N) {
-      if (ep.bias) bv = __ldg(ep.bias + nl);
-      if (rb_uniform) bv += __ldg(rb_uniform + nl);
-    }
     full = (o0 + NV <= n_store) && (n0 < N);
     if (full && ep.res1) {
 #pragma unroll
       for (int i = 0; i < CPR; ++i) {
         r1[i] = make_uint4(0, 0, 0, 0);
         if (rows.mT[i] >= 0)
-          r1[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.res1) +
-                                                       (size_t)rows.mT[i] * ep.ld_res1 + o0 + (lane % CPR) * 8));
+          r1[i] = ldg_v4_early(reinterpret_cast<const bf16*>(ep.res1) + (size_t)rows.mT[i] * ep.ld_res1 + o0 +
+                               (lane % CPR) * 8);
+      }
+    }
+  }
+};
+
+// bias (+ the warp-uniform rowbias row) of the up-to-three chunks a warp serves: lane j holds column
+// n_base + c*32 + j; fetched before the accumulator wait, redistributed through smem per chunk
+struct BiasPrefetch {
+  float b[3], u[3];
+  __device__ __forceinline__ void issue(const ctrlv_epilogue& ep, int n_base, int N, int nch, int sub,
+                                        const float* rb_uniform) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int c = sub + 3 * i;
+      const int nl = n_base + c * 32 + lane;
+      b[i] = 0.f; u[i] = 0.f;
+      if (c < nch && nl < N) {
+        if (ep.bias) b[i] = ldg_f32_early(ep.bias + nl);
+        if (rb_uniform) u[i] = ldg_f32_early(rb_uniform + nl);
       }
     }
   }
@@ -217,7 +248,7 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
 // one 32-column accumulator chunk of one row: TMEM load, bias, (GEGLU), residual, store
 template <bool GEGLU>
 __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t taddr, long long m, bool valid, int n0,
-                                         int n_store, float* sb, uint4* wst, const float* rb,
+                                         int n_store, float* sb, uint4* wst, const float* rb, float bv,
                                          const ResPrefetch<GEGLU ? 16 : 32>& pf,
                                          const EpRows<GEGLU ? 16 : 32>& rows) {
   constexpr int NV = GEGLU ? 16 : 32;
@@ -225,7 +256,7 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
   tmem_ld32(taddr, raw);
   // bias (+ warp-uniform rowbias): lane j fetched column j; broadcast through this warp's smem row
   __syncwarp();  // previous chunk's readers are done with the row
-  sb[threadIdx.x & 31] = pf.bv;
+  sb[threadIdx.x & 31] = bv;
   __syncwarp();
   tmem_ld_wait();
   float v[32];
@@ -258,42 +289,46 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
 // chunk groups, at most 3 chunks for BN <= 256).  Residual rows are fetched one chunk AHEAD — the
 // first one before the accumulator is even ready — so their HBM latency overlaps the MMA wait and
 // the previous chunk's math instead of sitting on the critical path.
-template <bool GEGLU, int EW>
+template <bool GEGLU>
 __device__ __forceinline__ void ep_tile(const ctrlv_epilogue& ep, uint64_t* tfull, uint32_t tphase, uint32_t t_row,
                                         long long m, int n_base, int N, int BN, int n_store, bool valid, int sub,
                                         float* sbias, uint4* wst, const float* rb, const float* rb_uniform) {
   constexpr int NV = GEGLU ? 16 : 32;
-  constexpr int G = EW / 4;
+  constexpr int G = kEpiWarps / 4;
   const int nch = BN / 32;
   const int c0 = sub, c1 = sub + G, c2 = sub + 2 * G;
   EpRows<NV> rows;
   rows.init(m, valid);
   ResPrefetch<NV> pa, pb;
+  BiasPrefetch bp;
   auto o_of = [&](int c) { return GEGLU ? ((n_base + c * 32) >> 1) : (n_base + c * 32); };
-  // the first TWO chunks' residual rows are requested before the accumulator is ready: their HBM
-  // latency hides under the MMA wait instead of under one chunk of epilogue math
-  if (c0 < nch) pa.issue(ep, rows, o_of(c0), n_store, n_base + c0 * 32, N, rb_uniform);
-  if (c1 < nch) pb.issue(ep, rows, o_of(c1), n_store, n_base + c1 * 32, N, rb_uniform);
+  // every bias value and the first TWO chunks' residual rows are requested before the accumulator is
+  // ready: their latency hides under the MMA wait instead of under epilogue math
+  bp.issue(ep, n_base, N, nch, sub, rb_uniform);
+  if (c0 < nch) pa.issue(ep, rows, o_of(c0), n_store, n_base + c0 * 32, N);
+  if (c1 < nch) pb.issue(ep, rows, o_of(c1), n_store, n_base + c1 * 32, N);
   mbar_wait(tfull, tphase);
   tc_fence_after();
   if (c0 >= nch) return;
   __syncwarp();
-  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c0 * 32), m, valid, n_base + c0 * 32, n_store, sbias, wst, rb, pa, rows);
+  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c0 * 32), m, valid, n_base + c0 * 32, n_store, sbias, wst, rb,
+                  bp.b[0] + bp.u[0], pa, rows);
   if (c1 >= nch) return;
-  if (c2 < nch) pa.issue(ep, rows, o_of(c2), n_store, n_base + c2 * 32, N, rb_uniform);
+  if (c2 < nch) pa.issue(ep, rows, o_of(c2), n_store, n_base + c2 * 32, N);
   __syncwarp();
-  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c1 * 32), m, valid, n_base + c1 * 32, n_store, sbias, wst, rb, pb, rows);
+  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c1 * 32), m, valid, n_base + c1 * 32, n_store, sbias, wst, rb,
+                  bp.b[1] + bp.u[1], pb, rows);
   if (c2 >= nch) return;
   __syncwarp();
-  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c2 * 32), m, valid, n_base + c2 * 32, n_store, sbias, wst, rb, pa, rows);
+  ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c2 * 32), m, valid, n_base + c2 * 32, n_store, sbias, wst, rb,
+                  bp.b[2] + bp.u[2], pa, rows);
 }
 
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) shares
 // one 256-row x BN tile: each CTA loads its own 128 A rows and HALF of the B tile, the leader issues
 // M=256 MMAs that read both halves — halves the shared-memory and L2 traffic of the B operand.
-template <int CG, int EW>
-__global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
-  constexpr int kEpiWarps = EW;
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -301,8 +336,8 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_con
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float wbias[EW][32];   // per-warp broadcast row for the bias chunk
-  __shared__ __align__(16) uint4 wstage[EW][128];  // per-warp 32 x 64 B transpose tile
+  __shared__ __align__(16) float wbias[kEpiWarps][32];   // per-warp broadcast row for the bias chunk
+  __shared__ __align__(16) uint4 wstage[kEpiWarps][128];  // per-warp 32 x 64 B transpose tile
 
   // 1024-byte aligned tile ring
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -335,6 +370,9 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;
+  // register reallocation between the warpgroups (whole warpgroups execute the same setmaxnreg)
+  if (warp < kFirstEpiWarp) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
   pdl_wait();  // everything above overlapped the predecessor's tail; its results are needed from here
 
   // work unit: (super-tile of CG consecutive m-tiles, n-tile); units are dealt round-robin to
@@ -452,10 +490,10 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_con
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp >= kFirstEpiWarp) {
     // ================================ epilogue ====================================
     const int q = warp & 3;  // TMEM lane quarter owned by this warp
-    const int sub = (warp - 2) >> 2;  // which of the 4 chunk groups this warp serves
+    const int sub = (warp - kFirstEpiWarp) >> 2;  // which of the 3 chunk groups this warp serves
     const int r = q * 32 + lane;
     const ctrlv_epilogue& ep = p.ep;
     const int n_out_total = ep.geglu ? p.N / 2 : p.N;
@@ -493,13 +531,13 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) igemm_kernel(const __grid_con
         if (uni && ref >= 0) rb_uniform = ep.rowbias + (size_t)ref * ep.ld_rowbias;
         else if (valid) rb = ep.rowbias + (size_t)my_ridx * ep.ld_rowbias;
       }
-      float* sbias = wbias[warp - 2];
+      float* sbias = wbias[warp - kFirstEpiWarp];
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
-      uint4* wst = wstage[warp - 2];
-      if (EW == 16 || ep.geglu)  // the 16-warp instantiation is GEGLU-only (keeps it inside 96 registers)
-        ep_tile<true, EW>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
+      uint4* wst = wstage[warp - kFirstEpiWarp];
+      if (ep.geglu)
+        ep_tile<true>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
       else
-        ep_tile<false, EW>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
+        ep_tile<false>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -537,10 +575,10 @@ static int device_props(const DevProps** out) {
     CTRLV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CTRLV_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     cudaFuncAttributes fa;
-    CTRLV_CUDA(cudaFuncGetAttributes(&fa, igemm_kernel<1, 12>));
+    CTRLV_CUDA(cudaFuncGetAttributes(&fa, igemm_kernel<1>));
     smem -= (int)fa.sharedSizeBytes;  // static shared memory (barriers, epilogue tiles) counts against the limit
-    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<1, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dp.max_smem = smem;
     dp.sms = sms;
   }
@@ -712,13 +750,11 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
 
   size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   if (p.bres) smem = (size_t)p.bres_off + (size_t)p.kblocks * p.BN * kBK * 2 + 1024;
-  // 16 epilogue warps for the GEGLU epilogue (erf math on 8 chunks of a 256-wide tile: 2 per warp)
-  int ew = 12;  // (16 warps measured no faster for the GEGLU epilogue: it is issue-bound, not latency-bound)
-  const int threads = 64 + ew * 32;
+  const int threads = kThreads;
   if (p.cg == 1) {
     int grid = p.tiles_total < g_num_sms ? p.tiles_total : g_num_sms;
     if (p.bres) grid = (g_num_sms / p.tiles_n) * p.tiles_n;
-    CTRLV_CUDA(launch_pdl(igemm_kernel<1, 12>, dim3(grid), dim3(threads), smem, stream, p));
+    CTRLV_CUDA(launch_pdl(igemm_kernel<1>, dim3(grid), dim3(threads), smem, stream, p));
   } else {
     const int pairs = p.tiles_total < g_num_sms / 2 ? p.tiles_total : g_num_sms / 2;
     cudaLaunchConfig_t cfg;
@@ -735,7 +771,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 2;
     count_launch();
-    CTRLV_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<2, 12>, p));
+    CTRLV_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<2>, p));
   }
   return CTRLV_OK;
 }
