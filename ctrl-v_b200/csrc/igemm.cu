@@ -370,9 +370,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;
-  // register reallocation between the warpgroups (whole warpgroups execute the same setmaxnreg)
-  if (warp < kFirstEpiWarp) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
   pdl_wait();  // everything above overlapped the predecessor's tail; its results are needed from here
 
   // work unit: (super-tile of CG consecutive m-tiles, n-tile); units are dealt round-robin to
@@ -391,6 +388,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     nunits = per_n * p.tiles_n;
   }
 
+  // register reallocation between the warpgroups: each warpgroup executes ONE setmaxnreg at the head of
+  // its role branch (ptxas budgets the code below it accordingly)
+  if (warp < kFirstEpiWarp) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
     // ================================ TMA producer ================================
     {  // warp-uniform loop, one elected lane issues (see the MMA issuer below)
@@ -490,7 +491,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         __syncwarp();
       }
     }
-  } else if (warp >= kFirstEpiWarp) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
     // ================================ epilogue ====================================
     const int q = warp & 3;  // TMEM lane quarter owned by this warp
     const int sub = (warp - kFirstEpiWarp) >> 2;  // which of the 3 chunk groups this warp serves
