@@ -261,7 +261,8 @@ def class_rooflines(prof, peaks):
         out["attention_spatial"] = {"bound": "tensor", "kernel": "ctrlv::attn2_kernel / attn_kernel<0>", "launches": n,
                                     "ms_per_step": ms, "achieved": fl / ms / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
                                     "frac": fl / ms / 1e9 / tf_peak}
-    for name, ops_, kern in (("groupnorm", ("groupnorm",), "ctrlv::gn_stats_kernel + gn_apply_kernel"),
+    for name, ops_, kern in (("groupnorm", ("groupnorm", "groupnorm_apply"),
+                              "ctrlv::gn_apply_kernel (statistics from the producers' epilogues; gn_stats_kernel only where none)"),
                              ("layernorm", ("layernorm",), "ctrlv::layernorm_kernel"),
                              ("attention_temporal", ("attn_temporal",), "ctrlv::attn_kernel<1>")):
         n, ms, _, by = agg(ops_)
@@ -544,10 +545,11 @@ def run_sweep(a):
             ctx_b = models._f(torch.cat([tr.attn2.b, tr.tattn2.b]))
             tr.attn2.off, tr.tattn2.off = 0, C
             ctx = ops.small_linear(ehs, ctx_w, ctx_b)
-            aux = SimpleNamespace(temb=ops.small_linear(emb, temb_w, temb_b, act_in=True), ctx=ctx, ctx_all=ctx,
-                                  vB=ctx.shape[0], b0=0)
+            # (block-level calls: the norm1 / transformer-norm input has no producer here, so those two norms run
+            # their statistics pass; the three norms inside the ResBlock take theirs from the conv epilogues)
+            aux = models._Aux(ops.small_linear(emb, temb_w, temb_b, act_in=True), ctx, arena=models._GNArena(4, F_))
             x = torch.randn(M, C, device=dev).to(BF)
-            ms = timeit(lambda: rb(x, aux, g))
+            ms = timeit(lambda: (aux.gn_reset(), rb(x, aux, g)))
             rec(f"{tag} SpatioTemporalResBlock C={C} {hh}x{ww} (2 conv3x3 + 2 conv(3,1,1) + 4 GroupNorm)", ms, "tensor",
                 flops=2.0 * M * (18 * C * C + 6 * C * C))
             ms = timeit(lambda: ops.conv3x3(x, F_, hh, ww, rb.conv1_w, bias=rb.conv1_b))

@@ -42,6 +42,12 @@ class Epilogue(C.Structure):
         ("out_f32", C.c_void_p),
         ("ld_out_f32", C.c_int32),
         ("n_store", C.c_int32),
+        ("gn_sums", C.c_void_p),
+        ("gn_rows_per_unit", C.c_int32),
+        ("gn_cg", C.c_int32),
+        ("gn_c_off", C.c_int32),
+        ("gn_units", C.c_int32),
+        ("gn_rep", C.c_int32),
     ]
 
 
@@ -91,6 +97,8 @@ SIGNATURES = {
     "ctrlv_conv_t3": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(Epilogue), _P]),
     "ctrlv_groupnorm_workspace": (_L, [_I]),
     "ctrlv_groupnorm": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P]),
+    "ctrlv_groupnorm_apply": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _F, _I, _P, _P, _I, _P]),
+    "ctrlv_axpby_gn": (_I, [_P, _P, _F, _F, _L, _I, _P, _P, _I, _I, _I, _I, _P]),
     "ctrlv_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _I, _P, _P]),
     "ctrlv_attn_spatial": (_I, [_P, _I, _I, _I, _F, _P, _P]),
     "ctrlv_attn_temporal": (_I, [_P, _I, _I, _I, _I, _F, _P, _P]),

@@ -50,6 +50,7 @@ struct IgemmParams {
   int bres;       // 1: weight-stationary — the CTA's whole B tile (all K) stays resident in smem
   int bres_off;   // byte offset of the resident B region (after the A ring)
   int m_tiles;    // tiles_x * tiles_y * tiles_z
+  FastDiv fd_rpu, fd_cg;  // GroupNorm statistics: division by rows per unit / channels per group
   ctrlv_epilogue ep;
 };
 
@@ -84,6 +85,96 @@ struct EpRows {  // per (tile, warp): the rows this lane touches in the transpos
     return row * CPR + (CPR == 4 ? (piece ^ ((row >> 1) & 3)) : (piece ^ ((row >> 2) & 1)));
   }
 };
+
+// ---- GroupNorm statistics of the stored tile (ep.gn_sums) ---------------------------------------
+// The nn.GroupNorm that consumes this kernel's output needs (sum, sum of squares) per (statistics unit,
+// channel group).  The epilogue already holds every output value: after the transposed read of the
+// staged bf16 tile a lane owns 8 consecutive columns of 4 rows, so it sums those rows per column,
+// splits the 8 columns between the (at most two) groups they fall in, an xor-shuffle reduces over
+// the 8 lanes that hold the same columns, and one lane per column piece adds the partials to
+// gn_sums[unit][group] as 64-bit FIXED-POINT integers (scale 2^16): integer addition is associative, so
+// the result is bit-identical from run to run whatever order the atomics land in — no float atomics.
+constexpr float kGnFix = 65536.0f;
+struct GnTile {  // per (tile, warp)
+  int uT[4];     // statistics unit of the 4 rows this lane touches in the transposed mapping (-1: no row)
+  int u0;        // smallest unit among the warp's rows (-1: the warp has no valid row)
+  bool multi;    // the warp's 32 rows straddle more than one unit (small frames): one pass per unit
+  __device__ __forceinline__ void init(const IgemmParams& p, long long m, bool valid) {
+    const int lane = threadIdx.x & 31;
+    const int mu = valid ? (int)fd_div((uint32_t)m, p.fd_rpu) : -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) uT[i] = __shfl_sync(0xffffffffu, mu, lane / 4 + 8 * i);
+    int mn = mu < 0 ? 0x7fffffff : mu, mx = mu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    u0 = mx < 0 ? -1 : mn;
+    multi = mx != u0;
+  }
+};
+
+__device__ __forceinline__ void gn_atomic(void* sums, size_t rep_off, int unit, int group, float s, float q) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(sums) + rep_off + ((size_t)unit * 32 + group) * 2;
+  atomicAdd(a, (unsigned long long)__float2ll_rn(s * kGnFix));
+  atomicAdd(a + 1, (unsigned long long)__float2ll_rn(q * kGnFix));
+}
+
+// ut[i]: the 8 stored bf16 values (columns o0 + 8*(lane%4) ..) of row lane/4 + 8*i
+__device__ __forceinline__ void gn_accumulate(const uint4* ut, const GnTile& gn, const ctrlv_epilogue& ep,
+                                              const IgemmParams& p, int o0) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = ep.gn_c_off + o0 + (lane & 3) * 8;  // channel of this lane's first column in the consumer's numbering
+  const int gA = (int)fd_div((uint32_t)c0, p.fd_cg);
+  const int jb = (gA + 1) * ep.gn_cg - c0;           // columns j >= jb fall into group gA + 1
+  // The table is replicated gn_rep times (a power of two) and every warp adds into "its" replica: with only
+  // a few statistics units (a temporal norm has one per clip) all SMs would otherwise hammer the same
+  // handful of L2 lines (measured: +33 us on a 62 us launch).  The consumer sums the replicas.
+  const size_t rep_off = (size_t)((blockIdx.x * (unsigned)kEpiWarps + (threadIdx.x >> 5)) & (unsigned)(ep.gn_rep - 1)) *
+                         (size_t)ep.gn_units * 64;
+  int ucur = gn.u0;
+  while (true) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (gn.uT[i] == ucur) {
+        const uint32_t w[4] = {ut[i].x, ut[i].y, ut[i].z, ut[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16x2(w[k]);
+          s[2 * k] += f.x; q[2 * k] = fmaf(f.x, f.x, q[2 * k]);
+          s[2 * k + 1] += f.y; q[2 * k + 1] = fmaf(f.y, f.y, q[2 * k + 1]);
+        }
+      }
+    }
+    float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < jb) { sA += s[j]; qA += q[j]; } else { sB += s[j]; qB += q[j]; }
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      sA += __shfl_xor_sync(0xffffffffu, sA, o); qA += __shfl_xor_sync(0xffffffffu, qA, o);
+      sB += __shfl_xor_sync(0xffffffffu, sB, o); qB += __shfl_xor_sync(0xffffffffu, qB, o);
+    }
+    if (lane < 4) {
+      gn_atomic(ep.gn_sums, rep_off, ucur, gA, sA, qA);
+      if (jb < 8) gn_atomic(ep.gn_sums, rep_off, ucur, gA + 1, sB, qB);
+    }
+    if (!gn.multi) break;
+    int nx = 0x7fffffff;  // next statistics unit present in this warp's rows
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (gn.uT[i] > ucur) nx = min(nx, gn.uT[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nx = min(nx, __shfl_xor_sync(0xffffffffu, nx, o));
+    if (nx == 0x7fffffff) break;
+    ucur = nx;
+  }
+}
 
 // Prefetch loads are volatile asm: the compiler may not sink them below the (volatile) accumulator wait,
 // so their latency overlaps the MMA instead of sitting on the epilogue's critical path.
@@ -152,7 +243,7 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u, float s) { 
 template <int NV>
 __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, long long m, bool valid, int o0,
                                           int n_store, const ResPrefetch<NV>& pf, const EpRows<NV>& rows,
-                                          uint4* wst) {
+                                          uint4* wst, const GnTile& gn, const IgemmParams& p) {
   constexpr int CPR = NV / 8;
   constexpr int RPI = 32 / CPR;
   const int lane = threadIdx.x & 31;
@@ -184,6 +275,11 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
         for (int j = 0; j < CPR; ++j) add_bf16x8(v + 8 * j, __ldg(rp + j), ep.s_res2);
       }
     }
+    if (ep.out_f32 && valid) {  // (before the bf16 path: v[] is dead once it is packed)
+      float4* op = reinterpret_cast<float4*>(ep.out_f32 + (size_t)m * ep.ld_out_f32 + o0);
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) op[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
     if (ep.out && NV == 16) {
       // GEGLU chunks yield only 32 B per row: the transpose does not pay (measured), store directly
       // One 256-bit store per lane = one whole 32-byte sector (two 16-byte stores leave the L2 with
@@ -214,18 +310,15 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
         wst[EpRows<NV>::slot(lane, j)] = u;
       }
       __syncwarp();
+      uint4 ut[CPR];
 #pragma unroll
       for (int i = 0; i < CPR; ++i) {
-        const uint4 u = wst[EpRows<NV>::slot(lane / CPR + RPI * i, lane % CPR)];
+        ut[i] = wst[EpRows<NV>::slot(lane / CPR + RPI * i, lane % CPR)];
         if (rows.mT[i] >= 0)
           *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)rows.mT[i] * ep.ld_out + o0 +
-                                    (lane % CPR) * 8) = u;
+                                    (lane % CPR) * 8) = ut[i];
       }
-    }
-    if (ep.out_f32 && valid) {
-      float4* op = reinterpret_cast<float4*>(ep.out_f32 + (size_t)m * ep.ld_out_f32 + o0);
-#pragma unroll
-      for (int j = 0; j < NV; j += 4) op[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      if (NV == 32 && ep.gn_sums && gn.u0 >= 0) gn_accumulate(ut, gn, ep, p, o0);  // warp-uniform
     }
   } else if (valid) {
     // ragged tail of a padded-N problem (e.g. conv_out with 4 real channels): scalar, predicated
@@ -250,7 +343,7 @@ template <bool GEGLU>
 __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t taddr, long long m, bool valid, int n0,
                                          int n_store, float* sb, uint4* wst, const float* rb, float bv,
                                          const ResPrefetch<GEGLU ? 16 : 32>& pf,
-                                         const EpRows<GEGLU ? 16 : 32>& rows) {
+                                         const EpRows<GEGLU ? 16 : 32>& rows, const GnTile& gn, const IgemmParams& p) {
   constexpr int NV = GEGLU ? 16 : 32;
   uint32_t raw[32];
   tmem_ld32(taddr, raw);
@@ -282,7 +375,7 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
       v[j] = o0; v[j + 1] = o1;
     }
   }
-  ep_finish<NV>(v, ep, m, valid, GEGLU ? (n0 >> 1) : n0, n_store, pf, rows, wst);
+  ep_finish<NV>(v, ep, m, valid, GEGLU ? (n0 >> 1) : n0, n_store, pf, rows, wst, gn, p);
 }
 
 // All 32-column chunks of one accumulator row owned by this warp (c = sub, sub + G, sub + 2G, G = 3
@@ -292,13 +385,17 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
 template <bool GEGLU>
 __device__ __forceinline__ void ep_tile(const ctrlv_epilogue& ep, uint64_t* tfull, uint32_t tphase, uint32_t t_row,
                                         long long m, int n_base, int N, int BN, int n_store, bool valid, int sub,
-                                        float* sbias, uint4* wst, const float* rb, const float* rb_uniform) {
+                                        float* sbias, uint4* wst, const float* rb, const float* rb_uniform,
+                                        const IgemmParams& p) {
   constexpr int NV = GEGLU ? 16 : 32;
   constexpr int G = kEpiWarps / 4;
   const int nch = BN / 32;
   const int c0 = sub, c1 = sub + G, c2 = sub + 2 * G;
   EpRows<NV> rows;
   rows.init(m, valid);
+  GnTile gn;
+  gn.u0 = -1; gn.multi = false;
+  if (!GEGLU && ep.gn_sums) gn.init(p, m, valid);
   ResPrefetch<NV> pa, pb;
   BiasPrefetch bp;
   auto o_of = [&](int c) { return GEGLU ? ((n_base + c * 32) >> 1) : (n_base + c * 32); };
@@ -312,16 +409,16 @@ __device__ __forceinline__ void ep_tile(const ctrlv_epilogue& ep, uint64_t* tful
   if (c0 >= nch) return;
   __syncwarp();
   ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c0 * 32), m, valid, n_base + c0 * 32, n_store, sbias, wst, rb,
-                  bp.b[0] + bp.u[0], pa, rows);
+                  bp.b[0] + bp.u[0], pa, rows, gn, p);
   if (c1 >= nch) return;
   if (c2 < nch) pa.issue(ep, rows, o_of(c2), n_store, n_base + c2 * 32, N);
   __syncwarp();
   ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c1 * 32), m, valid, n_base + c1 * 32, n_store, sbias, wst, rb,
-                  bp.b[1] + bp.u[1], pb, rows);
+                  bp.b[1] + bp.u[1], pb, rows, gn, p);
   if (c2 >= nch) return;
   __syncwarp();
   ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c2 * 32), m, valid, n_base + c2 * 32, n_store, sbias, wst, rb,
-                  bp.b[2] + bp.u[2], pa, rows);
+                  bp.b[2] + bp.u[2], pa, rows, gn, p);
 }
 
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) shares
@@ -538,9 +635,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
       uint4* wst = wstage[warp - kFirstEpiWarp];
       if (ep.geglu)
-        ep_tile<true>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
+        ep_tile<true>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform, p);
       else
-        ep_tile<false>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform);
+        ep_tile<false>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform, p);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -741,6 +838,19 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
     CTRLV_CHECK_ARG(p.ep.rowbias != nullptr && p.ep.rb_div > 0, "igemm: rowbias mode without table");
   if (p.ep.rb_mode == 2 || p.ep.rb_mode == 3)
     CTRLV_CHECK_ARG(p.ep.rb_mod > 0 && (p.ep.rb_mode == 2 || p.ep.rb_B > 0), "igemm: bad rowbias modulus");
+  if (p.ep.gn_sums) {
+    CTRLV_CHECK_ARG(!p.ep.geglu && p.ep.out != nullptr && p.ep.n_store == 0 && d->N % p.BN == 0,
+                    "igemm: GroupNorm statistics need a full-width bf16 output without GEGLU");
+    // an aligned 8-column piece must fall into at most two groups
+    CTRLV_CHECK_ARG(p.ep.gn_rows_per_unit > 0 && (p.ep.gn_cg >= 7 || p.ep.gn_cg == 4 || p.ep.gn_cg == 6) &&
+                        p.ep.gn_c_off >= 0 && p.ep.gn_c_off % 8 == 0 && (reinterpret_cast<uintptr_t>(p.ep.gn_sums) & 7) == 0,
+                    "igemm: GroupNorm statistics need rows_per_unit > 0, 4, 6 or >= 7 channels per group, c_off %% 8 == 0");
+    CTRLV_CHECK_ARG((p.ep.gn_c_off + d->N + p.ep.gn_cg - 1) / p.ep.gn_cg <= 32, "igemm: channels fall outside the 32 groups");
+    CTRLV_CHECK_ARG(p.ep.gn_rep >= 1 && (p.ep.gn_rep & (p.ep.gn_rep - 1)) == 0 && p.ep.gn_units >= 1,
+                    "igemm: gn_rep must be a power of two, gn_units >= 1");
+    p.fd_rpu = make_fastdiv((uint32_t)p.ep.gn_rows_per_unit);
+    p.fd_cg = make_fastdiv((uint32_t)p.ep.gn_cg);
+  }
   // vector paths need 16B-aligned rows
   const int n_out = p.ep.geglu ? d->N / 2 : d->N;
   const int n_store = p.ep.n_store > 0 ? p.ep.n_store : n_out;

@@ -82,6 +82,90 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ src0, int C0, const bf1
 }
 
 // ------------------------------------------------------------------------------------------
+// out = a*x + b*y (the ControlNet residual added into a UNet skip connection) fused with the statistics
+// of `out` for the GroupNorm that consumes it: same thread layout and block reduction as
+// gn_stats_kernel; the block's group sums are added to sums[unit][group] as int64 fixed point
+// (x 2^16, integer atomics: order-independent, hence deterministic) — the format the igemm epilogue uses.
+// ------------------------------------------------------------------------------------------
+__global__ void axpby_gn_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, float a, float b, int C,
+                                int rows_per_unit, int rows_per_split, int nsplit, int nwork,
+                                bf16* __restrict__ out, unsigned long long* __restrict__ sums, int cg, int c_off,
+                                int n_units, int n_rep) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float gn_smem[];  // [nwork][8] thread sums, then [vpr*4][2] channel-pair sums
+  const int vpr = C >> 3;
+  const int unit = blockIdx.x / nsplit;
+  const int split = blockIdx.x % nsplit;
+  const int tid = threadIdx.x;
+  const int vec = tid % vpr;
+  const int rpar = nwork / vpr;
+  const int rsub = tid < nwork ? tid / vpr : rows_per_unit;
+  const int r_begin = split * rows_per_split;
+  int r_end = r_begin + rows_per_split;
+  if (r_end > rows_per_unit) r_end = rows_per_unit;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  const size_t row0 = (size_t)unit * rows_per_unit;
+#pragma unroll 4
+  for (int r = r_begin + rsub; r < r_end; r += rpar) {
+    const size_t off = (row0 + r) * C + (vec << 3);
+    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + off));
+    uint32_t wo[4] = {ux.x, ux.y, ux.z, ux.w};
+    if (y) {  // (y == nullptr: statistics of x itself, nothing written)
+      const uint4 uy = __ldg(reinterpret_cast<const uint4*>(y + off));
+      const uint32_t wy[4] = {uy.x, uy.y, uy.z, uy.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fx = unpack_bf16x2(wo[k]), fy = unpack_bf16x2(wy[k]);
+        wo[k] = pack_bf16x2(a * fx.x + b * fy.x, a * fx.y + b * fy.y);
+      }
+      *reinterpret_cast<uint4*>(out + off) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(wo[k]);  // statistics of the value the consumer will read
+      s[k] += f.x + f.y;
+      q[k] += f.x * f.x + f.y * f.y;
+    }
+  }
+  if (tid < nwork) {
+    float* t = gn_smem + (size_t)tid * 8;
+    t[0] = s[0]; t[1] = s[1]; t[2] = s[2]; t[3] = s[3];
+    t[4] = q[0]; t[5] = q[1]; t[6] = q[2]; t[7] = q[3];
+  }
+  __syncthreads();
+  const int npair = vpr * 4;
+  float* pair = gn_smem + (size_t)nwork * 8;  // [npair][2]
+  for (int pp = tid; pp < npair; pp += blockDim.x) {
+    const int v = pp >> 2, pi = pp & 3;
+    float ps = 0.f, pq = 0.f;
+    for (int rs = 0; rs < rpar; ++rs) {
+      const float* t = gn_smem + (size_t)(rs * vpr + v) * 8;
+      ps += t[pi];
+      pq += t[4 + pi];
+    }
+    pair[pp * 2] = ps; pair[pp * 2 + 1] = pq;
+  }
+  __syncthreads();
+  if (tid < kGroups) {
+    // channel pairs [lo, hi) of group tid that fall inside this tensor's channel range [c_off, c_off + C)
+    int lo = tid * cg - c_off, hi = lo + cg;
+    if (lo < 0) lo = 0;
+    if (hi > C) hi = C;
+    if (lo < hi) {
+      float gs = 0.f, gq = 0.f;
+      for (int i = lo >> 1; i < (hi >> 1); ++i) {
+        gs += pair[i * 2];
+        gq += pair[i * 2 + 1];
+      }
+      unsigned long long* o = sums + ((size_t)(blockIdx.x & (unsigned)(n_rep - 1)) * n_units + unit) * (kGroups * 2) + tid * 2;
+      atomicAdd(o, (unsigned long long)__float2ll_rn(gs * 65536.0f));
+      atomicAdd(o + 1, (unsigned long long)__float2ll_rn(gq * 65536.0f));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // GroupNorm apply (+SiLU): out[row][C0+C1] = act((x - mean) * rstd * gamma + beta)
 // grid = n_units * blocks_per_unit; a block stays inside one statistics unit.
 // ------------------------------------------------------------------------------------------
@@ -89,7 +173,8 @@ __global__ void __launch_bounds__(512, 3) gn_apply_kernel(const bf16* __restrict
                                 int C1, int rows_per_unit, int blocks_per_unit, int nsplit,
                                 int nwork, const float* __restrict__ partial, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu,
-                                bf16* __restrict__ out) {
+                                bf16* __restrict__ out, const long long* __restrict__ fixed_sums, int n_units,
+                                int n_rep) {
   pdl_wait();
   pdl_trigger();
   __shared__ float mean_s[kGroups], rstd_s[kGroups];
@@ -100,6 +185,35 @@ __global__ void __launch_bounds__(512, 3) gn_apply_kernel(const bf16* __restrict
   const int unit = blockIdx.x / blocks_per_unit;
   const int blk = blockIdx.x % blocks_per_unit;
   const int tid = threadIdx.x;
+  if (fixed_sums) {
+    // statistics accumulated by the producers of the input (igemm epilogue / axpby_gn): int64 fixed point
+    // (x 2^16), n_rep replicas of one 512-byte record per unit.  Warp w adds replicas w, w + nwarps, ...
+    // (lane = group, one 16-byte load each), then group g adds the warp sums: integer arithmetic, exact.
+    const int nwarps = blockDim.x >> 5;
+    const int wid = tid >> 5, lane = tid & 31;
+    long long (*wll)[kGroups][2] = reinterpret_cast<long long (*)[kGroups][2]>(wsum);
+    const longlong2* rec = reinterpret_cast<const longlong2*>(fixed_sums) + (size_t)unit * kGroups + lane;
+    long long fs = 0, fq = 0;
+    for (int i = wid; i < n_rep; i += nwarps) {
+      const longlong2 v = __ldg(rec + (size_t)i * n_units * kGroups);
+      fs += v.x;
+      fq += v.y;
+    }
+    wll[wid][lane][0] = fs;
+    wll[wid][lane][1] = fq;
+    __syncthreads();
+    if (tid < kGroups) {
+      fs = 0; fq = 0;
+      const int nw = nwarps < n_rep ? nwarps : n_rep;
+      for (int w = 0; w < nw; ++w) { fs += wll[w][tid][0]; fq += wll[w][tid][1]; }
+      const double cnt = (double)rows_per_unit * cg;
+      const double mean = (double)fs * (1.0 / 65536.0) / cnt;
+      double var = (double)fq * (1.0 / 65536.0) / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mean_s[tid] = (float)mean;
+      rstd_s[tid] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  } else
   // deterministic reduction of the split partials: warp w sums splits w, w+nwarps, ... (lane =
   // group, one coalesced 256-byte record per split, loads unrolled so they overlap), then group g
   // adds the warp sums in warp order (fp64)
@@ -265,14 +379,25 @@ extern "C" int64_t ctrlv_groupnorm_workspace(int32_t n_units) {
   return (int64_t)n_units * kMaxSplit * kGroups * 2 * sizeof(float);
 }
 
-extern "C" int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, int32_t C1,
-                               int32_t n_units, int32_t rows_per_unit, const float* gamma,
-                               const float* beta, float eps, int32_t silu, void* out,
-                               void* workspace, void* stream_) {
+static int n_sm_current(int* out) {
+  static int n_sm_of[64] = {0};  // per device ordinal
+  int dev = 0;
+  CTRLV_CUDA(cudaGetDevice(&dev));
+  CTRLV_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+  if (n_sm_of[dev] == 0) CTRLV_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
+  *out = n_sm_of[dev];
+  return CTRLV_OK;
+}
+
+// fixed_sums == nullptr: statistics pass into `workspace`, then apply; else apply only
+static int groupnorm_impl(const void* src0, int32_t C0, const void* src1, int32_t C1,
+                          int32_t n_units, int32_t rows_per_unit, const float* gamma,
+                          const float* beta, float eps, int32_t silu, void* out,
+                          void* workspace, const void* fixed_sums, int n_rep, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!src1) C1 = 0;
   const int C = C0 + C1;
-  CTRLV_CHECK_ARG(src0 && out && workspace && gamma && beta, "groupnorm: null pointer");
+  CTRLV_CHECK_ARG(src0 && out && (workspace || fixed_sums) && gamma && beta, "groupnorm: null pointer");
   CTRLV_CHECK_ARG(C0 % 8 == 0 && C1 % 8 == 0 && C % 64 == 0, "groupnorm: C0=%d C1=%d need %%8 and sum %%64", C0, C1);
   CTRLV_CHECK_ARG(n_units > 0 && rows_per_unit > 0, "groupnorm: empty input");
   const int vpr = C / 8;
@@ -284,12 +409,11 @@ extern "C" int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, i
   const int nthreads = (nwork + 31) / 32 * 32;
   // Both kernels do uniform work per block: size each grid to ONE full wave of resident blocks
   // (a 1.04-wave grid costs two waves).  Statistics splits and apply blocks are independent.
-  static int n_sm_of[64] = {0};  // per device ordinal
-  int dev = 0;
-  CTRLV_CUDA(cudaGetDevice(&dev));
-  CTRLV_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
-  if (n_sm_of[dev] == 0) CTRLV_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
-  const int n_sm = n_sm_of[dev];
+  int n_sm = 0;
+  {
+    const int rc = n_sm_current(&n_sm);
+    if (rc) return rc;
+  }
   const size_t st_smem = ((size_t)nwork * 8 + (size_t)vpr * 8) * sizeof(float);
   int occ_stats = 1, occ_apply = 1;
   CTRLV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_stats, gn_stats_kernel, nthreads, st_smem));
@@ -311,13 +435,72 @@ extern "C" int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, i
   const int rows_per_blk = (rows_per_unit + nblk - 1) / nblk;
   nblk = (rows_per_unit + rows_per_blk - 1) / rows_per_blk;
   float* partial = reinterpret_cast<float*>(workspace);
-  CTRLV_CUDA(launch_pdl(gn_stats_kernel, dim3(n_units * nsplit), dim3(nthreads), st_smem, stream,
-                        reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1,
-                        rows_per_unit, rows_per_split, nsplit, nwork, partial));
+  if (!fixed_sums)
+    CTRLV_CUDA(launch_pdl(gn_stats_kernel, dim3(n_units * nsplit), dim3(nthreads), st_smem, stream,
+                          reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1,
+                          rows_per_unit, rows_per_split, nsplit, nwork, partial));
   CTRLV_CUDA(launch_pdl(gn_apply_kernel, dim3(n_units * nblk), dim3(nthreads), (size_t)0, stream,
                         reinterpret_cast<const bf16*>(src0), C0, reinterpret_cast<const bf16*>(src1), C1,
                         rows_per_unit, nblk, nsplit, nwork, (const float*)partial, gamma, beta, eps, silu,
-                        reinterpret_cast<bf16*>(out)));
+                        reinterpret_cast<bf16*>(out), reinterpret_cast<const long long*>(fixed_sums), n_units, n_rep));
+  return CTRLV_OK;
+}
+
+extern "C" int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, int32_t C1,
+                               int32_t n_units, int32_t rows_per_unit, const float* gamma,
+                               const float* beta, float eps, int32_t silu, void* out,
+                               void* workspace, void* stream_) {
+  CTRLV_CHECK_ARG(workspace != nullptr, "groupnorm: null workspace");
+  return groupnorm_impl(src0, C0, src1, C1, n_units, rows_per_unit, gamma, beta, eps, silu, out, workspace,
+                        nullptr, 1, stream_);
+}
+
+extern "C" int ctrlv_groupnorm_apply(const void* src0, int32_t C0, const void* src1, int32_t C1,
+                                     int32_t n_units, int32_t rows_per_unit, const float* gamma,
+                                     const float* beta, float eps, int32_t silu, void* out,
+                                     const void* sums, int32_t n_rep, void* stream_) {
+  CTRLV_CHECK_ARG(sums != nullptr && (reinterpret_cast<uintptr_t>(sums) & 7) == 0, "groupnorm_apply: null or misaligned sums");
+  CTRLV_CHECK_ARG(n_rep >= 1 && (n_rep & (n_rep - 1)) == 0, "groupnorm_apply: n_rep must be a power of two");
+  return groupnorm_impl(src0, C0, src1, C1, n_units, rows_per_unit, gamma, beta, eps, silu, out, nullptr, sums,
+                        n_rep, stream_);
+}
+
+extern "C" int ctrlv_axpby_gn(const void* x, const void* y, float a, float b, int64_t rows, int32_t C, void* out,
+                              void* gn_sums, int32_t rows_per_unit, int32_t cg, int32_t c_off, int32_t n_rep,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTRLV_CHECK_ARG(x && ((y == nullptr) == (out == nullptr)) && gn_sums && rows > 0 && C > 0 && C % 8 == 0 && C <= 8 * 1024,
+                  "axpby_gn: bad arguments (y and out both or neither, C %% 8, C <= 8192)");
+  CTRLV_CHECK_ARG(rows_per_unit > 0 && rows % rows_per_unit == 0 && cg >= 2 && cg % 2 == 0 && c_off >= 0 && c_off % 2 == 0,
+                  "axpby_gn: rows %% rows_per_unit, even cg and c_off");
+  CTRLV_CHECK_ARG((c_off + C + cg - 1) / cg <= kGroups, "axpby_gn: channels fall outside the 32 groups");
+  CTRLV_CHECK_ARG(n_rep >= 1 && (n_rep & (n_rep - 1)) == 0, "axpby_gn: n_rep must be a power of two");
+  const int n_units = (int)(rows / rows_per_unit);
+  const int vpr = C / 8;
+  int rpar = 512 / vpr;
+  if (rpar < 1) rpar = 1;
+  if (rpar > rows_per_unit) rpar = rows_per_unit;
+  const int nwork = vpr * rpar;
+  const int nthreads = (nwork + 31) / 32 * 32;
+  int n_sm = 0;
+  {
+    const int rc = n_sm_current(&n_sm);
+    if (rc) return rc;
+  }
+  const size_t smem = ((size_t)nwork * 8 + (size_t)vpr * 8) * sizeof(float);
+  int occ = 1;
+  CTRLV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, axpby_gn_kernel, nthreads, smem));
+  if (occ < 1) occ = 1;
+  int nsplit = occ * n_sm / n_units;  // one wave of resident blocks
+  const int max_by_rows = (rows_per_unit + rpar - 1) / rpar;
+  if (nsplit > max_by_rows) nsplit = max_by_rows;
+  if (nsplit < 1) nsplit = 1;
+  const int rows_per_split = (rows_per_unit + nsplit - 1) / nsplit;
+  nsplit = (rows_per_unit + rows_per_split - 1) / rows_per_split;
+  CTRLV_CUDA(launch_pdl(axpby_gn_kernel, dim3(n_units * nsplit), dim3(nthreads), smem, stream,
+                        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(y), a, b, C, rows_per_unit,
+                        rows_per_split, nsplit, nwork, reinterpret_cast<bf16*>(out),
+                        reinterpret_cast<unsigned long long*>(gn_sums), cg, c_off, n_units, n_rep));
   return CTRLV_OK;
 }
 

@@ -21,6 +21,7 @@ Activations are channels-last: a reference tensor [B*T, C, h, w] is a [B*T*h*w, 
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -264,30 +265,93 @@ class _ResBlock:
         self.tconv2_w, self.tconv2_b = _w(_conv_t3(sd[t + ".conv2.weight"].float())), _f(sd[t + ".conv2.bias"])
         self.alpha = float(torch.sigmoid(sd[pfx + ".time_mixer.mix_factor"].float()).item())
 
-    def __call__(self, x, aux, g, x1=None):
+    def __call__(self, x, aux, g, x1=None, st_in=None, st_out=None):
         """x [M, C0] (| x1 [M, C1] skip connection) -> [M, Cout];  g = geometry (B, T, H, W);
-        aux.temb holds every block's time_emb_proj(silu(emb)) (one batched launch per forward)."""
+        aux.temb holds every block's time_emb_proj(silu(emb)) (one batched launch per forward).
+
+        GroupNorm statistics ride in the epilogue of the launch that PRODUCES a norm's input
+        (SURVEY.md §8 row g1): `st_in` = statistics table of norm1's input x (| x1) if the caller's
+        producers accumulated it; `st_out` = table of the GroupNorm that consumes this block's output
+        (None: no norm follows, or not fused), filled by the last conv here.  Each of the four norms
+        below therefore runs as one apply pass."""
         B, T, H, W = g
         F_, HW = B * T, H * W
-        a1 = ops.groupnorm(x, F_, HW, self.norm1.g, self.norm1.b, self.eps, True, src1=x1)
+        a1 = ops.groupnorm(x, F_, HW, self.norm1.g, self.norm1.b, self.eps, True, src1=x1, stats=st_in)
         temb = aux.temb[:, self.temb_off:self.temb_off + self.cout]
         ttemb = aux.temb[:, self.ttemb_off:self.ttemb_off + self.cout]
+        st = aux.gn_stats(F_, HW, self.cout)
         h = ops.conv3x3(a1, F_, H, W, self.conv1_w, bias=self.conv1_b, rowbias=temb, rb_mode=1,
-                        rb_div=T * HW)
-        a2 = ops.groupnorm(h, F_, HW, self.norm2.g, self.norm2.b, self.eps, True)
+                        rb_div=T * HW, gn=_gn(st))
+        a2 = ops.groupnorm(h, F_, HW, self.norm2.g, self.norm2.b, self.eps, True, stats=st)
+        st = aux.gn_stats(B, T * HW, self.cout)
         if self.has_shortcut:
-            xs = ops.conv3x3(a2, F_, H, W, self.conv2_w, sc0=x, sc1=x1, bias=self.conv2_b)
+            xs = ops.conv3x3(a2, F_, H, W, self.conv2_w, sc0=x, sc1=x1, bias=self.conv2_b, gn=_gn(st))
         else:
             assert x1 is None
-            xs = ops.conv3x3(a2, F_, H, W, self.conv2_w, bias=self.conv2_b, res1=x)
+            xs = ops.conv3x3(a2, F_, H, W, self.conv2_w, bias=self.conv2_b, res1=x, gn=_gn(st))
         # temporal resnet on [B, T, HW, C] (GroupNorm statistics across frames), then AlphaBlender:
         #   out = a*xs + (1-a)*(xs + h_t) = xs + (1-a)*h_t
-        a3 = ops.groupnorm(xs, B, T * HW, self.tnorm1.g, self.tnorm1.b, self.eps, True)
+        a3 = ops.groupnorm(xs, B, T * HW, self.tnorm1.g, self.tnorm1.b, self.eps, True, stats=st)
+        st = aux.gn_stats(B, T * HW, self.cout)
         h2 = ops.conv_t3(a3, B, T, HW, self.tconv1_w, bias=self.tconv1_b, rowbias=ttemb, rb_mode=1,
-                         rb_div=T * HW)
-        a4 = ops.groupnorm(h2, B, T * HW, self.tnorm2.g, self.tnorm2.b, self.eps, True)
+                         rb_div=T * HW, gn=_gn(st))
+        a4 = ops.groupnorm(h2, B, T * HW, self.tnorm2.g, self.tnorm2.b, self.eps, True, stats=st)
         return ops.conv_t3(a4, B, T, HW, self.tconv2_w, bias=self.tconv2_b, s_acc=1.0 - self.alpha,
-                           res1=xs, s_res1=1.0)
+                           res1=xs, s_res1=1.0, gn=_gn(st_out))
+
+
+def _gn(st, c_off: int = 0):
+    """epilogue argument `gn=` for a producer of channels c_off.. of the norm whose statistics `st` holds"""
+    return None if st is None else (st, c_off)
+
+
+# GroupNorm statistics from the producers' epilogues (True) or from gn_stats_kernel passes (False: the
+# round-1 path, kept for A/B measurements and as the parity cross-check of the fused statistics)
+GN_FUSED = os.environ.get("CTRLV_GN_FUSED", "1") != "0"
+
+
+class _Aux:
+    """Per-forward side inputs of the blocks: the batched time-embedding projections and 1-token context
+    vectors, plus the arena the GroupNorm statistics tables of this forward come from."""
+
+    def __init__(self, temb, ctx, ctx_all=None, vB=None, b0=0, arena=None):
+        self.temb, self.ctx = temb, ctx
+        self.ctx_all = ctx if ctx_all is None else ctx_all
+        self.vB = ctx.shape[0] if vB is None else vB
+        self.b0 = b0
+        self.arena = arena
+
+    def gn_stats(self, n_units: int, rows_per_unit: int, C_total):
+        """A zeroed statistics table for the GroupNorm(32, C_total) over `n_units` units (None: not fused)."""
+        return None if self.arena is None else self.arena.take(n_units, rows_per_unit, C_total)
+
+    def gn_reset(self):
+        """Re-zero the arena and hand its tables out again (callers that reuse one _Aux for several forwards)."""
+        if self.arena is not None and self.arena.enabled:
+            self.arena.buf.zero_()
+            self.arena.off = 0
+
+
+class _GNArena:
+    """Zeroed int64 storage for the GroupNorm statistics of one forward (ops.GNStats tables, one per
+    norm), handed out in call order so that a captured CUDA graph sees the same addresses on every
+    replay; ONE fill kernel per forward zeroes all of it."""
+
+    def __init__(self, n_tables: int, max_units: int, enabled: bool = True):
+        self.enabled = enabled
+        per_table = max(ops.GNStats.numel(u) for u in range(1, max_units + 1)) if enabled else 0
+        self.buf = torch.zeros((n_tables * per_table,), dtype=torch.int64, device="cuda") if enabled else None
+        self.off = 0
+
+    def take(self, n_units: int, rows_per_unit: int, C_total):
+        if not self.enabled or C_total is None or not ops.GNStats.fusable(C_total):
+            return None
+        n = ops.GNStats.numel(n_units)
+        if self.off + n > self.buf.numel():
+            raise RuntimeError("GroupNorm statistics arena exhausted")
+        st = ops.GNStats(self.buf[self.off:self.off + n], n_units, rows_per_unit, C_total)
+        self.off += n
+        return st
 
 
 def _fold_ln(w, b, norm_w, norm_b):
@@ -361,12 +425,13 @@ class _Transformer:
                                                   self.pos2.w, self.pos2.b)
         return self._pos_cache[T]
 
-    def __call__(self, x, aux, g):
+    def __call__(self, x, aux, g, st_in=None, st_out=None):
         """x [M, C] rows ordered (b, t, site); aux.ctx holds every block's 1-token cross-attention
-        vector to_out(to_v(ehs[b])) (one batched launch per forward)."""
+        vector to_out(to_v(ehs[b])) (one batched launch per forward).  st_in / st_out: GroupNorm statistics
+        tables of x (from its producer) / of the norm that consumes the result (see _ResBlock.__call__)."""
         B, T, H, W = g
         S, F_ = H * W, B * T
-        a = ops.groupnorm(x, F_, S, self.norm.g, self.norm.b, 1e-6, False)
+        a = ops.groupnorm(x, F_, S, self.norm.g, self.norm.b, 1e-6, False, stats=st_in)
         h = ops.linear(a, self.proj_in.w, bias=self.proj_in.b)
         # --- BasicTransformerBlock (spatial)
         n = ops.layernorm(h)
@@ -401,7 +466,7 @@ class _Transformer:
         # ff(n) + hm, then AlphaBlender: a*h + (1-a)*(ff + hm)
         h = ops.linear(self.tff.up(n), self.tff.w2, bias=self.tff.b2, s_acc=1.0 - self.alpha,
                        res1=hm, s_res1=1.0 - self.alpha, res2=h, s_res2=self.alpha)
-        return ops.linear(h, self.proj_out.w, bias=self.proj_out.b, res1=x)
+        return ops.linear(h, self.proj_out.w, bias=self.proj_out.b, res1=x, gn=_gn(st_out))
 
 
 class _TimeEmbed:
@@ -580,7 +645,7 @@ class _PackedModel(torch.nn.Module):
         ids = added_time_ids.to(device="cuda", dtype=torch.float32).contiguous()
         return self.embed(ts, ids)  # [B, 4*C0] fp32
 
-    def _aux(self, emb, ehs, branch: Optional[int] = None):
+    def _aux(self, emb, ehs, branch: Optional[int] = None, n_units: int = 0):
         """All per-sample vectors of one forward in two batched launches:
         temb[b] = every time_emb_proj(silu(emb[b])); ctx[b] = every to_out(to_v(ehs[b])).
 
@@ -590,14 +655,14 @@ class _PackedModel(torch.nn.Module):
         pairs row (b, s) with context (b*S + s) % 2B of the whole batch (Appendix A.5)."""
         temb = ops.small_linear(emb, self.temb_w, self.temb_b, act_in=True)
         ctx = ops.small_linear(ehs, self.ctx_w, self.ctx_b)
+        arena = _GNArena(self._n_gn, n_units, enabled=GN_FUSED) if n_units else None
         if branch is None:
-            return SimpleNamespace(temb=temb, ctx=ctx, ctx_all=ctx, vB=ctx.shape[0], b0=0)
+            return _Aux(temb, ctx, arena=arena)
         Bl = emb.shape[0]
         if ehs.shape[0] != 2 * Bl:
             raise ValueError(f"branch-sharded forward needs the contexts of both CFG halves: got {ehs.shape[0]} rows "
                              f"for a local batch of {Bl}")
-        return SimpleNamespace(temb=temb, ctx=ctx[branch * Bl:(branch + 1) * Bl], ctx_all=ctx, vB=2 * Bl,
-                               b0=branch * Bl)
+        return _Aux(temb, ctx[branch * Bl:(branch + 1) * Bl], ctx_all=ctx, vB=2 * Bl, b0=branch * Bl, arena=arena)
 
     def _finish_pack(self, resblocks, transformers):
         tw, tb, off = [], [], 0
@@ -614,26 +679,51 @@ class _PackedModel(torch.nn.Module):
                 cw.append(ca.w); cb.append(ca.b); off += ca.C
                 ca.w = ca.b = None
         self.ctx_w, self.ctx_b = _w(torch.cat(cw)), _f(torch.cat(cb))
+        # statistics tables one forward can ask for: four per ResBlock (norm2, the two temporal norms, the
+        # consumer of its output), one per transformer output, conv_in / down- / upsamplers, the skip adds
+        self._n_gn = 4 * len(resblocks) + len(transformers) + 40
 
-    def _encode(self, x, aux, g):
-        """conv_in output -> (mid input, skip list, geometry list)."""
+    def _conv_in(self, inp64, aux, g):
+        """conv_in (ControlNet: + control_conv_in, one merged conv) with the statistics for the first norm1"""
         B, T, H, W = g
+        st = aux.gn_stats(B * T, H * W, self.cfg["block_out_channels"][0])
+        return ops.conv3x3(inp64, B * T, H, W, self.conv_in_w, bias=self.conv_in_b, gn=_gn(st)), st
+
+    def _encode(self, x, st, aux, g):
+        """conv_in output (+ its GroupNorm statistics) -> (mid input, its statistics, skip list, geometry list).
+        Every stage is handed the statistics table of the GroupNorm that consumes its output (None before a
+        downsampler, whose conv fills the table instead) so that no norm of the encoder needs a statistics pass."""
+        B, T, H, W = g
+        F_ = B * T
         skips, geoms = [x], [g]
         for res, att, ds in self.down:
             for j, r in enumerate(res):
-                x = r(x, aux, g)
+                last = j == len(res) - 1
+                HW = g[2] * g[3]
+                st_blk = None if (last and ds is not None) else aux.gn_stats(F_, HW, r.cout)
                 if att is not None:
-                    x = att[j](x, aux, g)
+                    st_a = aux.gn_stats(F_, HW, r.cout)
+                    x = r(x, aux, g, st_in=st, st_out=st_a)
+                    x = att[j](x, aux, g, st_in=st_a, st_out=st_blk)
+                else:
+                    x = r(x, aux, g, st_in=st, st_out=st_blk)
+                st = st_blk
                 skips.append(x); geoms.append(g)
             if ds is not None:
-                x = ops.conv3x3(x, B * T, g[2], g[3], ds.w, stride=2, bias=ds.b)
                 g = (B, T, g[2] // 2, g[3] // 2)
+                st = aux.gn_stats(F_, g[2] * g[3], x.shape[1])
+                x = ops.conv3x3(x, F_, g[2] * 2, g[3] * 2, ds.w, stride=2, bias=ds.b, gn=_gn(st))
                 skips.append(x); geoms.append(g)
-        return x, skips, geoms, g
+        return x, st, skips, geoms, g
 
-    def _mid(self, x, aux, g):
+    def _mid(self, x, st, aux, g, st_out=None):
         r0, a0, r1 = self.mid
-        return r1(a0(r0(x, aux, g), aux, g), aux, g)
+        F_, HW = g[0] * g[1], g[2] * g[3]
+        st_a = aux.gn_stats(F_, HW, r0.cout)
+        x = r0(x, aux, g, st_in=st, st_out=st_a)
+        st_r = aux.gn_stats(F_, HW, r0.cout)
+        x = a0(x, aux, g, st_in=st_a, st_out=st_r)
+        return r1(x, aux, g, st_in=st_r, st_out=st_out)
 
     def _all_blocks(self):
         res, att = [], []
@@ -694,10 +784,10 @@ class ControlNetModel(_PackedModel):
     def forward_rows(self, inp64, emb, ehs, g, conditioning_scale: float = 1.0, branch: Optional[int] = None):
         """inp64: [M, 64] padded channels-last input [sample(8) | control_cond(4) | 0]."""
         B, T, H, W = g
-        aux = self._aux(emb, ehs, branch)
-        x = ops.conv3x3(inp64, B * T, H, W, self.conv_in_w, bias=self.conv_in_b)
-        x, skips, geoms, gm = self._encode(x, aux, g)
-        x = self._mid(x, aux, gm)
+        aux = self._aux(emb, ehs, branch, n_units=B * T)
+        x, st = self._conv_in(inp64, aux, g)
+        x, st, skips, geoms, gm = self._encode(x, st, aux, g)
+        x = self._mid(x, st, aux, gm)
         res = [ops.linear(s, z.w, bias=z.b, s_acc=float(conditioning_scale)) for s, z in zip(skips, self.zero_convs)]
         mid = ops.linear(x, self.zero_mid.w, bias=self.zero_mid.b, s_acc=float(conditioning_scale))
         return res, mid, geoms, gm
@@ -783,28 +873,64 @@ class UNetSpatioTemporalConditionModel(_PackedModel):
                      branch: Optional[int] = None):
         """inp64 [M, 64] -> noise prediction rows [M, out_channels] fp32."""
         B, T, H, W = g
-        aux = self._aux(emb, ehs, branch)
-        x = ops.conv3x3(inp64, B * T, H, W, self.conv_in_w, bias=self.conv_in_b)
-        x, skips, geoms, gm = self._encode(x, aux, g)
+        aux = self._aux(emb, ehs, branch, n_units=B * T)
+        F_ = B * T
+        x, st = self._conv_in(inp64, aux, g)
+        x, st, skips, geoms, gm = self._encode(x, st, aux, g)
         if join is not None:
             join()  # the residuals come from another stream (DenoiseStep two-stream mode)
+        # Decoder ResBlock k (in execution order) normalises cat([x (cx[k] channels), skip k]): the stage before
+        # it accumulates the x half of table k at channel offset 0, the residual add (skip + r) the skip half at
+        # offset cx[k].  Without residuals a raw skip already fed an encoder norm (a second consumer, another group
+        # width): its half comes from one statistics-only pass of the same reduction, so that a zero residual and
+        # no residual give bit-identical results.
+        cx, c = [], skips[-1].shape[1]
+        for res, _, _ in self.up:
+            for r in res:
+                cx.append(c)
+                c = r.cout
+        nsk = len(skips)
+        st_cat = [None] * (nsk + 1)  # k-th pop <-> skips[nsk - 1 - k]; [nsk]: no further norm1
+        for i, (s_, gg) in enumerate(zip(skips, geoms)):
+            st_cat[nsk - 1 - i] = aux.gn_stats(F_, gg[2] * gg[3], cx[nsk - 1 - i] + s_.shape[1])
         if down_res is not None:  # unet_spatio_temporal_condition.py:119-127
-            skips = [ops.axpby(s, r) for s, r in zip(skips, down_res)]
-        x = self._mid(x, aux, gm)
+            skips = [ops.axpby(s_, r_, gn=_gn(st_cat[nsk - 1 - i], cx[nsk - 1 - i]))
+                     for i, (s_, r_) in enumerate(zip(skips, down_res))]
+        else:
+            for i, s_ in enumerate(skips):
+                if st_cat[nsk - 1 - i] is not None:
+                    ops.gn_stats_of(s_, (st_cat[nsk - 1 - i], cx[nsk - 1 - i]))
+        x = self._mid(x, st, aux, gm)
         if mid_res is not None:  # :136-137
-            x = ops.axpby(x, mid_res)
+            x = ops.axpby(x, mid_res, gn=_gn(st_cat[0], 0))
+        elif st_cat[0] is not None:
+            ops.gn_stats_of(x, (st_cat[0], 0))  # (same reduction as the residual add: see above)
         g = gm
-        for res, att, us in self.up:
+        k = 0
+        st = None
+        for i, (res, att, us) in enumerate(self.up):
+            HW = g[2] * g[3]
             for j, r in enumerate(res):
                 skip = skips.pop()
-                x = r(x, aux, g, x1=skip)
+                if j < len(res) - 1:
+                    st_stage = st_cat[k + 1]        # the next ResBlock of this block
+                elif us is not None:
+                    st_stage = None                 # the upsampler's convs fill table k + 1
+                else:
+                    st_stage = aux.gn_stats(F_, HW, r.cout)  # conv_norm_out
                 if att is not None:
-                    x = att[j](x, aux, g)
+                    st_a = aux.gn_stats(F_, HW, r.cout)
+                    x = r(x, aux, g, x1=skip, st_in=st_cat[k], st_out=st_a)
+                    x = att[j](x, aux, g, st_in=st_a, st_out=st_stage)
+                else:
+                    x = r(x, aux, g, x1=skip, st_in=st_cat[k], st_out=st_stage)
+                st = st_stage
+                k += 1
             if us is not None:
                 # Upsample2D: nearest 2x + 3x3 conv, fused as four 2x2 phase convs of the low-res frame
-                x = ops.upsample2x_conv3x3(x, B * T, g[2], g[3], us.w, bias=us.b)
+                x = ops.upsample2x_conv3x3(x, F_, g[2], g[3], us.w, bias=us.b, gn=_gn(st_cat[k]))
                 g = (B, T, g[2] * 2, g[3] * 2)
-        a = ops.groupnorm(x, B * T, g[2] * g[3], self.norm_out.g, self.norm_out.b, 1e-5, True)
+        a = ops.groupnorm(x, B * T, g[2] * g[3], self.norm_out.g, self.norm_out.b, 1e-5, True, stats=st)
         oc = self.cfg["out_channels"]
         if out_f32 is None:
             out_f32 = torch.empty((x.shape[0], oc), device="cuda", dtype=torch.float32)

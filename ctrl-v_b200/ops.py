@@ -63,9 +63,54 @@ def _req(t: torch.Tensor, dtype, name: str):
         raise ValueError(f"{name}: expected a CUDA tensor")
 
 
+class GNStats:
+    """(sum, sum of squares) accumulators of ONE nn.GroupNorm(32, C_total), filled by the launches that
+    produce its input (igemm epilogue `gn=`, `axpby(gn=)`) so that the norm runs without a statistics
+    pass: int64 fixed point [rep][n_units][32][2] (value * 2^16; integer atomics, hence order-independent and
+    bit-reproducible), replicated `rep` times so that the producers' atomics do not all land on the same few
+    L2 lines when there are only a few units.  `buf` must be zero before the first producer runs."""
+
+    __slots__ = ("buf", "n_units", "rows_per_unit", "C", "cg", "rep")
+
+    def __init__(self, buf: torch.Tensor, n_units: int, rows_per_unit: int, C_total: int):
+        assert buf.dtype == torch.int64 and buf.is_contiguous() and buf.numel() == self.numel(n_units)
+        assert C_total % 32 == 0
+        self.buf, self.n_units, self.rows_per_unit, self.C, self.cg = buf, n_units, rows_per_unit, C_total, C_total // 32
+        self.rep = self.replicas(n_units)
+
+    @staticmethod
+    def replicas(n_units: int) -> int:
+        """power of two, >= 128 table rows in total"""
+        r = 1
+        while r * n_units < 128:
+            r *= 2
+        return r
+
+    @classmethod
+    def numel(cls, n_units: int) -> int:
+        return cls.replicas(n_units) * n_units * 64
+
+    def total(self) -> torch.Tensor:
+        """[n_units, 32, 2] float64 (sum, sum of squares): the replicas added up (test / debugging helper)"""
+        return self.buf.view(self.rep, self.n_units, 32, 2).sum(0).double() / 65536.0
+
+    @staticmethod
+    def fusable(C_total: int) -> bool:
+        """The epilogue splits an aligned 8-column piece between at most two groups (cg = 4, 6 or >= 8) and
+        the residual-add kernel reduces channel pairs (even cg)."""
+        cg = C_total // 32
+        return C_total % 32 == 0 and cg % 2 == 0 and cg >= 4
+
+
 def make_ep(out=None, out_f32=None, bias=None, rowbias=None, rb_mode=0, rb_div=1, rb_mod=1, rb_B=1,
-            geglu=False, s_acc=1.0, res1=None, s_res1=1.0, res2=None, s_res2=1.0, n_store=0) -> Epilogue:
+            geglu=False, s_acc=1.0, res1=None, s_res1=1.0, res2=None, s_res2=1.0, n_store=0, gn=None) -> Epilogue:
+    """gn = (GNStats, c_off): also accumulate the statistics of `out` for the GroupNorm that consumes it,
+    `out` being channels c_off.. of that norm's (possibly concatenated) input."""
     ep = Epilogue()
+    if gn is not None:
+        st, c_off = gn
+        ep.gn_sums, ep.gn_rows_per_unit, ep.gn_cg, ep.gn_c_off = st.buf.data_ptr(), st.rows_per_unit, st.cg, c_off
+        ep.gn_units, ep.gn_rep = st.n_units, st.rep
     if bias is not None:
         _req(bias, torch.float32, "bias")
     ep.bias = _p(bias)
@@ -105,7 +150,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
     assert w.shape[1] == K and w.is_contiguous() and a.stride(1) == 1
     kw = _alloc_out(M, N, kw.get("geglu", False), kw)
     ep = make_ep(**kw)
-    tok = _prof("linear", (M, K, N, bool(kw.get("geglu")), kw.get("res1") is not None, kw.get("res2") is not None), 2.0 * M * K * N)
+    tok = _prof("linear", (M, K, N, bool(kw.get("geglu")), kw.get("res1") is not None, kw.get("res2") is not None, kw.get("gn") is not None), 2.0 * M * K * N)
     check(lib().ctrlv_linear(a.data_ptr(), a.stride(0), M, K, w.data_ptr(), N, C.byref(ep), _stream()),
           "ctrlv_linear")
     _prof_end(tok)
@@ -131,7 +176,7 @@ def conv3x3(x: torch.Tensor, frames: int, H: int, W: int, w: torch.Tensor, strid
     Mo = frames * (H // stride) * (W // stride)
     kw = _alloc_out(Mo, N, kw.get("geglu", False), kw)
     ep = make_ep(**kw)
-    tok = _prof("conv3x3", (frames, H, W, stride, C0 + C1, SC0 + SC1, N), 2.0 * Mo * w.shape[1] * N)
+    tok = _prof("conv3x3", (frames, H, W, stride, C0 + C1, SC0 + SC1, N, kw.get("gn") is not None), 2.0 * Mo * w.shape[1] * N)
     check(lib().ctrlv_conv3x3(x.data_ptr(), C0, _p(src1), C1, frames, H, W, stride, _p(sc0), SC0,
                               _p(sc1), SC1, w.data_ptr(), N, C.byref(ep), _stream()), "ctrlv_conv3x3")
     _prof_end(tok)
@@ -147,7 +192,7 @@ def conv_t3(x: torch.Tensor, B: int, T: int, HW: int, w: torch.Tensor, **kw) -> 
     assert w.shape[1] == 3 * Cc and x.shape[0] == B * T * HW
     kw = _alloc_out(B * T * HW, N, kw.get("geglu", False), kw)
     ep = make_ep(**kw)
-    tok = _prof("conv_t3", (B, T, HW, Cc, N), 2.0 * B * T * HW * 3 * Cc * N)
+    tok = _prof("conv_t3", (B, T, HW, Cc, N, kw.get("gn") is not None), 2.0 * B * T * HW * 3 * Cc * N)
     check(lib().ctrlv_conv_t3(x.data_ptr(), Cc, B, T, HW, w.data_ptr(), N, C.byref(ep), _stream()),
           "ctrlv_conv_t3")
     _prof_end(tok)
@@ -169,8 +214,10 @@ def _gn_workspace(n_units: int) -> torch.Tensor:
 
 def groupnorm(x: torch.Tensor, n_units: int, rows_per_unit: int, gamma: torch.Tensor, beta: torch.Tensor,
               eps: float, silu: bool, src1: Optional[torch.Tensor] = None,
-              out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """GroupNorm(32) [+SiLU] over statistics units of `rows_per_unit` rows; x (| src1) -> out."""
+              out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None,
+              stats: Optional[GNStats] = None) -> torch.Tensor:
+    """GroupNorm(32) [+SiLU] over statistics units of `rows_per_unit` rows; x (| src1) -> out.
+    `stats`: the statistics were accumulated by the producers of x (| src1): normalise only."""
     _req(x, BF16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
     assert x.is_contiguous() and x.shape[0] == n_units * rows_per_unit
     C0 = x.shape[1]
@@ -181,6 +228,14 @@ def groupnorm(x: torch.Tensor, n_units: int, rows_per_unit: int, gamma: torch.Te
     assert gamma.numel() == C0 + C1 and beta.numel() == C0 + C1
     if out is None:
         out = torch.empty((x.shape[0], C0 + C1), dtype=BF16, device="cuda")
+    if stats is not None:
+        assert (stats.n_units, stats.rows_per_unit, stats.C) == (n_units, rows_per_unit, C0 + C1), "GNStats mismatch"
+        tok = _prof("groupnorm_apply", (n_units, rows_per_unit, C0 + C1), nbytes=4.0 * x.shape[0] * (C0 + C1))
+        check(lib().ctrlv_groupnorm_apply(x.data_ptr(), C0, _p(src1), C1, n_units, rows_per_unit, gamma.data_ptr(),
+                                          beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(),
+                                          stats.buf.data_ptr(), stats.rep, _stream()), "ctrlv_groupnorm_apply")
+        _prof_end(tok)
+        return out
     if ws is None:
         ws = _gn_workspace(n_units)
     tok = _prof("groupnorm", (n_units, rows_per_unit, C0 + C1), nbytes=4.0 * x.shape[0] * (C0 + C1))
@@ -306,13 +361,33 @@ def upsample2x(x: torch.Tensor, frames: int, H: int, W: int) -> torch.Tensor:
 
 
 def axpby(x: torch.Tensor, y: torch.Tensor, a: float = 1.0, b: float = 1.0,
-          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+          out: Optional[torch.Tensor] = None, gn=None) -> torch.Tensor:
+    """out = a*x + b*y (bf16); gn = (GNStats, c_off) also accumulates the statistics of `out` (rows [M, C])."""
     _req(x, BF16, "x"); _req(y, BF16, "y")
     assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
     if out is None:
         out = torch.empty_like(x)
+    if gn is not None:
+        st, c_off = gn
+        M, Cc = x.shape
+        assert M == st.n_units * st.rows_per_unit
+        check(lib().ctrlv_axpby_gn(x.data_ptr(), y.data_ptr(), a, b, M, Cc, out.data_ptr(), st.buf.data_ptr(),
+                                   st.rows_per_unit, st.cg, c_off, st.rep, _stream()), "ctrlv_axpby_gn")
+        return out
     check(lib().ctrlv_axpby(x.data_ptr(), y.data_ptr(), a, b, x.numel(), out.data_ptr(), _stream()), "ctrlv_axpby")
     return out
+
+
+def gn_stats_of(x: torch.Tensor, gn) -> None:
+    """Accumulate the GroupNorm statistics of x [M, C] itself into gn = (GNStats, c_off) — the same reduction
+    as `axpby(gn=)`, for a tensor whose producer could not (a skip connection with two consumers)."""
+    _req(x, BF16, "x")
+    assert x.is_contiguous()
+    st, c_off = gn
+    M, Cc = x.shape
+    assert M == st.n_units * st.rows_per_unit
+    check(lib().ctrlv_axpby_gn(x.data_ptr(), None, 1.0, 0.0, M, Cc, None, st.buf.data_ptr(), st.rows_per_unit, st.cg,
+                               c_off, st.rep, _stream()), "ctrlv_axpby_gn")
 
 
 def nchw_to_nhwc(src: torch.Tensor, out: torch.Tensor, c_off: int = 0) -> torch.Tensor:
@@ -437,7 +512,8 @@ def pack_upconv3x3(w: torch.Tensor, device="cuda", dtype=BF16) -> torch.Tensor:
 
 
 def upsample2x_conv3x3(x: torch.Tensor, frames: int, H: int, W: int, wp: torch.Tensor,
-                       bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                       gn=None) -> torch.Tensor:
     """x [frames*H*W, C] -> conv3x3(nearest2x(x)) as rows [frames*2H*2W, N]; wp from pack_upconv3x3."""
     _req(x, BF16, "x"); _req(wp, BF16, "wp")
     assert x.is_contiguous() and wp.is_contiguous() and x.shape[0] == frames * H * W
@@ -447,7 +523,7 @@ def upsample2x_conv3x3(x: torch.Tensor, frames: int, H: int, W: int, wp: torch.T
     if out is None:
         out = torch.empty((frames * 4 * H * W, N), dtype=BF16, device="cuda")
     tok = _prof("upconv3x3", (frames, H, W, C0, N), 2.0 * frames * H * W * 16 * C0 * N)
-    ep = make_ep(out=out, bias=bias)
+    ep = make_ep(out=out, bias=bias, gn=gn)
     check(lib().ctrlv_upsample2x_conv3x3(x.data_ptr(), C0, frames, H, W, wp.data_ptr(), N, C.byref(ep), _stream()),
           "ctrlv_upsample2x_conv3x3")
     _prof_end(tok)

@@ -74,6 +74,17 @@ typedef struct ctrlv_epilogue {
   float* out_f32;    /* fp32 [M][ld_out_f32] or NULL */
   int32_t ld_out_f32;
   int32_t n_store;   /* number of valid output columns (0 = all) */
+  /* Optional: statistics for the nn.GroupNorm(32) that consumes `out` (diffusers ResnetBlock2D /
+   * TemporalResnetBlock norm1/norm2, TransformerSpatioTemporalModel.norm, conv_norm_out), accumulated
+   * by this launch's epilogue so that the norm needs no statistics pass of its own:
+   *   gn_sums[r][m / gn_rows_per_unit][(gn_c_off + n) / gn_cg] += (sum, sum of squares) of the stored bf16 value
+   * as int64 fixed point (value * 2^16, two's complement) — see ctrlv_groupnorm_apply.  r is one of gn_rep
+   * replicas of the table (a power of two; the consumer adds them up): with few units a single table is an L2
+   * hot spot for the whole chip.  The caller zeroes gn_sums before the first producer; several producers
+   * (skip-concat halves, the four upsample phases) may add into the same table.  Needs gn_cg in {4, 6, >= 7},
+   * gn_c_off % 8 == 0, a bf16 `out`, no GEGLU, n_store == 0. */
+  void* gn_sums;     /* int64 [gn_rep][gn_units][32][2] or NULL */
+  int32_t gn_rows_per_unit, gn_cg, gn_c_off, gn_units, gn_rep;
 } ctrlv_epilogue;
 
 /* One operand source of the implicit GEMM: a channels-last view [Z][Y][X][C] with element
@@ -152,6 +163,21 @@ int64_t ctrlv_groupnorm_workspace(int32_t n_units);
 int ctrlv_groupnorm(const void* src0, int32_t C0, const void* src1, int32_t C1, int32_t n_units,
                     int32_t rows_per_unit, const float* gamma, const float* beta, float eps,
                     int32_t silu, void* out, void* workspace, void* stream);
+
+/* The normalise(+SiLU) half of ctrlv_groupnorm for an input whose statistics were accumulated by its
+ * producers (ctrlv_epilogue.gn_sums / ctrlv_axpby_gn): sums = int64 [n_rep][n_units][32][2] fixed point
+ * (sum, sum of squares) * 2^16, the n_rep replicas being added up.  Same arithmetic as ctrlv_groupnorm from the statistics on. */
+int ctrlv_groupnorm_apply(const void* src0, int32_t C0, const void* src1, int32_t C1, int32_t n_units,
+                          int32_t rows_per_unit, const float* gamma, const float* beta, float eps,
+                          int32_t silu, void* out, const void* sums, int32_t n_rep, void* stream);
+
+/* out = a*x + b*y on bf16 rows [rows][C] (the ControlNet residual add into a skip connection,
+ * unet_spatio_temporal_condition.py:119-127,136-137) that also accumulates the GroupNorm statistics of
+ * `out` for its consumer, exactly like ctrlv_epilogue.gn_sums: group (c_off + c) / cg of unit row /
+ * rows_per_unit.  y == out == NULL: only the statistics of x (a skip connection used as is: the
+ * same reduction, so a zero residual gives bit-identical results to no residual). */
+int ctrlv_axpby_gn(const void* x, const void* y, float a, float b, int64_t rows, int32_t C, void* out,
+                   void* gn_sums, int32_t rows_per_unit, int32_t cg, int32_t c_off, int32_t n_rep, void* stream);
 
 /* nn.LayerNorm(C, eps) over rows, with an optional fp32 row-bias added first
  * (x + rowbias[(m / rb_div) % rb_mod]): the frame-position embedding of

@@ -18,11 +18,11 @@ ops.profile_flush()
 tot = sum(v[1] for v in ops.PROFILE.values()) / 3
 print(f"sum of timed ops: {tot:.2f} ms/step")
 byop = {}
-for (op, key), (n, ms, fl) in ops.PROFILE.items():
+for (op, key), (n, ms, fl, _by) in ops.PROFILE.items():
     r = byop.setdefault(op, [0, 0.0, 0.0]); r[0] += n / 3; r[1] += ms / 3; r[2] += fl / 3
 for op, (n, ms, fl) in sorted(byop.items(), key=lambda kv: -kv[1][1]):
     print(f"{op:14s} n={n:5.0f} {ms:8.3f} ms  {fl/ms/1e9 if fl else 0:8.1f} TFLOP/s")
 print("--- per shape (sorted by time)")
-for (op, key), (n, ms, fl) in sorted(ops.PROFILE.items(), key=lambda kv: -kv[1][1]):
+for (op, key), (n, ms, fl, _by) in sorted(ops.PROFILE.items(), key=lambda kv: -kv[1][1]):
     n /= 3; ms /= 3; fl /= 3
     print(f"{ms:8.3f} ms n={n:4.0f} avg={1e3*ms/n:8.1f} us {fl/ms/1e9 if fl else 0:7.1f} TF  {op} {key}")

@@ -192,6 +192,122 @@ def test_groupnorm(ops, units, rows, C0, C1, silu, eps):
     assert rel(out, ref.permute(0, 2, 1).reshape(-1, C)) < TOL_BF16
 
 
+def _gn_table(ops, units, rows, C_total):
+    return ops.GNStats(torch.zeros(ops.GNStats.numel(units), dtype=torch.int64, device="cuda"), units, rows, C_total)
+
+
+def _gn_expected(y, units, rows, C_total, c_off):
+    """(sum, sum of squares) per (unit, group) of the STORED bf16 tensor y [units*rows, C] occupying channels
+    c_off.. of a GroupNorm(32, C_total) input (float64 on the GPU), and the same sums of magnitudes."""
+    cg = C_total // 32
+    C = y.shape[1]
+    grp = (torch.arange(C, device=y.device) + c_off) // cg
+    onehot = torch.zeros(C, 32, dtype=torch.float64, device=y.device)
+    onehot[torch.arange(C, device=y.device), grp] = 1.0
+    yd = y.double().view(units, rows, C)
+    exp = torch.stack([yd.sum(1) @ onehot, (yd * yd).sum(1) @ onehot], -1)  # [units, 32, 2]
+    mag = torch.stack([yd.abs().sum(1) @ onehot, (yd * yd).sum(1) @ onehot], -1)
+    return exp, mag
+
+
+def _gn_check(st, expected, n_values):
+    """fp32 partial sums of <= 256 values each (relative 2^-22 per add), every partial rounded once to 2^-16."""
+    exp, mag = expected
+    got = st.total()
+    tol = 4e-6 * mag + (n_values / 32.0 + 2.0) * 2.0 ** -16
+    assert torch.all((got - exp).abs() <= tol), (float((got - exp).abs().max()), float(tol.min()))
+
+
+@pytest.mark.parametrize("kind,geom,C,N,C_total,c_off,temporal", [
+    ("conv3x3", (4, 16, 16), 64, 320, 320, 0, False),       # 10 channels per group: pieces straddle groups
+    ("conv3x3", (28, 5, 8), 64, 128, 128, 0, False),        # 40-row frames: a warp's 32 rows straddle units
+    ("conv3x3", (6, 8, 8), 64, 256, 256, 0, True),          # statistics across frames (unit = clip of 3 frames)
+    ("conv3x3_s2", (3, 16, 32), 64, 256, 256, 0, False),
+    ("linear", (2, 24, 40), 128, 640, 1920, 1280, False),   # skip half of a 1920-wide concat norm (60 per group)
+    ("linear_res", (28, 40, 1), 64, 1280, 1280, 0, False),
+    ("conv_t3", (2, 14, 160), 64, 192, 192, 0, True),
+    ("upconv", (2, 5, 8), 64, 128, 384, 0, False),          # four phase launches add into one table
+])
+def test_groupnorm_statistics_from_the_producer_epilogue(ops, kind, geom, C, N, C_total, c_off, temporal):
+    dev = "cuda"
+    F_, H, W = geom
+    x = torch.randn(F_ * H * W, C, device=dev).to(BF)
+    bias = torch.randn(N, device=dev)
+    if kind.startswith("conv3x3"):
+        stride = 2 if kind.endswith("s2") else 1
+        w = (torch.randn(N, 9 * C, device=dev) / (9 * C) ** 0.5).to(BF)
+        rows_frame = (H // stride) * (W // stride)
+        run = lambda gn: ops.conv3x3(x, F_, H, W, w, stride=stride, bias=bias, gn=gn)
+    elif kind.startswith("linear"):
+        w = (torch.randn(N, C, device=dev) / C ** 0.5).to(BF)
+        res = torch.randn(F_ * H * W, N, device=dev).to(BF) if kind.endswith("res") else None
+        rows_frame = H * W
+        run = lambda gn: ops.linear(x, w, bias=bias, res1=res, gn=gn)
+    elif kind == "conv_t3":
+        w = (torch.randn(N, 3 * C, device=dev) / (3 * C) ** 0.5).to(BF)
+        rows_frame = W  # geom = (B, T, HW)
+        run = lambda gn: ops.conv_t3(x, F_, H, W, w, bias=bias, gn=gn)
+    else:
+        wp = ops.pack_upconv3x3(torch.randn(N, C, 3, 3, device=dev) / (9 * C) ** 0.5)
+        rows_frame = 4 * H * W
+        run = lambda gn: ops.upsample2x_conv3x3(x, F_, H, W, wp, bias=bias, gn=gn)
+    if kind == "conv_t3":
+        units, rows = F_, H * W
+    elif temporal:
+        units, rows = F_ // 3, 3 * rows_frame
+    else:
+        units, rows = F_, rows_frame
+    plain = run(None)
+    st = _gn_table(ops, units, rows, C_total)
+    y = run((st, c_off))
+    st2 = _gn_table(ops, units, rows, C_total)
+    run((st2, c_off))
+    torch.cuda.synchronize()
+    assert torch.equal(y, plain)                 # the statistics do not disturb the output
+    assert torch.equal(st.buf.view(st.rep, -1).sum(0), st2.buf.view(st.rep, -1).sum(0))  # integer sums: bit-reproducible
+    _gn_check(st, _gn_expected(y, units, rows, C_total, c_off), rows * (C_total // 32))
+
+
+@pytest.mark.parametrize("units,rows,C,C_total,c_off", [(28, 160, 1280, 1920, 640), (3, 2560, 320, 640, 320), (5, 7, 64, 128, 64)])
+def test_axpby_with_groupnorm_statistics(ops, units, rows, C, C_total, c_off):
+    dev = "cuda"
+    x = torch.randn(units * rows, C, device=dev).to(BF)
+    r = (torch.randn(units * rows, C, device=dev) * 0.3).to(BF)
+    st = _gn_table(ops, units, rows, C_total)
+    y = ops.axpby(x, r, gn=(st, c_off))
+    torch.cuda.synchronize()
+    assert torch.equal(y, ops.axpby(x, r))
+    _gn_check(st, _gn_expected(y, units, rows, C_total, c_off), rows * (C_total // 32))
+
+
+@pytest.mark.parametrize("F_,H,W,C0,C1,silu", [(28, 10, 16, 320, 0, True), (6, 5, 8, 1280, 640, True), (4, 16, 16, 128, 0, False)])
+def test_groupnorm_from_producer_statistics_equals_two_pass(ops, F_, H, W, C0, C1, silu):
+    """conv -> (residual add) -> GroupNorm with the statistics taken from the producers' epilogues agrees with
+    the two-pass GroupNorm of the same stored tensors (and with torch), and is bit-reproducible."""
+    dev = "cuda"
+    HW, C = H * W, C0 + C1
+    xin = torch.randn(F_ * HW, 64, device=dev).to(BF)
+    w = (torch.randn(C0, 9 * 64, device=dev) / 24.0).to(BF)
+    g = torch.randn(C, device=dev); b = torch.randn(C, device=dev)
+    s_ = torch.randn(F_ * HW, C1, device=dev).to(BF) if C1 else None
+    outs = []
+    for _ in range(2):
+        st = _gn_table(ops, F_, HW, C)
+        y0 = ops.conv3x3(xin, F_, H, W, w, gn=(st, 0))
+        y1 = ops.axpby(s_, s_, 0.5, 0.25, gn=(st, C0)) if C1 else None
+        outs.append((ops.groupnorm(y0, F_, HW, g, b, 1e-6, silu, src1=y1, stats=st), y0, y1))
+    torch.cuda.synchronize()
+    (fused, y0, y1), (fused2, _, _) = outs
+    assert torch.equal(fused, fused2)
+    two_pass = ops.groupnorm(y0, F_, HW, g, b, 1e-6, silu, src1=y1)
+    assert rel(fused, two_pass) < 2e-3
+    x = torch.cat([y0, y1], 1) if C1 else y0
+    ref = F.group_norm(x.float().view(F_, HW, C).permute(0, 2, 1), 32, g, b, 1e-6)
+    if silu:
+        ref = F.silu(ref)
+    assert rel(fused, ref.permute(0, 2, 1).reshape(-1, C)) < TOL_BF16
+
+
 @pytest.mark.parametrize("M,C,rb", [(4096, 320, False), (1120, 1280, False), (14 * 2 * 24, 64, True), (14 * 40, 640, True), (77, 128, False)])
 def test_layernorm(ops, M, C, rb):
     dev = "cuda"
