@@ -92,6 +92,8 @@ SIGNATURES = {
     "ctrlv_igemm_plan": (_I, [C.POINTER(IgemmDesc), _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ctrlv_igemm_override": (_I, [_I, _I, _I]),
     "ctrlv_linear": (_I, [_P, _L, _I, _I, _P, _I, C.POINTER(Epilogue), _P]),
+    "ctrlv_feedforward": (_I, [_P, _L, _I, _I, _P, _P, _P, C.POINTER(Epilogue), _P]),
+    "ctrlv_feedforward_override": (_I, [_I]),
     "ctrlv_conv3x3": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I,
                            C.POINTER(Epilogue), _P]),
     "ctrlv_conv_t3": (_I, [_P, _I, _I, _I, _I, _P, _I, C.POINTER(Epilogue), _P]),

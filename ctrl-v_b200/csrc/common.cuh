@@ -325,6 +325,17 @@ __device__ __forceinline__ void umma_ss_cg2(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
+// D[tmem, both CTAs] (+)= A[tmem, both CTAs] * B^T: each CTA's TMEM lanes hold its 128 rows of A and of D
+__device__ __forceinline__ void umma_ts_cg2(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // UMMA shared-memory matrix descriptor (64 bit), sm_100:
 //   [0,14)  start address >> 4          [16,30) leading byte offset >> 4
 //   [32,46) stride byte offset >> 4     [46,48) version = 1

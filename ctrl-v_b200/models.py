@@ -308,6 +308,11 @@ def _gn(st, c_off: int = 0):
 # GroupNorm statistics from the producers' epilogues (True) or from gn_stats_kernel passes (False: the
 # round-1 path, kept for A/B measurements and as the parity cross-check of the fused statistics)
 GN_FUSED = os.environ.get("CTRLV_GN_FUSED", "1") != "0"
+# FeedForward as one fused launch where the width allows it (True) or as two igemm launches (False: A/B runs)
+FF_FUSED = os.environ.get("CTRLV_FF_FUSED", "1") != "0"
+if os.environ.get("CTRLV_FF_CG"):  # A/B runs: force single CTAs (1) or CTA pairs (2) in the fused FeedForward
+    from . import _lib as _l
+    _l.check(_l.load().ctrlv_feedforward_override(int(os.environ["CTRLV_FF_CG"])))
 
 
 class _Aux:
@@ -374,8 +379,13 @@ class _FF:
         self.w1, self.b1 = _w(w1), _f(b1)
         self.w2, self.b2 = _w(sd[pfx + ".net.2.weight"]), _f(sd[pfx + ".net.2.bias"])
 
-    def up(self, n):
-        return ops.linear(n, self.w1, bias=self.b1, geglu=True)
+    def __call__(self, n, **kw):
+        """GEGLU up-projection + down-projection with the output epilogue `kw` (res1, rowbias, ...): one fused
+        launch where the width allows it (the 4C-wide intermediate stays in tensor memory), two igemm launches
+        otherwise."""
+        if FF_FUSED and n.shape[1] <= ops.FF_FUSED_MAX_C:
+            return ops.feedforward(n, self.w1, self.b1, self.w2, bias=self.b2, **kw)
+        return ops.linear(ops.linear(n, self.w1, bias=self.b1, geglu=True), self.w2, bias=self.b2, **kw)
 
 
 class _SelfAttn:
@@ -440,12 +450,11 @@ class _Transformer:
         ctx = aux.ctx[:, self.attn2.off:self.attn2.off + self.C]
         h = ops.linear(att, self.attn1.out.w, bias=self.attn1.out.b, rowbias=ctx, rb_mode=1, rb_div=T * S, res1=h)
         n = ops.layernorm(h)
-        h = ops.linear(self.ff.up(n), self.ff.w2, bias=self.ff.b2, res1=h)
+        h = self.ff(n, res1=h)
         # --- TemporalBasicTransformerBlock on h + pos[t]; sequences are the T frames of a site
         pos = self.pos_emb(T)
         n = ops.layernorm(h, rowbias=pos, rb_div=S, rb_mod=T)
-        hm = ops.linear(self.tff_in.up(n), self.tff_in.w2, bias=self.tff_in.b2, res1=h,
-                        rowbias=pos, rb_mode=2, rb_div=S, rb_mod=T)
+        hm = self.tff_in(n, res1=h, rowbias=pos, rb_mode=2, rb_div=S, rb_mod=T)
         n = ops.layernorm(hm)
         qkv = ops.linear(n, self.tattn1.wqkv, bias=self.tattn1.bqkv)
         att = ops.attn_temporal(qkv, B, T, S, self.heads)
@@ -464,8 +473,7 @@ class _Transformer:
         hm = ops.linear(att, self.tattn1.out.w, bias=self.tattn1.out.b, rowbias=ctx_t, res1=hm, **kw)
         n = ops.layernorm(hm)
         # ff(n) + hm, then AlphaBlender: a*h + (1-a)*(ff + hm)
-        h = ops.linear(self.tff.up(n), self.tff.w2, bias=self.tff.b2, s_acc=1.0 - self.alpha,
-                       res1=hm, s_res1=1.0 - self.alpha, res2=h, s_res2=self.alpha)
+        h = self.tff(n, s_acc=1.0 - self.alpha, res1=hm, s_res1=1.0 - self.alpha, res2=h, s_res2=self.alpha)
         return ops.linear(h, self.proj_out.w, bias=self.proj_out.b, res1=x, gn=_gn(st_out))
 
 

@@ -157,6 +157,25 @@ def linear(a: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
     return kw["out"] if kw.get("out") is not None else kw["out_f32"]
 
 
+FF_FUSED_MAX_C = 320  # ctrlv_feedforward keeps D [128 x C], S [128 x 128] and H [128 x 64] in the 512 TMEM columns
+
+
+def feedforward(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, **kw) -> torch.Tensor:
+    """out = epilogue(GEGLU(x @ w1^T + b1) @ w2^T) in ONE launch (C <= 320); w1 / b1 with interleaved
+    (value, gate) rows; kw = the output epilogue (bias = b2, rowbias, s_acc, res1, res2, out)."""
+    _req(x, BF16, "x"); _req(w1, BF16, "w1"); _req(w2, BF16, "w2"); _req(b1, torch.float32, "b1")
+    M, Cc = x.shape
+    assert x.stride(1) == 1 and w1.is_contiguous() and w2.is_contiguous()
+    assert tuple(w1.shape) == (8 * Cc, Cc) and tuple(w2.shape) == (Cc, 4 * Cc) and b1.numel() == 8 * Cc
+    kw = _alloc_out(M, Cc, False, kw)
+    ep = make_ep(**kw)
+    tok = _prof("feedforward", (M, Cc, kw.get("res1") is not None, kw.get("res2") is not None), 2.0 * M * Cc * 12 * Cc)
+    check(lib().ctrlv_feedforward(x.data_ptr(), x.stride(0), M, Cc, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                  C.byref(ep), _stream()), "ctrlv_feedforward")
+    _prof_end(tok)
+    return kw["out"]
+
+
 def conv3x3(x: torch.Tensor, frames: int, H: int, W: int, w: torch.Tensor, stride: int = 1,
             src1: Optional[torch.Tensor] = None, sc0: Optional[torch.Tensor] = None,
             sc1: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:

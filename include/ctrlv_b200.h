@@ -138,6 +138,19 @@ int ctrlv_igemm_override(int32_t bn, int32_t cta_group, int32_t stages);
 int ctrlv_linear(const void* A, int64_t lda, int32_t M, int32_t K, const void* W, int32_t N,
                  const ctrlv_epilogue* ep, void* stream);
 
+/* diffusers FeedForward(dim = C, activation "geglu", mult 4) of BasicTransformerBlock.ff and
+ * TemporalBasicTransformerBlock.ff_in / .ff as ONE launch for C <= 320 (level 0 of the SVD UNet):
+ *     out = s_acc * (GEGLU(x W1^T + b1) W2^T + bias + rowbias[ridx(m)]) + s_res1 * res1 + s_res2 * res2
+ * x [M][ldx] bf16 (C columns used); W1 [8C][C] with the GEGLU (value, gate) rows interleaved, b1 [8C] fp32
+ * likewise; W2 [C][4C]; `ep` is the output epilogue (bias = b2 [C], rowbias, s_acc, res1, res2, bf16 out with
+ * 32-byte aligned rows).  The [M][4C] intermediate stays in tensor memory (see csrc/ff.cu).  Same result as
+ * ctrlv_linear(geglu) followed by ctrlv_linear up to the bf16 rounding of the intermediate (identical here:
+ * the hidden activations are rounded to bf16 before the second contraction in both forms). */
+int ctrlv_feedforward(const void* x, int64_t ldx, int32_t M, int32_t C, const void* W1, const float* b1,
+                      const void* W2, const ctrlv_epilogue* ep, void* stream);
+/* Tuning / test hook (process-global): force single CTAs (1) or CTA pairs (2) in ctrlv_feedforward; 0 = automatic. */
+int ctrlv_feedforward_override(int32_t cta_group);
+
 /* nn.Conv2d 3x3, padding 1, stride 1 or 2 (ResnetBlock2D.conv1/conv2, Downsample2D,
  * Upsample2D.conv, conv_in, conv_out) on channels-last frames [frames][H][W][C].
  *  - up to two input sources (src1 may be NULL): channel concat of the UNet skip connection

@@ -41,7 +41,21 @@ def convt(B, T, HW, C, N):
     res = torch.randn(B * T * HW, N, device=dev).to(BF)
     return (lambda: ops.conv_t3(x, B, T, HW, w, bias=b, out=out, res1=res, s_acc=0.5)), 2.0 * B * T * HW * 3 * C * N
 
+def ff(M, C, fused, res2=False):
+    x = torch.randn(M, C, device=dev).to(BF)
+    w1 = (torch.randn(8 * C, C, device=dev) / C ** 0.5).to(BF); b1 = torch.randn(8 * C, device=dev)
+    w2 = (torch.randn(C, 4 * C, device=dev) / (4 * C) ** 0.5).to(BF); b2 = torch.randn(C, device=dev)
+    out = torch.empty(M, C, device=dev, dtype=BF); hid = torch.empty(M, 4 * C, device=dev, dtype=BF)
+    kw = dict(bias=b2, out=out, res1=torch.randn(M, C, device=dev).to(BF))
+    if res2: kw["res2"] = torch.randn(M, C, device=dev).to(BF); kw["s_res2"] = 0.5
+    if fused:
+        return (lambda: ops.feedforward(x, w1, b1, w2, **kw)), 2.0 * M * C * 12 * C
+    return (lambda: ops.linear(ops.linear(x, w1, bias=b1, geglu=True, out=hid), w2, **kw)), 2.0 * M * C * 12 * C
+
 CASES = [
+    ("ff L0 fused 71680x320", lambda: ff(71680, 320, True), 14),
+    ("ff L0 fused 71680x320 +res2", lambda: ff(71680, 320, True, True), 7),
+    ("ff L0 two-launch 71680x320", lambda: ff(71680, 320, False), 0),
     ("geglu_up L0 71680x320->2560", lambda: lin(71680, 320, 2560, geglu=True), 21),
     ("geglu_up L1 17920x640->5120", lambda: lin(17920, 640, 5120, geglu=True), 21),
     ("geglu_up L2 4480x1280->10240", lambda: lin(4480, 1280, 10240, geglu=True), 21),

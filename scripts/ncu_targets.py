@@ -20,6 +20,16 @@ elif which == "attn":
     qkv = torch.randn(28 * 2560, 960, device=dev).to(BF)
     for _ in range(3): ops.attn_spatial(qkv, 28, 2560, 5)
     torch.cuda.synchronize()
+if which in ("ff", "ff1"):
+    from ctrlv_b200 import _lib
+    _lib.load().ctrlv_feedforward_override(1 if which == "ff1" else 0)
+    M, C = 71680, 320
+    x = torch.randn(M, C, device=dev).to(BF)
+    w1 = (torch.randn(8 * C, C, device=dev) / C ** 0.5).to(BF); b1 = torch.randn(8 * C, device=dev)
+    w2 = (torch.randn(C, 4 * C, device=dev) / (4 * C) ** 0.5).to(BF); b2 = torch.randn(C, device=dev)
+    res = torch.randn(M, C, device=dev).to(BF)
+    for _ in range(3): ops.feedforward(x, w1, b1, w2, bias=b2, res1=res)
+    torch.cuda.synchronize()
 print("ok")
 if which == "norms":
     x = torch.randn(71680, 320, device=dev).to(BF); g = torch.randn(320, device=dev); b = torch.randn(320, device=dev); o = torch.empty_like(x)

@@ -192,6 +192,62 @@ def test_groupnorm(ops, units, rows, C0, C1, silu, eps):
     assert rel(out, ref.permute(0, 2, 1).reshape(-1, C)) < TOL_BF16
 
 
+@pytest.mark.parametrize("M,C,flags", [
+    (128, 64, {}),
+    (1000, 64, dict(res1=True)),                                  # ragged M, one hidden chunk ring wrap
+    (4096, 128, dict(res1=True, rowbias=True)),                    # tff_in: + frame-position embedding
+    (2048, 256, dict(res1=True, res2=True, s_acc=0.3)),            # tff: AlphaBlender epilogue
+    (300, 320, dict(res1=True)),                                   # C = 320: two 160-wide MMA2 tiles, 512 TMEM columns
+    (71680, 320, dict(res1=True)),                                 # BASELINE config-2 level-0 shape (4 waves of tiles)
+])
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_feedforward_fused(ops, M, C, flags, cta_group):
+    """ctrlv_feedforward (GEGLU up-projection + down-projection in one launch, intermediate in TMEM) against
+    the two-launch form and against torch (diffusers FeedForward with exact-erf GELU)."""
+    dev = "cuda"
+    x = torch.randn(M, C, device=dev).to(BF)
+    w1 = (torch.randn(8 * C, C, device=dev) / C ** 0.5).to(BF)      # rows: (value, gate) interleaved
+    b1 = torch.randn(8 * C, device=dev) * 0.5
+    w2 = (torch.randn(C, 4 * C, device=dev) / (4 * C) ** 0.5).to(BF)
+    b2 = torch.randn(C, device=dev)
+    kw = dict(bias=b2)
+    if flags.get("res1"):
+        kw["res1"] = torch.randn(M, C, device=dev).to(BF)
+        kw["s_res1"] = 1.0 - flags.get("s_acc", 0.0) if "s_acc" in flags else 1.0
+    if flags.get("res2"):
+        kw["res2"] = torch.randn(M, C, device=dev).to(BF)
+        kw["s_res2"] = 0.7
+    if "s_acc" in flags:
+        kw["s_acc"] = flags["s_acc"]
+    if flags.get("rowbias"):
+        T, S = 4, M // 16
+        kw.update(rowbias=torch.randn(T, C, device=dev), rb_mode=2, rb_div=S, rb_mod=T)
+    from ctrlv_b200 import _lib
+    _lib.check(_lib.load().ctrlv_feedforward_override(cta_group))  # single CTAs / CTA pairs (cta_group::2)
+    try:
+        fused = ops.feedforward(x, w1, b1, w2, **kw)
+        fused2 = ops.feedforward(x, w1, b1, w2, **kw)
+    finally:
+        _lib.load().ctrlv_feedforward_override(0)
+    two = ops.linear(ops.linear(x, w1, bias=b1, geglu=True), w2, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, fused2)
+    # reference: fp32 math on the bf16 operands, hidden activations rounded to bf16 like both kernels do
+    u = x.float() @ w1.float().t() + b1
+    hid = (u[:, 0::2] * F.gelu(u[:, 1::2])).to(BF).float()
+    ref = hid @ w2.float().t() + b2
+    if flags.get("rowbias"):
+        ref = ref + kw["rowbias"][(torch.arange(M, device=dev) // kw["rb_div"]) % kw["rb_mod"]]
+    ref = ref * kw.get("s_acc", 1.0)
+    if "res1" in kw:
+        ref = ref + kw["s_res1"] * kw["res1"].float()
+    if "res2" in kw:
+        ref = ref + kw["s_res2"] * kw["res2"].float()
+    assert not torch.isnan(fused).any()
+    assert rel(fused, ref) < TOL_BF16 and rel(two, ref) < TOL_BF16
+    assert rel(fused, two) < 2e-3
+
+
 def _gn_table(ops, units, rows, C_total):
     return ops.GNStats(torch.zeros(ops.GNStats.numel(units), dtype=torch.int64, device="cuda"), units, rows, C_total)
 
