@@ -336,7 +336,7 @@ def run_b200(a):
     ops.PROFILE = None
     st._graph = gsave
     st.latents.copy_(lat_keep)
-    gemm_ops = ("linear", "conv3x3", "conv_t3", "upconv3x3")
+    gemm_ops = ("linear", "conv3x3", "conv_t3", "upconv3x3", "feedforward")
     gemm_ms = sum(v[1] for k, v in prof.items() if k[0] in gemm_ops)
     gemm_fl = sum(v[2] for k, v in prof.items() if k[0] in gemm_ops)
     gemm_n = sum(v[0] * (4 if k[0] == "upconv3x3" else 1) for k, v in prof.items() if k[0] in gemm_ops)
@@ -426,7 +426,7 @@ def run_b200(a):
                 break
             except Exception:
                 continue
-    roofline = {"bound": "tensor", "kernel": "ctrlv::igemm_kernel (tcgen05 implicit GEMM: Linear / 3x3 / temporal conv)",
+    roofline = {"bound": "tensor", "kernel": "ctrlv::igemm_kernel (tcgen05 implicit GEMM: Linear / 3x3 / temporal conv) + ctrlv::ff_kernel (fused FeedForward at C = 320)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": int(gemm_n),
                 "timing": "CUDA events around every igemm launch of one eager (un-captured) step in this process, on the "

@@ -104,6 +104,7 @@ SIGNATURES = {
     "ctrlv_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _I, _P, _P]),
     "ctrlv_attn_spatial": (_I, [_P, _I, _I, _I, _F, _P, _P]),
     "ctrlv_attn_temporal": (_I, [_P, _I, _I, _I, _I, _F, _P, _P]),
+    "ctrlv_cross_attn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _F, _I, _I, _I, _I, _P, _P]),
     "ctrlv_small_linear": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ctrlv_sinusoid": (_I, [_P, _I, _I, _I, _P, _P]),
     "ctrlv_prep_input": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),

@@ -276,8 +276,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  .relaxed: these arrives only hand TMEM buffers back to
+// the MMA issuer (ordered by tcgen05.fence::before_thread_sync), no generic-proxy data is published through
+// them — the .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR per arrive (12 % of the samples of
+// the CTA-pair FeedForward kernel).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in the executing CTA's smem, the transaction bytes are
 // credited to the barrier at `bar_cluster_addr` (the leader CTA's barrier).

@@ -319,10 +319,11 @@ class _Aux:
     """Per-forward side inputs of the blocks: the batched time-embedding projections and 1-token context
     vectors, plus the arena the GroupNorm statistics tables of this forward come from."""
 
-    def __init__(self, temb, ctx, ctx_all=None, vB=None, b0=0, arena=None):
+    def __init__(self, temb, ctx, ctx_all=None, vB=None, b0=0, arena=None, L=1, ehs_rows=None):
         self.temb, self.ctx = temb, ctx
+        self.L, self.ehs_rows = L, ehs_rows  # L > 1: the contexts as bf16 rows [n_ctx*L, D] for real cross-attention
         self.ctx_all = ctx if ctx_all is None else ctx_all
-        self.vB = ctx.shape[0] if vB is None else vB
+        self.vB = ctx.shape[0] if vB is None else vB  # contexts in the whole (virtual) batch
         self.b0 = b0
         self.arena = arena
 
@@ -408,10 +409,31 @@ class _CrossAttnL1:
         self.off = None  # column offset inside the model-wide batched context table
 
 
+class _CrossAttn:
+    """General cross-attention (context of L > 1 tokens): to_q with its LayerNorm's affine part folded in,
+    to_k | to_v fused into one projection of the context, to_out.  Packed lazily — the Box2Video pipelines only
+    ever pass a 1-token context, which _CrossAttnL1 handles without any of this."""
+
+    def __init__(self, sd, pfx, norm):
+        wq, bq = _fold_ln(sd[pfx + ".to_q.weight"], None, sd[norm + ".weight"], sd[norm + ".bias"])
+        self.wq, self.bq = _w(wq), _f(bq)
+        self.wkv = _w(torch.cat([sd[pfx + ".to_k.weight"], sd[pfx + ".to_v.weight"]], 0))
+        self.out = _Lin(sd, pfx + ".to_out.0")
+
+    def __call__(self, h, aux, heads, **ctx_index):
+        """h + to_out(softmax(to_q(LN(h)) to_k(ctx)^T / 8) to_v(ctx)); ctx_index: which context a row attends to"""
+        q = ops.linear(ops.layernorm(h), self.wq, bias=self.bq)
+        kv = ops.linear(aux.ehs_rows, self.wkv)
+        o = ops.cross_attn(q, kv, aux.L, heads, **ctx_index)
+        return ops.linear(o, self.out.w, bias=self.out.b, res1=h)
+
+
 class _Transformer:
     def __init__(self, sd, pfx, heads, time_context_order):
         self.heads = heads
         self.order = time_context_order
+        self._sd, self._pfx = sd, pfx  # (the owner's state dict, not a copy: general cross-attention packs lazily)
+        self._xattn = None
         self.norm = _Norm(sd, pfx + ".norm")
         self.proj_in, self.proj_out = _Lin(sd, pfx + ".proj_in"), _Lin(sd, pfx + ".proj_out")
         b = pfx + ".transformer_blocks.0"
@@ -425,6 +447,12 @@ class _Transformer:
         self.alpha = float(torch.sigmoid(sd[pfx + ".time_mixer.mix_factor"].float()).item())
         self.C = self.proj_in.w.shape[0]
         self._pos_cache: Dict[int, torch.Tensor] = {}
+
+    def xattn(self):
+        if self._xattn is None:
+            b, t = self._pfx + ".transformer_blocks.0", self._pfx + ".temporal_transformer_blocks.0"
+            self._xattn = (_CrossAttn(self._sd, b + ".attn2", b + ".norm2"), _CrossAttn(self._sd, t + ".attn2", t + ".norm2"))
+        return self._xattn
 
     def pos_emb(self, T):
         """time_pos_embed(time_proj(arange(T))): depends on weights and T only."""
@@ -447,8 +475,13 @@ class _Transformer:
         n = ops.layernorm(h)
         qkv = ops.linear(n, self.attn1.wqkv, bias=self.attn1.bqkv)
         att = ops.attn_spatial(qkv, F_, S, self.heads)
-        ctx = aux.ctx[:, self.attn2.off:self.attn2.off + self.C]
-        h = ops.linear(att, self.attn1.out.w, bias=self.attn1.out.b, rowbias=ctx, rb_mode=1, rb_div=T * S, res1=h)
+        general = aux.L > 1  # context of several tokens: real cross-attention; one token: a per-sample vector
+        if general:
+            h = ops.linear(att, self.attn1.out.w, bias=self.attn1.out.b, res1=h)
+            h = self.xattn()[0](h, aux, self.heads, ctx_mode=1, ctx_div=T * S)
+        else:
+            ctx = aux.ctx[:, self.attn2.off:self.attn2.off + self.C]
+            h = ops.linear(att, self.attn1.out.w, bias=self.attn1.out.b, rowbias=ctx, rb_mode=1, rb_div=T * S, res1=h)
         n = ops.layernorm(h)
         h = self.ff(n, res1=h)
         # --- TemporalBasicTransformerBlock on h + pos[t]; sequences are the T frames of a site
@@ -458,7 +491,13 @@ class _Transformer:
         n = ops.layernorm(hm)
         qkv = ops.linear(n, self.tattn1.wqkv, bias=self.tattn1.bqkv)
         att = ops.attn_temporal(qkv, B, T, S, self.heads)
-        if self.order == "s_major":  # diffusers 0.27.2: context of row (b, s) is ctx[(b*S + s) % B]
+        if general:
+            hm = ops.linear(att, self.tattn1.out.w, bias=self.tattn1.out.b, res1=hm)
+            if self.order == "s_major":  # context of row (b, s) is that of clip (b*S + s) % B (see below)
+                hm = self.xattn()[1](hm, aux, self.heads, ctx_mode=3, ctx_div=T * S, ctx_mod=S, ctx_B=aux.vB)
+            else:
+                hm = self.xattn()[1](hm, aux, self.heads, ctx_mode=1, ctx_div=T * S)
+        elif self.order == "s_major":  # diffusers 0.27.2: context of row (b, s) is ctx[(b*S + s) % B]
             # over the WHOLE batch (vB rows); a branch-sharded process owns global rows b0 .. b0+B-1, so
             # its local index (b*S + s) is offset by b0*S: rotate the table instead of the index
             tab = aux.ctx_all
@@ -470,7 +509,8 @@ class _Transformer:
         else:
             ctx_t = aux.ctx[:, self.tattn2.off:self.tattn2.off + self.C]
             kw = dict(rb_mode=1, rb_div=T * S)
-        hm = ops.linear(att, self.tattn1.out.w, bias=self.tattn1.out.b, rowbias=ctx_t, res1=hm, **kw)
+        if not general:
+            hm = ops.linear(att, self.tattn1.out.w, bias=self.tattn1.out.b, rowbias=ctx_t, res1=hm, **kw)
         n = ops.layernorm(hm)
         # ff(n) + hm, then AlphaBlender: a*h + (1-a)*(ff + hm)
         h = self.tff(n, s_acc=1.0 - self.alpha, res1=hm, s_res1=1.0 - self.alpha, res2=h, s_res2=self.alpha)
@@ -636,10 +676,11 @@ class _PackedModel(torch.nn.Module):
             raise TypeError("`timestep` must be a torch.Tensor (0-d or [batch])")
         if sample.dim() != 5:
             raise ValueError(f"`sample` must be [batch, frames, channels, height, width], got {tuple(sample.shape)}")
-        if encoder_hidden_states.dim() != 3 or encoder_hidden_states.shape[1] != 1:
-            raise NotImplementedError(
-                "encoder_hidden_states must be [batch, 1, cross_attention_dim]: the sm_100a path implements "
-                "the 1-token image-embedding context of the Box2Video pipeline")
+        if encoder_hidden_states.dim() != 3:
+            raise ValueError(f"`encoder_hidden_states` must be [batch, tokens, cross_attention_dim], got "
+                             f"{tuple(encoder_hidden_states.shape)}")
+        if encoder_hidden_states.shape[1] > 256:
+            raise NotImplementedError("contexts longer than 256 tokens are not supported by ctrlv_cross_attn")
         h, w = sample.shape[-2:]
         if h % 8 != 0 or w % 8 != 0:
             raise ValueError(f"latent height and width have to be divisible by 8 but are {h} and {w}.")
@@ -662,8 +703,17 @@ class _PackedModel(torch.nn.Module):
         holds the contexts of BOTH halves [2B, D], because the diffusers-0.27.2 `time_context` order
         pairs row (b, s) with context (b*S + s) % 2B of the whole batch (Appendix A.5)."""
         temb = ops.small_linear(emb, self.temb_w, self.temb_b, act_in=True)
-        ctx = ops.small_linear(ehs, self.ctx_w, self.ctx_b)
         arena = _GNArena(self._n_gn, n_units, enabled=GN_FUSED) if n_units else None
+        if ehs.dim() == 3 and ehs.shape[1] > 1:
+            # a context of several tokens (controlnet.py:230,244-245 allow it; the pipelines never produce it):
+            # real cross-attention in every transformer block, contexts kept as bf16 rows
+            if branch is not None:
+                raise NotImplementedError("CFG-branch-sharded forward with a multi-token context")
+            Bc, L, D = ehs.shape
+            return _Aux(temb, None, ctx_all=temb, vB=Bc, arena=arena, L=L,
+                        ehs_rows=ehs.reshape(Bc * L, D).to(BF16).contiguous())
+        ehs = ehs.reshape(ehs.shape[0], -1)
+        ctx = ops.small_linear(ehs, self.ctx_w, self.ctx_b)
         if branch is None:
             return _Aux(temb, ctx, arena=arena)
         Bl = emb.shape[0]
@@ -817,7 +867,7 @@ class ControlNetModel(_PackedModel):
         ops.nchw_to_nhwc(_as_f32_or_bf16(sample).reshape(B * T, Cin, H, W), inp, 0)
         ops.nchw_to_nhwc(_as_f32_or_bf16(control_cond).reshape(B * T, Cin // 2, H, W), inp, Cin)
         emb = self._embed(sample, timestep, added_time_ids)
-        ehs = encoder_hidden_states.to(device="cuda", dtype=torch.float32).reshape(B, -1).contiguous()
+        ehs = encoder_hidden_states.to(device="cuda", dtype=torch.float32).contiguous()  # [B, L, D]
         res, mid, geoms, gm = self.forward_rows(inp, emb, ehs, (B, T, H, W), conditioning_scale)
         down = [_from_rows(r, B * T, gg[2], gg[3]) for r, gg in zip(res, geoms)]
         midt = _from_rows(mid, B * T, gm[2], gm[3])
@@ -958,7 +1008,7 @@ class UNetSpatioTemporalConditionModel(_PackedModel):
         inp = torch.zeros((B * T * H * W, 64), device="cuda", dtype=BF16)
         ops.nchw_to_nhwc(_as_f32_or_bf16(sample).reshape(B * T, Cin, H, W), inp, 0)
         emb = self._embed(sample, timestep, added_time_ids)
-        ehs = encoder_hidden_states.to(device="cuda", dtype=torch.float32).reshape(B, -1).contiguous()
+        ehs = encoder_hidden_states.to(device="cuda", dtype=torch.float32).contiguous()  # [B, L, D]
         down = mid = None
         if is_controlnet:
             down = [_to_rows(r, r.shape[1]) for r in down_block_additional_residuals]

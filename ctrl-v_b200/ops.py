@@ -314,6 +314,22 @@ def attn_temporal(qkv: torch.Tensor, B: int, T: int, S: int, heads: int, scale: 
     return out
 
 
+def cross_attn(q: torch.Tensor, kv: torch.Tensor, L: int, heads: int, ctx_mode: int = 1, ctx_div: int = 1,
+               ctx_mod: int = 1, ctx_B: int = 1, scale: Optional[float] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Cross-attention over L > 1 context tokens: q [M, C] (projected), kv [n_ctx*L, 2C] = to_k | to_v of the
+    contexts; row m attends to context ridx(m) (make_ep's rb_mode conventions)."""
+    _req(q, BF16, "q"); _req(kv, BF16, "kv")
+    M, Cc = q.shape
+    assert Cc == heads * 64 and kv.shape[1] == 2 * Cc and kv.shape[0] % L == 0 and q.stride(1) == 1 and kv.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, Cc), dtype=BF16, device="cuda")
+    check(lib().ctrlv_cross_attn(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), M, heads, L, kv.shape[0] // L,
+                                 scale if scale is not None else 0.125, ctx_mode, ctx_div, ctx_mod, ctx_B,
+                                 out.data_ptr(), _stream()), "ctrlv_cross_attn")
+    return out
+
+
 def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
                  act_in: bool = False, act_out: bool = False, out: Optional[torch.Tensor] = None,
                  accumulate: bool = False) -> torch.Tensor:

@@ -211,6 +211,16 @@ int ctrlv_attn_spatial(const void* qkv, int32_t frames, int32_t S, int32_t heads
 int ctrlv_attn_temporal(const void* qkv, int32_t B, int32_t T, int32_t S, int32_t heads,
                         float scale, void* out, void* stream);
 
+/* Cross-attention core for a context of L > 1 tokens (diffusers Attention with encoder_hidden_states
+ * [batch, L, D]; controlnet.py:230,244-245): q [M][ldq] bf16 (heads of 64 channels, already projected by to_q),
+ * kv [n_ctx*L][ldkv] bf16 = to_k(ctx) | to_v(ctx) side by side (K in columns [0, C), V in [C, 2C)), L <= 256.
+ * Row m attends to context ridx(m), ridx as in ctrlv_epilogue.rb_mode (1: m / div, 2: (m / div) % mod,
+ * 3: the diffusers-0.27.2 S-major time_context order).  out [M][C] bf16.  L = 1 needs no kernel: the
+ * softmax over one key is 1 (the pipelines' case, folded into a per-sample vector by the host). */
+int ctrlv_cross_attn(const void* q, int64_t ldq, const void* kv, int64_t ldkv, int32_t M, int32_t heads, int32_t L,
+                     int32_t n_ctx, float scale, int32_t ctx_mode, int32_t ctx_div, int32_t ctx_mod, int32_t ctx_B,
+                     void* out, void* stream);
+
 /* Small-M dense layers on CUDA cores (embedding MLPs, time_emb_proj, 1-token cross-attention
  * value path): y[M][N] = act_in(x)[M][K] * W[N][K]^T + b, M <= 32; x, y fp32; W bf16.
  * act_in: 0 none, 1 SiLU.  act_out: 0 none, 1 SiLU.  accumulate: 1 adds the result to y

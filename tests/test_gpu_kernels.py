@@ -248,6 +248,23 @@ def test_feedforward_fused(ops, M, C, flags, cta_group):
     assert rel(fused, two) < 2e-3
 
 
+@pytest.mark.parametrize("B,T,S,heads,L,mode", [(2, 3, 40, 2, 5, 1), (2, 4, 24, 1, 77, 3), (3, 2, 16, 4, 256, 1), (2, 2, 9, 2, 33, 3)])
+def test_cross_attn_short_context(ops, B, T, S, heads, L, mode):
+    dev = "cuda"
+    C, M = heads * 64, B * T * S
+    q = torch.randn(M, C, device=dev).to(BF)
+    kv = torch.randn(B * L, 2 * C, device=dev).to(BF)
+    kw = dict(ctx_mode=1, ctx_div=T * S) if mode == 1 else dict(ctx_mode=3, ctx_div=T * S, ctx_mod=S, ctx_B=B)
+    out = ops.cross_attn(q, kv, L, heads, **kw)
+    m = torch.arange(M, device=dev)
+    ctx = m // (T * S) if mode == 1 else ((m // (T * S)) * S + m % S) % B
+    k = kv[:, :C].float().view(B, L, heads, 64)[ctx]          # [M, L, heads, 64]
+    v = kv[:, C:].float().view(B, L, heads, 64)[ctx]
+    qq = q.float().view(M, heads, 1, 64)
+    ref = F.scaled_dot_product_attention(qq, k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3)).reshape(M, C)
+    assert not torch.isnan(out).any() and rel(out, ref) < 5e-3
+
+
 def _gn_table(ops, units, rows, C_total):
     return ops.GNStats(torch.zeros(ops.GNStats.numel(units), dtype=torch.int64, device="cuda"), units, rows, C_total)
 

@@ -467,3 +467,25 @@ def test_groupnorm_statistics_from_epilogues_match_the_two_pass_path(tiny):
     assert rel(y1, oy) < 2e-2 and rel(y0, oy) < 2e-2
     assert rel(y1, y0) < 2e-2 and max(rel(a, b) for a, b in zip(d1, d0)) < 2e-2
     assert n1 < n0 - 40, (n1, n0)  # the tiny widths fuse every norm of >= 128 channels
+
+
+@pytest.mark.parametrize("L", [3, 77])
+def test_multi_token_context_cross_attention(tiny, L):
+    """controlnet.py:230,244-245: `encoder_hidden_states` is [batch, tokens, dim]; the pipelines pass one token
+    (folded into a per-sample vector), a longer context runs real cross-attention (ctrlv_cross_attn) in every
+    spatial and temporal transformer block, with the 0.27.2 S-major `time_context` order."""
+    ou, oc, mu, mc = tiny
+    inp, x = _inputs(3, 8, 16, 7.0)
+    t = torch.tensor(0.486, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    ehs = torch.randn(2, L, inp["image_embeddings"].shape[-1], generator=g).to(dev)
+    with torch.no_grad():
+        od, om = oc(x, t, ehs, inp["added_time_ids"], control_cond=inp["cond_em"], return_dict=False)
+        oy = ou(x, t, ehs, inp["added_time_ids"], od, om, return_dict=False)[0]
+        oy1 = ou(x, t, ehs[:, :1], inp["added_time_ids"], od, om, return_dict=False)[0]
+    md, mm = mc(x, t, ehs, inp["added_time_ids"], control_cond=inp["cond_em"], return_dict=False)
+    my = mu(x, t, ehs, inp["added_time_ids"], md, mm, return_dict=False)[0]
+    torch.cuda.synchronize()
+    assert max(rel(a, b) for a, b in zip(md, od)) < 2.5e-2 and rel(mm, om) < 2.5e-2
+    assert rel(my, oy) < 2e-2
+    assert rel(oy, oy1) > 1e-2  # the extra tokens matter in this test

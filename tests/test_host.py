@@ -88,8 +88,11 @@ def test_input_validation_mirrors_reference():
         chk(ok, 1.0, ehs, ids)  # controlnet.py:262-264: timestep must be a tensor
     with pytest.raises(ValueError):
         chk(torch.zeros(2, 3, 8, 12, 16), torch.tensor(1.0), ehs, ids)
+    chk(ok, torch.tensor(1.0), torch.zeros(2, 4, 1024), ids)  # multi-token contexts are accepted (ctrlv_cross_attn)
+    with pytest.raises(ValueError):
+        chk(ok, torch.tensor(1.0), torch.zeros(2, 1024), ids)
     with pytest.raises(NotImplementedError):
-        chk(ok, torch.tensor(1.0), torch.zeros(2, 4, 1024), ids)
+        chk(ok, torch.tensor(1.0), torch.zeros(2, 300, 1024), ids)
 
 
 def test_pipeline_check_inputs():
