@@ -267,7 +267,7 @@ class StableVideoControlPipeline:
     `output_type` "pt" / "np" / "pil"); with an `image_encoder`
     (`ctrlv_b200.clip.CLIPVisionModelWithProjection`, row f-3) it embeds the conditioning image (:220:
     antialiased resize to 224 + CLIP ViT-H).  `image` is a PIL image, a list of them, or a
-    [B, 3, H, W] tensor in [0, 1], already at `height` x `width`.  Without those modules pass
+    [B, 3, H, W] tensor in [0, 1] (resized to `height` x `width` like `VaeImageProcessor.preprocess`).  Without those modules pass
     `image_embeddings=`, `image_latents=` and 4-channel `cond_images` latents (:86-88) and use
     `output_type="latent"`."""
 
@@ -408,14 +408,32 @@ class StableVideoControlPipeline:
                 "`unet.config.time_embedding_type` and `text_encoder_2.config.projection_dim`.")
         return torch.tensor([add_time_ids], dtype=torch.float32).repeat(batch_size, 1)
 
-    def _encode_vae_image(self, image, height, width, noise_aug_strength, generator):  # :228-241
-        """`image_processor.preprocess` for a tensor in [0, 1] (normalise to [-1, 1]; resizing is not
-        implemented: pass the image at the target size), noise augmentation, VAE `.mode()`."""
+    @classmethod
+    def _preprocess_image(cls, image, height: int, width: int) -> torch.Tensor:
+        """`VaeImageProcessor.preprocess(image, height, width)` of diffusers 0.27.2 up to (not including) the
+        [-1, 1] normalisation (pipeline_video_control.py:227): PIL images are resized with PIL's Lanczos filter
+        (the processor's default `resample`), tensors with `F.interpolate(size=...)`'s default nearest-neighbour
+        rule (source index = floor(dst * in / out)) — a pure gather, done with index_select.  Returns
+        [B, 3, height, width] fp32 in [0, 1]."""
+        if not isinstance(image, torch.Tensor):
+            from PIL import Image
+            imgs = image if isinstance(image, list) else [image]
+            imgs = [im if im.size == (width, height) else im.resize((width, height), resample=Image.LANCZOS) for im in imgs]
+            return cls._image_to_tensor01(imgs)
+        image = cls._image_to_tensor01(image)
+        H, W = image.shape[-2:]
+        if (H, W) != (height, width):
+            iy = torch.floor(torch.arange(height, dtype=torch.float32) * (H / height)).long().clamp_(max=H - 1)
+            ix = torch.floor(torch.arange(width, dtype=torch.float32) * (W / width)).long().clamp_(max=W - 1)
+            image = image.index_select(-2, iy.to(image.device)).index_select(-1, ix.to(image.device))
+        return image
+
+    def _encode_vae_image(self, image, height, width, noise_aug_strength, generator):  # :227-241
+        """`image_processor.preprocess` (resize to height x width, normalise to [-1, 1]), noise augmentation,
+        VAE `.mode()`."""
         if self.vae is None:
             raise NotImplementedError("pass image_latents=[B,4,h,w] or construct the pipeline with a `vae`")
-        image = self._image_to_tensor01(image)
-        if tuple(image.shape[-2:]) != (height, width):
-            raise NotImplementedError(f"`image` must already be {height}x{width}; resizing is not implemented")
+        image = self._preprocess_image(image, height, width)
         image = 2.0 * image.to(torch.float32) - 1.0
         noise = torch.randn(image.shape, generator=generator, dtype=torch.float32,
                             device=generator.device if generator is not None else "cpu")

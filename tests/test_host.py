@@ -330,3 +330,22 @@ def test_scheduler_from_pretrained_config(tmp_path):
             EulerDiscreteScheduler.from_config(dict(svd, **bad))
     with pytest.raises(OSError):
         EulerDiscreteScheduler.from_pretrained(str(tmp_path / "nowhere"))
+
+
+def test_conditioning_image_is_resized_like_the_vae_image_processor():
+    """pipeline_video_control.py:227 `image_processor.preprocess(image, height, width)`: diffusers 0.27.2 resizes
+    tensors with F.interpolate's default nearest rule and PIL images with PIL's Lanczos filter."""
+    import numpy as np
+    import torch.nn.functional as F
+    from PIL import Image
+    from ctrlv_b200.pipeline import StableVideoControlPipeline as P
+    g = torch.Generator().manual_seed(0)
+    for (H, W, h, w) in ((48, 80, 32, 64), (30, 50, 64, 96), (64, 64, 64, 64), (37, 53, 40, 24)):
+        x = torch.rand(2, 3, H, W, generator=g)
+        assert torch.equal(P._preprocess_image(x, h, w), F.interpolate(x, size=(h, w)))
+    im = Image.fromarray((np.random.RandomState(0).rand(48, 80, 3) * 255).astype("uint8"))
+    got = P._preprocess_image([im, im], 32, 64)
+    want = torch.from_numpy(np.array(im.resize((64, 32), resample=Image.LANCZOS)).astype("float32") / 255.0).permute(2, 0, 1)
+    assert got.shape == (2, 3, 32, 64) and torch.equal(got[0], want) and torch.equal(got[1], want)
+    assert torch.equal(P._preprocess_image(im, 48, 80)[0],
+                       torch.from_numpy(np.array(im).astype("float32") / 255.0).permute(2, 0, 1))
