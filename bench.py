@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--plan", action="store_true",
+                    help="replay the step from a library launch plan (ctrlv_plan_run: launches re-issued from C) instead "
+                         "of a CUDA graph")
     a = ap.parse_args()
     dflt = (25, 576, 1024) if a.config == 4 else (14, 320, 512)
     a.frames = a.frames or dflt[0]
@@ -308,8 +311,9 @@ def run_b200(a):
         clip_ids = [a.clip_offset + rank]
         n_job_steps = a.steps
     Bc = len(clip_ids)
-    st = pipeline.DenoiseStep(unet, ctrl, Bc, T, h, w, cfg=True, conditioning_scale=1.0, use_graph=not a.no_graph,
-                              cfg_branch=pair.branch if pair else None, exchange=pair.exchange if pair else None)
+    st = pipeline.DenoiseStep(unet, ctrl, Bc, T, h, w, cfg=True, conditioning_scale=1.0, use_graph=not (a.no_graph or a.plan),
+                              use_plan=a.plan, cfg_branch=pair.branch if pair else None,
+                              exchange=pair.exchange if pair else None)
     st.set_schedule(sch.sigmas, sch.timesteps)
     hb = st.make_host_buffers()
     fill_host_inputs(hb, st, sch, clip_ids)
@@ -327,6 +331,7 @@ def run_b200(a):
     # and per-class achieved rates
     ops.PROFILE = {}
     st._graph, gsave = None, st._graph
+    st._plan, psave = None, st._plan
     lat_keep = st.latents.clone()
     n0 = lib.ctrlv_launch_count()
     st.step(0)
@@ -334,7 +339,7 @@ def run_b200(a):
     ops.profile_flush()
     prof = ops.PROFILE
     ops.PROFILE = None
-    st._graph = gsave
+    st._graph, st._plan = gsave, psave
     st.latents.copy_(lat_keep)
     gemm_ops = ("linear", "conv3x3", "conv_t3", "upconv3x3", "feedforward")
     gemm_ms = sum(v[1] for k, v in prof.items() if k[0] in gemm_ops)
@@ -457,7 +462,7 @@ def run_b200(a):
             "config": {"workload": work, "baseline_config": a.config, "clips_per_gpu": Bc, "cfg_batch": 2 * Bc,
                        "parallelism": par, "weights": "random-init, full SVD architecture",
                        "l2_policy": "inputs+weights (4.4 GB bf16) exceed the 126 MB L2; no flush",
-                       "cuda_graph": not a.no_graph, "first_clip": a.clip_offset},
+                       "cuda_graph": not (a.no_graph or a.plan), "library_plan": bool(a.plan), "first_clip": a.clip_offset},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * steps_done, "launches_per_step": launches_per_step,

@@ -88,6 +88,14 @@ SIGNATURES = {
     "ctrlv_version": (C.c_char_p, []),
     "ctrlv_device_check": (_I, []),
     "ctrlv_launch_count": (_L, []),
+    "ctrlv_plan_create": (_I, [_P, C.POINTER(_P)]),
+    "ctrlv_plan_fork": (_I, []),
+    "ctrlv_plan_join": (_I, []),
+    "ctrlv_plan_finish": (_I, [_P]),
+    "ctrlv_plan_size": (_L, [_P]),
+    "ctrlv_plan_run": (_I, [_P, _P]),
+    "ctrlv_plan_destroy": (_I, [_P]),
+    "ctrlv_memset_zero": (_I, [_P, _L, _P]),
     "ctrlv_igemm": (_I, [C.POINTER(IgemmDesc), _P]),
     "ctrlv_igemm_plan": (_I, [C.POINTER(IgemmDesc), _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ctrlv_igemm_override": (_I, [_I, _I, _I]),

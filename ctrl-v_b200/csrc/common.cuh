@@ -4,6 +4,8 @@
 // the builders below.
 #pragma once
 #include <cstring>
+#include <tuple>
+#include <utility>
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -49,23 +51,55 @@ bool pdl_enabled();
 // every kernel launch of the library is counted (ctrlv_launch_count(): the number a caller reports as
 // "launches of this library" is measured, not derived)
 void count_launch();
+// ---- launch plans (ctrlv_plan_*, include/ctrlv_b200.h) ------------------------------------------------
+// While a plan is being recorded on the calling thread, every kernel launch of the library is also appended
+// to it: kernel entry, launch configuration and a copy of the argument bytes (tensor maps included, so a
+// replay encodes nothing).  ctrlv_plan_run re-issues the recorded launches from C.
+bool plan_recording();
+void plan_record_launch(const void* func, dim3 grid, dim3 block, size_t smem, int cluster_x, cudaStream_t stream,
+                        void** args, const size_t* sizes, int nargs);
 #ifdef __CUDACC__
-template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                                     cudaStream_t stream, Args&&... args) {
+template <typename Tuple, size_t... I>
+static inline cudaError_t launch_tuple(const void* func, dim3 grid, dim3 block, size_t smem, int cluster_x,
+                                       cudaStream_t stream, Tuple& t, std::index_sequence<I...>) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster_x; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  ++na;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (unsigned)na;
+  void* argv[] = {(void*)&std::get<I>(t)...};
+  const size_t sizes[] = {sizeof(typename std::tuple_element<I, Tuple>::type)...};
   count_launch();
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (plan_recording()) plan_record_launch(func, grid, block, smem, cluster_x, stream, argv, sizes, (int)sizeof...(I));
+  return cudaLaunchKernelExC(&cfg, func, argv);
+}
+// every kernel of the library is launched through one of these two
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t stream, Args&&... args) {
+  std::tuple<KArgs...> t(static_cast<KArgs>(args)...);
+  return launch_tuple(reinterpret_cast<const void*>(kernel), grid, block, smem, 1, stream, t,
+                      std::index_sequence_for<KArgs...>{});
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                          cudaStream_t stream, Args&&... args) {  // thread-block clusters of 2 CTAs
+  std::tuple<KArgs...> t(static_cast<KArgs>(args)...);
+  return launch_tuple(reinterpret_cast<const void*>(kernel), grid, block, smem, 2, stream, t,
+                      std::index_sequence_for<KArgs...>{});
 }
 #endif
 

@@ -509,21 +509,7 @@ extern "C" int ctrlv_feedforward(const void* x, int64_t ldx, int32_t M, int32_t 
   } else {
     const int units = (p.tiles + 1) / 2;
     const int pairs = units < dp.sms / 2 ? units : dp.sms / 2;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kFfThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-    cfg.attrs = attr;
-    cfg.numAttrs = 2;
-    count_launch();
-    CTRLV_CUDA(cudaLaunchKernelEx(&cfg, ff_kernel<2>, p));
+    CTRLV_CUDA(launch_cluster2(ff_kernel<2>, dim3(2 * pairs), dim3(kFfThreads), smem, stream, p));
   }
   return CTRLV_OK;
 }

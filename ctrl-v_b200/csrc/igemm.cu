@@ -870,21 +870,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
     CTRLV_CUDA(launch_pdl(igemm_kernel<1>, dim3(grid), dim3(threads), smem, stream, p));
   } else {
     const int pairs = p.tiles_total < g_num_sms / 2 ? p.tiles_total : g_num_sms / 2;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-    cfg.attrs = attr;
-    cfg.numAttrs = 2;
-    count_launch();
-    CTRLV_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<2>, p));
+    CTRLV_CUDA(launch_cluster2(igemm_kernel<2>, dim3(2 * pairs), dim3(threads), smem, stream, p));
   }
   return CTRLV_OK;
 }

@@ -334,7 +334,7 @@ class _Aux:
     def gn_reset(self):
         """Re-zero the arena and hand its tables out again (callers that reuse one _Aux for several forwards)."""
         if self.arena is not None and self.arena.enabled:
-            self.arena.buf.zero_()
+            ops.memset_zero(self.arena.buf)
             self.arena.off = 0
 
 
@@ -346,7 +346,8 @@ class _GNArena:
     def __init__(self, n_tables: int, max_units: int, enabled: bool = True):
         self.enabled = enabled
         per_table = max(ops.GNStats.numel(u) for u in range(1, max_units + 1)) if enabled else 0
-        self.buf = torch.zeros((n_tables * per_table,), dtype=torch.int64, device="cuda") if enabled else None
+        self.buf = (ops.memset_zero(torch.empty((n_tables * per_table,), dtype=torch.int64, device="cuda"))
+                    if enabled else None)
         self.off = 0
 
     def take(self, n_units: int, rows_per_unit: int, C_total):

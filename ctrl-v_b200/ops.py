@@ -413,6 +413,13 @@ def axpby(x: torch.Tensor, y: torch.Tensor, a: float = 1.0, b: float = 1.0,
     return out
 
 
+def memset_zero(t: torch.Tensor) -> torch.Tensor:
+    """Zero a contiguous tensor through the library (recordable by a launch plan, unlike torch's fill kernel)."""
+    assert t.is_contiguous() and t.is_cuda
+    check(lib().ctrlv_memset_zero(t.data_ptr(), t.numel() * t.element_size(), _stream()), "ctrlv_memset_zero")
+    return t
+
+
 def gn_stats_of(x: torch.Tensor, gn) -> None:
     """Accumulate the GroupNorm statistics of x [M, C] itself into gn = (GNStats, c_off) — the same reduction
     as `axpby(gn=)`, for a tensor whose producer could not (a skip connection with two consumers)."""

@@ -107,7 +107,7 @@ class DenoiseStep:
     def __init__(self, unet: UNetSpatioTemporalConditionModel, controlnet: Optional[ControlNetModel],
                  batch: int, num_frames: int, h: int, w: int, cfg: bool = True,
                  conditioning_scale: float = 1.0, use_graph: bool = True, two_streams: bool = True,
-                 cfg_branch: Optional[int] = None, exchange: Optional[Callable] = None):
+                 cfg_branch: Optional[int] = None, exchange: Optional[Callable] = None, use_plan: bool = False):
         if cfg_branch is not None and (not cfg or cfg_branch not in (0, 1)):
             raise ValueError("cfg_branch is 0 (uncond) or 1 (cond) and needs cfg=True")
         self.cfg_branch, self.exchange = cfg_branch, exchange
@@ -118,6 +118,10 @@ class DenoiseStep:
         self.nb = 2 * batch if cfg else batch
         self.scale = conditioning_scale
         self.use_graph = use_graph
+        # use_plan: replay the step from a library launch plan (ctrlv_plan_run: the launches are re-issued from C
+        # with the arguments recorded once) instead of a CUDA graph — what a non-Python host would do
+        self.use_plan = use_plan
+        self._plan, self._pool = None, None
         dev = "cuda"
         xdim = unet.cfg["cross_attention_dim"]
         xdim = xdim if isinstance(xdim, int) else xdim[0]
@@ -171,17 +175,26 @@ class DenoiseStep:
                 # kernels fill the tails / small grids of the UNet encoder's
                 main = torch.cuda.current_stream()
                 self._side.wait_stream(main)
+                ops.lib().ctrlv_plan_fork()  # (recorded when a launch plan is being built, else a no-op)
                 with torch.cuda.stream(self._side):
                     emb_c = self.controlnet.embed(ts, ids)
                     down, mid, _, _ = self.controlnet.forward_rows(self.inp, emb_c, self.ehs, g, self.scale, branch=br)
                     for t in list(down) + [mid]:
                         t.record_stream(main)
-                join = lambda: main.wait_stream(self._side)
+                join = lambda: (main.wait_stream(self._side), ops.lib().ctrlv_plan_join())
             else:
                 emb_c = self.controlnet.embed(ts, ids)
                 down, mid, _, _ = self.controlnet.forward_rows(self.inp, emb_c, self.ehs, g, self.scale, branch=br)
         emb_u = self.unet.embed(ts, ids)
         self.unet.forward_rows(self.inp, emb_u, self.ehs, g, down, mid, out_f32=out, join=join, branch=br)
+
+    def __del__(self):
+        if getattr(self, "_plan", None) is not None:
+            try:
+                ops.lib().ctrlv_plan_destroy(self._plan)
+            except Exception:
+                pass
+            self._plan = None
 
     def set_schedule(self, sigmas: torch.Tensor, timesteps: torch.Tensor):
         n = timesteps.numel()
@@ -199,7 +212,23 @@ class DenoiseStep:
         self.step_params.copy_(self._host_params[0], non_blocking=True)
         self._body()
         torch.cuda.synchronize()
-        if self.use_graph:
+        if self.use_plan:
+            # record one step into a library plan; its intermediates come from a private pool that is never used
+            # again, so the recorded addresses stay this step's own
+            import ctypes
+            from ._lib import check
+            lib = ops.lib()
+            self._pool = torch.cuda.MemPool()
+            plan = ctypes.c_void_p()
+            with torch.cuda.use_mem_pool(self._pool):
+                check(lib.ctrlv_plan_create(torch.cuda.current_stream().cuda_stream, ctypes.byref(plan)), "ctrlv_plan_create")
+                try:
+                    self._body()
+                finally:
+                    check(lib.ctrlv_plan_finish(plan), "ctrlv_plan_finish")
+            self._plan = plan
+            torch.cuda.synchronize()
+        elif self.use_graph:
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr):
                 self._body()
@@ -210,7 +239,10 @@ class DenoiseStep:
     def run_model(self, i: int):
         """Everything of step i up to the model output (the whole step when not branch-sharded)."""
         self.step_params.copy_(self._host_params[i], non_blocking=True)
-        if self._graph is not None:
+        if self._plan is not None:
+            from ._lib import check
+            check(ops.lib().ctrlv_plan_run(self._plan, torch.cuda.current_stream().cuda_stream), "ctrlv_plan_run")
+        elif self._graph is not None:
             self._graph.replay()
         else:
             self._body()

@@ -41,6 +41,30 @@ int64_t ctrlv_launch_count(void);
 int ctrlv_device_check(void);
 
 /* ------------------------------------------------------------------------------------------
+ * Launch plans (what replaces the loop body pipeline_video_control.py:305-324 for a host that
+ * is not Python).  A plan records everything this library is asked to do on the calling thread between
+ * ctrlv_plan_create and ctrlv_plan_finish — every kernel launch with its configuration and a copy of its
+ * arguments (tensor maps are encoded ONCE, at record time), ctrlv_memset_zero calls, and the fork / join points
+ * of a second stream — while executing it normally.  ctrlv_plan_run(plan, stream) then re-issues the whole
+ * sequence from C: one call per denoise step (`ctrlv_denoise_step` of SURVEY §8(b) is ctrlv_plan_run on a plan
+ * recorded from one ControlNet + UNet + CFG/Euler step), no per-launch host work besides cudaLaunchKernelExC.
+ * The caller keeps every buffer the recorded calls referenced alive and at the same address (per-step scalars
+ * — sigma, timestep — live in device memory for that reason, see ctrlv_prep_input / ctrlv_cfg_euler).
+ * Launches recorded on a stream other than `main_stream` replay on a stream owned by the plan, ordered against
+ * the main stream by the recorded ctrlv_plan_fork (side waits for main) / ctrlv_plan_join (main waits for side).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct ctrlv_plan ctrlv_plan;
+int ctrlv_plan_create(void* main_stream, ctrlv_plan** out); /* start recording on the calling thread */
+int ctrlv_plan_fork(void);                                  /* no-ops when the thread is not recording */
+int ctrlv_plan_join(void);
+int ctrlv_plan_finish(ctrlv_plan* plan);                    /* stop recording */
+int64_t ctrlv_plan_size(const ctrlv_plan* plan);            /* recorded kernel launches */
+int ctrlv_plan_run(ctrlv_plan* plan, void* stream);
+int ctrlv_plan_destroy(ctrlv_plan* plan);
+/* cudaMemsetAsync(ptr, 0, bytes) that a plan can record (zeroing of GroupNorm statistics tables). */
+int ctrlv_memset_zero(void* ptr, int64_t bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused epilogue of every tensor-core contraction (acc = fp32 accumulator of element (m, n)):
  *     v   = acc + bias[n] + rowbias[ridx(m)][n]
  *     v   = geglu ? v_value * gelu_erf(v_gate) : v          (columns interleaved value/gate)

@@ -489,3 +489,35 @@ def test_multi_token_context_cross_attention(tiny, L):
     assert max(rel(a, b) for a, b in zip(md, od)) < 2.5e-2 and rel(mm, om) < 2.5e-2
     assert rel(my, oy) < 2e-2
     assert rel(oy, oy1) > 1e-2  # the extra tokens matter in this test
+
+
+def test_step_replayed_from_a_library_plan_equals_eager_and_graph(tiny):
+    """ctrlv_plan_create / _finish / _run — the whole step (ControlNet on the side stream, UNet, CFG +
+    Euler) recorded once and re-issued from C, arguments and tensor maps frozen at record time.  Bit-identical to
+    the eager step and to the CUDA-graph replay, also after unrelated allocations recycle the caching allocator."""
+    from ctrlv_b200 import _lib, pipeline
+    from oracle import sampling as S
+    ou, oc, mu, mc = tiny
+    T, h, w = 4, 16, 16
+    inp = S.make_inputs(T=T, h=h, w=w, xdim=mu.cfg["cross_attention_dim"], device=dev)
+    sch = S.EulerDiscreteSchedulerOracle(); sch.set_timesteps(6)
+    outs = {}
+    for mode in ("eager", "graph", "plan"):
+        st = pipeline.DenoiseStep(mu, mc, 1, T, h, w, cfg=True, use_graph=(mode == "graph"), use_plan=(mode == "plan"))
+        st.set_schedule(sch.sigmas, sch.timesteps)
+        st.image_latents.copy_(inp["image_latents"]); st.cond_em.copy_(inp["cond_em"])
+        st.ehs.copy_(inp["image_embeddings"].reshape(2, -1)); st.added_time_ids.copy_(inp["added_time_ids"])
+        st.guidance.copy_(inp["guidance"])
+        st.latents.copy_(inp["latents"] * float(sch.init_noise_sigma))
+        st.capture()
+        if mode == "plan":
+            n = _lib.load().ctrlv_plan_size(st._plan)
+            assert n > 300, n  # every launch of the step is in the plan
+        junk = [torch.randn(1 << 20, device=dev) for _ in range(6)]
+        for i in range(6):
+            st.step(i)
+        torch.cuda.synchronize()
+        outs[mode] = st.latents.clone()
+        del junk
+    assert torch.isfinite(outs["plan"]).all()
+    assert torch.equal(outs["plan"], outs["eager"]) and torch.equal(outs["graph"], outs["eager"])
