@@ -1,6 +1,6 @@
 """Compact per-kernel metric extracts from `ncu --set full` reports (read on the CPU with `ncu -i`):
-    python scripts/ncu_extract.py gpurun_out/ncu6_conv.ncu-rep ... -> profiles/r01_ncu_raw_<name>.csv
-One row per (kernel launch, metric): the columns the roofline statements in profiles/r01_ncu_summary.md
+    python scripts/ncu_extract.py gpurun_out/ncu6_conv.ncu-rep ... -> profiles/r02_ncu_raw_<name>.csv
+One row per (kernel launch, metric): the columns the roofline statements in profiles/r02_ncu_summary.md
 are read from (duration, tensor / XU / FMA pipe activity, issue slots, DRAM and L2 bytes, registers,
 occupancy), so the summary can be checked without the multi-MB .ncu-rep files."""
 import csv
@@ -27,7 +27,7 @@ def main():
                 and not re.search(r"\.(max|min|sum)\.pct|TriageCompute", n)]
         kcol = names.index("Kernel Name")
         name = re.sub(r"^ncu\d*_|\.ncu-rep$", "", os.path.basename(rep))
-        out = os.path.join(root, "profiles", f"r01_ncu_raw_{name}.csv")
+        out = os.path.join(root, "profiles", f"r02_ncu_raw_{name}.csv")
         with open(out, "w", newline="") as f:
             w = csv.writer(f)
             w.writerow(["launch", "kernel", "metric", "unit", "value"])
