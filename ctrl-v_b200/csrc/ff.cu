@@ -14,7 +14,7 @@
 // so the 4C-wide intermediate never leaves the SM, the second contraction runs under the GEGLU math of the
 // next chunk, and there is one tile set-up and one output epilogue per 128 rows instead of eleven.
 // W1_j / W2_j stream through a TMA ring in the order the MMA warp consumes them:
-//   W1(0), then for j = 0..J-1: [W1(j+1)], W2(j).
+//   W1(0), W1(1), then for j = 0..J-1: [W1(j+2)], W2(j)   (MMA1 runs two chunks ahead of MMA2).
 // TMEM columns: D [0, C), S [C, C+128), H double-buffered [C+128, C+192)  (C = 320: exactly 512).
 //
 // CG = 2 (the production form): a CTA pair (cluster of 2, tcgen05 cta_group::2) works on two adjacent row
@@ -163,33 +163,34 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
     // ================================ TMA producer ================================
     int stage = 0;
     uint32_t phase = 0;
-    // `rows` weight rows per tile in total; each CTA of a pair loads rows / CG of them, starting at its share.
+    // One ring slot holds a whole operand group — all KB1 k-blocks of a W1 chunk, or all n-tiles of a W2 chunk —
+    // so the MMA warp pays one barrier wait / elect / commit round per group instead of one per 16-32 KB block:
+    // with a round per block its own instruction stream (~75 instructions, ~600 cycles per round) outlasted the
+    // 256 cycles of tensor work a block carries, in every organisation of the other warps.
+    // `rows` weight rows per block in total; each CTA of a pair loads rows / CG of them, starting at its share.
     // CG = 2: both CTAs credit the LEADER's full barrier, which expects the pair's bytes.
-    auto load_w = [&](const CUtensorMap* tm, int c0, int row0, int rows) {
+    auto load_group = [&](const CUtensorMap* tm, int nblk, int rows, bool w1, int j) {
       mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
         uint8_t* dst = ring + (size_t)stage * p.stage_bytes;
-        if (CG == 1) {
-          mbar_expect_tx(&full_bar[stage], (uint32_t)(rows * 128));
-          tma_load_2d(dst, tm, &full_bar[stage], c0, row0);
-        } else {
-          const uint32_t lead_bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
-          if (crank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(rows * 128));
-          tma_load_2d_cg2(dst, tm, lead_bar, c0, row0 + (int)crank * (rows / 2));
+        const int blk_bytes = (rows / CG) * 128;
+        const uint32_t lead_bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
+        if (CG == 1 || crank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(nblk * rows * 128));
+        for (int b = 0; b < nblk; ++b) {
+          const int c0 = w1 ? b * 64 : j * 64;                     // K coordinate (W1: channel block, W2: hidden chunk)
+          const int r0 = (w1 ? j * 128 : b * rows) + (int)crank * (rows / CG);
+          if (CG == 1) tma_load_2d(dst + (size_t)b * blk_bytes, tm, &full_bar[stage], c0, r0);
+          else tma_load_2d_cg2(dst + (size_t)b * blk_bytes, tm, lead_bar, c0, r0);
         }
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     };
-    auto w1 = [&](int j) {
-      for (int kb = 0; kb < p.KB1; ++kb) load_w(&p.tmW1, kb * 64, j * 128, 128);
-    };
-    auto w2 = [&](int j) {
-      for (int t = 0; t < p.ntile2; ++t) load_w(&p.tmW2, j * 64, t * p.n2, p.n2);
-    };
-    for (int it = 0; it < nloc; ++it) {
+    auto w1 = [&](int j) { load_group(&p.tmW1, p.KB1, 128, true, j); };
+    auto w2 = [&](int j) { load_group(&p.tmW2, p.ntile2, p.n2, false, j); };
+    auto load_x = [&](int it) {  // the x tile of this CTA's it-th unit, once MMA1 of the previous unit is done with x
       const int m0 = tile_row0(it);
-      mbar_wait_relaxed(&x_empty, (uint32_t)((it & 1) ^ 1));  // MMA1 of the previous tile is done with x
+      mbar_wait_relaxed(&x_empty, (uint32_t)((it & 1) ^ 1));
       if (elect_one()) {
         if (CG == 1) {
           mbar_expect_tx(&x_full, (uint32_t)(p.KB1 * kFfXBlock));
@@ -201,12 +202,24 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
         }
       }
       __syncwarp();
-      if (it == 0) w1(0);
+    };
+    // x first, then the weight chunks in the MMA warp's order (x BEFORE the next unit's first chunks: those sit
+    // in the ring until MMA1 can read x, a ring shorter than two chunks would otherwise never drain)
+    if (nloc > 0) {
+      load_x(0);
+      w1(0);
+      if (p.J > 1) w1(1);
+    }
+    for (int it = 0; it < nloc; ++it) {
       for (int j = 0; j < p.J; ++j) {
-        if (j + 1 < p.J) w1(j + 1);
+        if (j + 2 < p.J) w1(j + 2);
         w2(j);
       }
-      if (it + 1 < nloc) w1(0);  // the next tile's first chunk streams in under this tile's tail
+      if (it + 1 < nloc) {  // the next unit's x and first chunks stream in under this unit's tail
+        load_x(it + 1);
+        w1(0);
+        if (p.J > 1) w1(1);
+      }
     }
   } else if (warp == 1 && crank == 0) {
     // ================================ MMA issuer (warp-uniform, elected lane issues) ============
@@ -226,22 +239,25 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
           ff_wait(&s_free[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1));
           tc_fence_after();
         }
-        for (int kb = 0; kb < p.KB1; ++kb) {
-          ff_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint64_t da = make_sdesc(aX + (uint32_t)(kb * kFfXBlock), 16, 1024);
-          const uint64_t db = make_sdesc(aR + (uint32_t)(stage * p.stage_bytes), 16, 1024);
-          if (elect_one()) {
+        ff_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t da0 = make_sdesc(aX, 16, 1024);
+          const uint64_t db0 = make_sdesc(aR + (uint32_t)(stage * p.stage_bytes), 16, 1024);
+          for (int kb = 0; kb < p.KB1; ++kb) {
+            // k-block kb of x / of this CTA's share of the W1 chunk; +2 in the >>4 address field = 32 bytes = K 16
+            const uint64_t da = da0 + (uint64_t)((kb * kFfXBlock) >> 4);
+            const uint64_t db = db0 + (uint64_t)((kb * (128 / CG) * 128) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (CG == 1) umma_ss(tS, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (uint32_t)((kb | k) != 0));
               else umma_ss_cg2(tS, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (uint32_t)((kb | k) != 0));
             }
-            commit(&empty_bar[stage]);
           }
-          __syncwarp();
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          commit(&empty_bar[stage]);
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
         if (elect_one()) {
           commit(&s_full[g & 1]);
           if (j == p.J - 1) commit(&x_empty);
@@ -257,11 +273,12 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
           ff_wait(&d_free, (uint32_t)((it & 1) ^ 1));
           tc_fence_after();
         }
-        for (int t = 0; t < p.ntile2; ++t) {
-          ff_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint64_t db = make_sdesc(aR + (uint32_t)(stage * p.stage_bytes), 16, 1024);
-          if (elect_one()) {
+        ff_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t db0 = make_sdesc(aR + (uint32_t)(stage * p.stage_bytes), 16, 1024);
+          for (int t = 0; t < p.ntile2; ++t) {
+            const uint64_t db = db0 + (uint64_t)((t * (p.n2 / CG) * 128) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (CG == 1)
@@ -271,11 +288,11 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
                 umma_ts_cg2(tD + (uint32_t)(t * p.n2), tH + (uint32_t)(buf * 32 + k * 8), db + (uint64_t)(2 * k), idesc2,
                             (uint32_t)((j | k) != 0));
             }
-            commit(&empty_bar[stage]);
           }
-          __syncwarp();
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          commit(&empty_bar[stage]);
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
         if (elect_one()) {
           commit(&h_free[buf]);
           if (j == p.J - 1) commit(&d_full);
@@ -284,9 +301,13 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
       };
       ff_wait(&x_full, (uint32_t)(it & 1));
       tc_fence_after();
+      // MMA1 runs TWO chunks ahead of MMA2: S(j + 2) only waits for the epilogue to have pulled S(j + 1) out of
+      // TMEM, so the S hand-off loop never queues behind a second contraction that is still waiting for its
+      // GEGLU output, and MMA2(j) fills the tensor pipe during the next hand-off instead
       mma1(0);
+      if (p.J > 1) mma1(1);
       for (int j = 0; j < p.J; ++j) {
-        if (j + 1 < p.J) mma1(j + 1);
+        if (j + 2 < p.J) mma1(j + 2);
         mma2(j);
       }
     }
@@ -468,13 +489,15 @@ extern "C" int ctrlv_feedforward(const void* x, int64_t ldx, int32_t M, int32_t 
   // CTA pairs whenever there are two tiles and the weight halves keep whole 8-row swizzle groups
   p.cg = (g_ff_force_cg ? g_ff_force_cg : ((p.tiles >= 2 && p.n2 % 16 == 0) ? 2 : 1));
   CTRLV_CHECK_ARG(p.cg == 1 || p.n2 % 16 == 0, "feedforward: cta_group 2 needs an MMA2 n-tile that is a multiple of 16");
-  p.stage_bytes = (p.n2 * 128 > kFfXBlock ? p.n2 * 128 : kFfXBlock) / p.cg;
-  p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
+  {  // one ring slot = one operand group: a whole W1 chunk (KB1 k-blocks) or a whole W2 chunk (ntile2 n-tiles)
+    const int g1 = p.KB1 * (128 / p.cg) * 128, g2 = p.ntile2 * (p.n2 / p.cg) * 128;
+    p.stage_bytes = ((g1 > g2 ? g1 : g2) + 1023) / 1024 * 1024;
+  }
   p.off_ring = p.KB1 * kFfXBlock;
   const int bias_bytes = (2 * p.H + C) * 4;
   int stages = (dp.max_smem - 1024 - p.off_ring - bias_bytes) / p.stage_bytes;
   if (stages > kFfMaxStages) stages = kFfMaxStages;
-  CTRLV_CHECK_ARG(stages >= 2, "feedforward: not enough shared memory");
+  CTRLV_CHECK_ARG(stages >= 1, "feedforward: not enough shared memory");
   p.stages = stages;
   p.off_b1 = p.off_ring + stages * p.stage_bytes;
   p.off_b2 = p.off_b1 + 2 * p.H * 4;
