@@ -28,6 +28,10 @@ namespace ctrlv {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
+#ifndef CTRLV_MMA_BATCH
+#define CTRLV_MMA_BATCH 4
+#endif
+constexpr int kMmaBatch = CTRLV_MMA_BATCH;  // most k-blocks issued per round of the MMA warp (IgemmParams::mma_batch)
 constexpr int kEpiWarps = 12;     // epilogue warps: 3 per TMEM lane quarter
 constexpr int kFirstEpiWarp = 4;  // warps 0-3: TMA producer, MMA issuer, two idle (one warpgroup)
 constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;
@@ -50,6 +54,7 @@ struct IgemmParams {
   int bres;       // 1: weight-stationary — the CTA's whole B tile (all K) stays resident in smem
   int bres_off;   // byte offset of the resident B region (after the A ring)
   int m_tiles;    // tiles_x * tiles_y * tiles_z
+  int mma_batch;  // k-blocks per round of the MMA warp (<= kMmaBatch, <= stages)
   FastDiv fd_rpu, fd_cg;  // GroupNorm statistics: division by rows per unit / channels per group
   ctrlv_epilogue ep;
 };
@@ -556,30 +561,51 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         mbar_wait_relaxed(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+        // kMmaBatch k-blocks per round of this warp: one barrier-wait / elect / branch sequence (~75 instructions,
+        // 400-600 cycles of a single warp's dependent uniform-datapath work) then carries 4 * kMmaBatch MMAs.
+        // With one k-block per round the issue stream outlasted the tensor work of every tile narrower than 256
+        // columns (a 64-wide k-block of a 128-column tile is 256 tensor cycles).
+        for (int kb = 0; kb < p.kblocks; kb += p.mma_batch) {
+          const int nb = min(p.mma_batch, p.kblocks - kb);
+          int st[kMmaBatch];
+          {
+            int s_ = stage;
+            uint32_t ph_ = phase;
+#pragma unroll
+            for (int b = 0; b < kMmaBatch; ++b) {
+              st[b] = s_;
+              if (b < nb) mbar_wait(&full_bar[s_], ph_);
+              if (++s_ == p.stages) { s_ = 0; ph_ ^= 1; }
+            }
+          }
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = p.bres ? smem_u32(smem + p.bres_off + (size_t)kb * p.BN * kBK * 2) : sa + kBM * kBK * 2;
-          const uint64_t da = make_sdesc(sa, 16, 1024);
-          const uint64_t db = make_sdesc(sb, 16, 1024);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              // advance 32 bytes (16 bf16) inside the 128B swizzle atom: +2 in the >>4 address field
-              if (CG == 1)
-                umma_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-              else
-                umma_ss_cg2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            for (int b = 0; b < kMmaBatch; ++b) {
+              if (b < nb) {
+                const uint32_t sa = smem_u32(smem + (size_t)st[b] * p.stage_bytes);
+                const uint32_t sb = p.bres ? smem_u32(smem + p.bres_off + (size_t)(kb + b) * p.BN * kBK * 2) : sa + kBM * kBK * 2;
+                const uint64_t da = make_sdesc(sa, 16, 1024);
+                const uint64_t db = make_sdesc(sb, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                  // advance 32 bytes (16 bf16) inside the 128B swizzle atom: +2 in the >>4 address field
+                  if (CG == 1)
+                    umma_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)(((kb + b) | k) != 0));
+                  else
+                    umma_ss_cg2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)(((kb + b) | k) != 0));
+                }
+                if (CG == 1) umma_commit(&empty_bar[st[b]]);
+                else umma_commit_cg2(&empty_bar[st[b]]);
+              }
             }
-            if (CG == 1) umma_commit(&empty_bar[stage]);
-            else umma_commit_cg2(&empty_bar[stage]);
           }
           __syncwarp();
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          for (int b = 0; b < nb; ++b)
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
         }
         if (elect_one()) {
           if (CG == 1) umma_commit(&tfull_bar[as]);
@@ -687,7 +713,7 @@ static int device_props(const DevProps** out) {
 }
 
 // tile-plan overrides for tuning sweeps (ctrlv_igemm_override; 0 = heuristic)
-static int g_force_bn = 0, g_force_cg = 0, g_force_stages = 0;
+static int g_force_bn = 0, g_force_cg = 0, g_force_stages = 0, g_force_batch = 0;
 
 // choose the (bx, by, bz) row box (<= 128 rows) that wastes the fewest MMA rows
 static void choose_box(int X, int Y, int Z, int* bx, int* by, int* bz) {
@@ -830,6 +856,13 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   if (g_force_stages) stages = g_force_stages;
   CTRLV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for 2 stages");
   p.stages = stages;
+  // k-blocks per round of the MMA warp: 2 halves its per-round overhead everywhere; 4 pays for the long-K convs
+  // when the ring is deep enough that waiting for four full stages does not starve the producer (measured on the
+  // step's problems: conv3x3 levels 1-3 another 1-5 %, the K <= 2560 Linears lose with 4)
+  p.mma_batch = (kblocks >= 40 && stages >= 6) ? 4 : 2;
+  if (g_force_batch) p.mma_batch = g_force_batch;
+  if (p.mma_batch > stages) p.mma_batch = stages;
+  if (p.mma_batch > kMmaBatch) p.mma_batch = kMmaBatch;
   p.tmem_cols = 2 * p.BN <= 128 ? 128 : (2 * p.BN <= 256 ? 256 : 512);
   p.ep = d->ep;  // s_acc is taken literally: 0 gives out = s_res1*res1 + s_res2*res2 (conditioning_scale = 0)
   CTRLV_CHECK_ARG(p.ep.out != nullptr || p.ep.out_f32 != nullptr, "igemm: no output");
