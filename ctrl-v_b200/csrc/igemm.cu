@@ -25,6 +25,9 @@
 
 namespace ctrlv {
 
+#ifndef CTRLV_EPI_ROWOWN
+#define CTRLV_EPI_ROWOWN 1
+#endif
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
@@ -194,15 +197,30 @@ __device__ __forceinline__ uint4 ldg_v4_early(const void* p) {
   return v;
 }
 
+__device__ __forceinline__ void ldg_v8_early(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+
 template <int NV>
 struct ResPrefetch {
   static constexpr int CPR = NV / 8;
   uint4 r1[CPR];  // transposed mapping: piece (lane % CPR) of rows lane / CPR + RPI * i
+                  // (row-owner mapping: the CPR pieces of this lane's own row)
   bool full;      // warp-uniform: the whole chunk lies inside the stored columns
   __device__ __forceinline__ void issue(const ctrlv_epilogue& ep, const EpRows<NV>& rows, int o0, int n_store,
-                                        int n0, int N) {
+                                        int n0, int N, bool rowown, long long m, bool valid) {
     const int lane = threadIdx.x & 31;
     full = (o0 + NV <= n_store) && (n0 < N);
+    if (NV == 32 && rowown) {
+      if (full && ep.res1 && valid) {
+        const bf16* rp = reinterpret_cast<const bf16*>(ep.res1) + (size_t)m * ep.ld_res1 + o0;
+        ldg_v8_early(rp, r1[0], r1[1]);
+        ldg_v8_early(rp + 16, r1[CPR > 2 ? 2 : 0], r1[CPR > 3 ? 3 : 1]);
+      }
+      return;
+    }
     if (full && ep.res1) {
 #pragma unroll
       for (int i = 0; i < CPR; ++i) {
@@ -248,7 +266,7 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u, float s) { 
 template <int NV>
 __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, long long m, bool valid, int o0,
                                           int n_store, const ResPrefetch<NV>& pf, const EpRows<NV>& rows,
-                                          uint4* wst, const GnTile& gn, const IgemmParams& p) {
+                                          uint4* wst, const GnTile& gn, const IgemmParams& p, bool rowown) {
   constexpr int CPR = NV / 8;
   constexpr int RPI = 32 / CPR;
   const int lane = threadIdx.x & 31;
@@ -257,7 +275,13 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
     for (int j = 0; j < NV; ++j) v[j] *= ep.s_acc;
   }
   if (pf.full) {
-    if (ep.res1) {
+    if (ep.res1 && NV == 32 && rowown) {
+      // row-owner mapping: the lane's own 64 bytes arrived as two whole-sector 256-bit loads
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < CPR; ++j) add_bf16x8(v + 8 * j, pf.r1[j], ep.s_res1);
+      }
+    } else if (ep.res1) {
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < CPR; ++i) wst[EpRows<NV>::slot(lane / CPR + RPI * i, lane % CPR)] = pf.r1[i];
@@ -285,7 +309,19 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
 #pragma unroll
       for (int j = 0; j < NV; j += 4) op[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
-    if (ep.out && NV == 16) {
+    if (ep.out && NV == 32 && rowown) {
+      // no GroupNorm statistics to take from the staged tile: store the lane's own row as two whole 32-byte
+      // sectors (256-bit stores) — no smem transposes, no per-row address arithmetic for four rows
+      if (valid) {
+        bf16* op = reinterpret_cast<bf16*>(ep.out) + (size_t)m * ep.ld_out + o0;
+#pragma unroll
+        for (int h = 0; h < NV / 16; ++h)
+          st_global_v8(op + 16 * h, pack_bf16x2(v[16 * h], v[16 * h + 1]), pack_bf16x2(v[16 * h + 2], v[16 * h + 3]),
+                       pack_bf16x2(v[16 * h + 4], v[16 * h + 5]), pack_bf16x2(v[16 * h + 6], v[16 * h + 7]),
+                       pack_bf16x2(v[16 * h + 8], v[16 * h + 9]), pack_bf16x2(v[16 * h + 10], v[16 * h + 11]),
+                       pack_bf16x2(v[16 * h + 12], v[16 * h + 13]), pack_bf16x2(v[16 * h + 14], v[16 * h + 15]));
+      }
+    } else if (ep.out && NV == 16) {
       // GEGLU chunks yield only 32 B per row: the transpose does not pay (measured), store directly
       // One 256-bit store per lane = one whole 32-byte sector (two 16-byte stores leave the L2 with
       // half-written sectors: measured, the store path cost a quarter of the K = 320 GEGLU kernel).
@@ -348,7 +384,8 @@ template <bool GEGLU>
 __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t taddr, long long m, bool valid, int n0,
                                          int n_store, float* sb, uint4* wst, const float* rb, float bv,
                                          const ResPrefetch<GEGLU ? 16 : 32>& pf,
-                                         const EpRows<GEGLU ? 16 : 32>& rows, const GnTile& gn, const IgemmParams& p) {
+                                         const EpRows<GEGLU ? 16 : 32>& rows, const GnTile& gn, const IgemmParams& p,
+                                         bool rowown) {
   constexpr int NV = GEGLU ? 16 : 32;
   uint32_t raw[32];
   tmem_ld32(taddr, raw);
@@ -380,7 +417,7 @@ __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t tadd
       v[j] = o0; v[j + 1] = o1;
     }
   }
-  ep_finish<NV>(v, ep, m, valid, GEGLU ? (n0 >> 1) : n0, n_store, pf, rows, wst, gn, p);
+  ep_finish<NV>(v, ep, m, valid, GEGLU ? (n0 >> 1) : n0, n_store, pf, rows, wst, gn, p, rowown);
 }
 
 // All 32-column chunks of one accumulator row owned by this warp (c = sub, sub + G, sub + 2G, G = 3
@@ -391,7 +428,7 @@ template <bool GEGLU>
 __device__ __forceinline__ void ep_tile(const ctrlv_epilogue& ep, uint64_t* tfull, uint32_t tphase, uint32_t t_row,
                                         long long m, int n_base, int N, int BN, int n_store, bool valid, int sub,
                                         float* sbias, uint4* wst, const float* rb, const float* rb_uniform,
-                                        const IgemmParams& p) {
+                                        const IgemmParams& p, bool rowown) {
   constexpr int NV = GEGLU ? 16 : 32;
   constexpr int G = kEpiWarps / 4;
   const int nch = BN / 32;
@@ -407,23 +444,23 @@ __device__ __forceinline__ void ep_tile(const ctrlv_epilogue& ep, uint64_t* tful
   // every bias value and the first TWO chunks' residual rows are requested before the accumulator is
   // ready: their latency hides under the MMA wait instead of under epilogue math
   bp.issue(ep, n_base, N, nch, sub, rb_uniform);
-  if (c0 < nch) pa.issue(ep, rows, o_of(c0), n_store, n_base + c0 * 32, N);
-  if (c1 < nch) pb.issue(ep, rows, o_of(c1), n_store, n_base + c1 * 32, N);
+  if (c0 < nch) pa.issue(ep, rows, o_of(c0), n_store, n_base + c0 * 32, N, rowown, m, valid);
+  if (c1 < nch) pb.issue(ep, rows, o_of(c1), n_store, n_base + c1 * 32, N, rowown, m, valid);
   mbar_wait(tfull, tphase);
   tc_fence_after();
   if (c0 >= nch) return;
   __syncwarp();
   ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c0 * 32), m, valid, n_base + c0 * 32, n_store, sbias, wst, rb,
-                  bp.b[0] + bp.u[0], pa, rows, gn, p);
+                  bp.b[0] + bp.u[0], pa, rows, gn, p, rowown);
   if (c1 >= nch) return;
-  if (c2 < nch) pa.issue(ep, rows, o_of(c2), n_store, n_base + c2 * 32, N);
+  if (c2 < nch) pa.issue(ep, rows, o_of(c2), n_store, n_base + c2 * 32, N, rowown, m, valid);
   __syncwarp();
   ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c1 * 32), m, valid, n_base + c1 * 32, n_store, sbias, wst, rb,
-                  bp.b[1] + bp.u[1], pb, rows, gn, p);
+                  bp.b[1] + bp.u[1], pb, rows, gn, p, rowown);
   if (c2 >= nch) return;
   __syncwarp();
   ep_chunk<GEGLU>(ep, t_row + (uint32_t)(c2 * 32), m, valid, n_base + c2 * 32, n_store, sbias, wst, rb,
-                  bp.b[2] + bp.u[2], pa, rows, gn, p);
+                  bp.b[2] + bp.u[2], pa, rows, gn, p, rowown);
 }
 
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) shares
@@ -626,6 +663,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const int n_store = ep.n_store > 0 ? ep.n_store : n_out_total;
     const uint32_t tempty_lead0 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
     const uint32_t tempty_lead1 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u;
+    // row-owner stores / residual loads (two 256-bit accesses per 64-byte row piece) when nothing needs the
+    // staged, transposed tile (no GroupNorm statistics) and every row piece is 32-byte aligned
+    const bool rowown = CTRLV_EPI_ROWOWN && !ep.geglu && ep.gn_sums == nullptr && ep.out != nullptr && (ep.ld_out % 16) == 0 &&
+                        (reinterpret_cast<uintptr_t>(ep.out) & 31) == 0 &&
+                        (ep.res1 == nullptr || ((ep.ld_res1 % 16) == 0 && (reinterpret_cast<uintptr_t>(ep.res1) & 31) == 0));
     // position of this thread's row inside the tile box (loop invariant)
     const int ix = r % p.bx;
     const int iy = (r / p.bx) % p.by;
@@ -661,9 +703,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
       uint4* wst = wstage[warp - kFirstEpiWarp];
       if (ep.geglu)
-        ep_tile<true>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform, p);
+        ep_tile<true>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform, p, false);
       else
-        ep_tile<false>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform, p);
+        ep_tile<false>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform, p, rowown);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
