@@ -416,6 +416,9 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
     const uint32_t idesc_qk = make_idesc(128, 128, 0, 0);
     const uint32_t idesc_pv = make_idesc(128, 64, 0, 1);  // A (= P) from TMEM, B (= V) MN-major
     const uint32_t aQ = smem_u32(sQ), aKV = smem_u32(sKV);
+    // descriptor bases once (this warp's instruction stream is a single dependent chain: every descriptor rebuilt
+    // inside a round is tensor-pipe idle time); a ring slot / k-step only adds to the >>4 address field
+    const uint64_t dQ0 = make_sdesc(aQ, 16, 1024), dK0 = make_sdesc(aKV, 16, 1024), dV0 = make_sdesc(aKV, 1024, 1024);
     int n = 0;  // ring position of the block in use
     auto issue_qk = [&](int t, bool release) {  // S_t = Q_t K^T
       const int slot = n & 3;
@@ -424,11 +427,10 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
         tc_fence_after();
       }
       if (elect_one()) {
-        const uint32_t aK = aKV + slot * kTile;
+        const uint64_t dq = dQ0 + (uint64_t)((t * kTile) >> 4), dk = dK0 + (uint64_t)((slot * kTile) >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_ss(tmem_base + t * 128, make_sdesc(aQ + t * kTile + k * 32, 16, 1024),
-                  make_sdesc(aK + k * 32, 16, 1024), idesc_qk, (uint32_t)(k != 0));
+          umma_ss(tmem_base + t * 128, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_qk, (uint32_t)(k != 0));
         if (release) umma_commit(&kv_empty[slot]);
         umma_commit(&s_full[t]);
       }
@@ -441,11 +443,11 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn2_kernel(const __grid_co
         tc_fence_after();
       }
       if (elect_one()) {
-        const uint32_t aV = aKV + slot * kTile;
+        const uint64_t dv = dV0 + (uint64_t)((slot * kTile) >> 4);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + k * 8,
-                  make_sdesc(aV + k * 2048, 1024, 1024), idesc_pv, (uint32_t)((j | k) != 0));
+          umma_ts(tmem_base + 256 + t * 64, tmem_base + 384 + t * 64 + k * 8, dv + (uint64_t)(k * (2048 >> 4)), idesc_pv,
+                  (uint32_t)((j | k) != 0));
         if (release) umma_commit(&kv_empty[slot]);
         umma_commit(&o_full[t]);
       }
