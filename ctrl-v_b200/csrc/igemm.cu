@@ -54,8 +54,6 @@ struct IgemmParams {
   int BN, N, stages, a_bytes, stage_bytes, tmem_cols;
   int omx, omy, oox, ooy, oX, oY;  // output-row remap (identity: 1, 1, 0, 0, X, Y)
   int cg;  // 1 or 2 CTAs per tile (tcgen05 cta_group)
-  int bres;       // 1: weight-stationary — the CTA's whole B tile (all K) stays resident in smem
-  int bres_off;   // byte offset of the resident B region (after the A ring)
   int m_tiles;    // tiles_x * tiles_y * tiles_z
   int mma_batch;  // k-blocks per round of the MMA warp (<= kMmaBatch, <= stages)
   FastDiv fd_rpu, fd_cg;  // GroupNorm statistics: division by rows per unit / channels per group
@@ -473,7 +471,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
-  __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float wbias[kEpiWarps][32];   // per-warp broadcast row for the bias chunk
   __shared__ __align__(16) uint4 wstage[kEpiWarps][128];  // per-warp 32 x 64 B transpose tile
@@ -492,7 +489,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&bres_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps * CG);  // CG = 2: both CTAs' epilogue warps free the leader's buffer
@@ -513,20 +509,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 
   // work unit: (super-tile of CG consecutive m-tiles, n-tile); units are dealt round-robin to
   // clusters; inside a pair CTA r owns m-tile CG*super + r
-  // Weight-stationary mode (small K): CTA c keeps n-tile c % tiles_n for its whole life and walks
-  // the m-tiles c / tiles_n, + grid / tiles_n, ...; concurrent CTAs still share A tiles through L2.
-  int unit0 = (int)blockIdx.x / CG;
-  int nunits = (int)gridDim.x / CG;
-  int nloc = (p.tiles_total - unit0 + nunits - 1) / nunits;
-  const int bres_nt = (int)blockIdx.x % p.tiles_n;
-  if (CG == 1 && p.bres) {
-    const int per_n = (int)gridDim.x / p.tiles_n;  // host makes the grid a multiple of tiles_n
-    const int first = (int)blockIdx.x / p.tiles_n;
-    nloc = first < p.m_tiles ? (p.m_tiles - first + per_n - 1) / per_n : 0;
-    unit0 = first * p.tiles_n + bres_nt;   // so that tile = unit0 + it * nunits decodes as usual
-    nunits = per_n * p.tiles_n;
-  }
-
+  const int unit0 = (int)blockIdx.x / CG;
+  const int nunits = (int)gridDim.x / CG;
+  const int nloc = (p.tiles_total - unit0 + nunits - 1) / nunits;
   // register reallocation between the warpgroups: each warpgroup executes ONE setmaxnreg at the head of
   // its role branch (ptxas budgets the code below it accordingly)
   if (warp < kFirstEpiWarp) {
@@ -536,11 +521,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     {  // warp-uniform loop, one elected lane issues (see the MMA issuer below)
       int stage = 0;
       uint32_t phase = 0;
-      if (CG == 1 && p.bres && nloc > 0 && elect_one()) {  // the whole [BN x K] weight tile, once
-        mbar_expect_tx(&bres_bar, (uint32_t)(p.kblocks * p.BN * kBK * 2));
-        for (int kb = 0; kb < p.kblocks; ++kb)
-          tma_load_2d(smem + p.bres_off + (size_t)kb * p.BN * kBK * 2, &p.tmB, &bres_bar, kb * kBK, bres_nt * p.BN);
-      }
       for (int it = 0; it < nloc; ++it) {
         const int tile = unit0 + it * nunits;
         uint32_t q_, nt_, tx_, ty_, tz_;
@@ -564,9 +544,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 if (crank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * (p.a_bytes + (p.BN / 2) * kBK * 2)));
                 tma_load_4d_cg2(sa, &p.tmA[sg.map], lead_bar, sg.c0 + ch * kBK, x0 + sg.dx, y0 + sg.dy, z0 + sg.dz);
                 tma_load_2d_cg2(sb, &p.tmB, lead_bar, kb * kBK, nt * p.BN + (int)crank * (p.BN / 2));
-              } else if (p.bres) {
-                mbar_expect_tx(&full_bar[stage], (uint32_t)p.a_bytes);
-                tma_load_4d(sa, &p.tmA[sg.map], &full_bar[stage], sg.c0 + ch * kBK, x0 + sg.dx, y0 + sg.dy, z0 + sg.dz);
               } else {
                 mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + p.BN * kBK * 2));
                 tma_load_4d(sa, &p.tmA[sg.map], &full_bar[stage], sg.c0 + ch * kBK, x0 + sg.dx, y0 + sg.dy, z0 + sg.dz);
@@ -591,7 +568,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const uint32_t idesc = make_idesc(kBM * CG, p.BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      if (CG == 1 && p.bres && nloc > 0) mbar_wait(&bres_bar, 0);
       for (int it = 0; it < nloc; ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -621,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             for (int b = 0; b < kMmaBatch; ++b) {
               if (b < nb) {
                 const uint32_t sa = smem_u32(smem + (size_t)st[b] * p.stage_bytes);
-                const uint32_t sb = p.bres ? smem_u32(smem + p.bres_off + (size_t)(kb + b) * p.BN * kBK * 2) : sa + kBM * kBK * 2;
+                const uint32_t sb = sa + kBM * kBK * 2;
                 const uint64_t da = make_sdesc(sa, 16, 1024);
                 const uint64_t db = make_sdesc(sb, 16, 1024);
 #pragma unroll
@@ -755,7 +731,7 @@ static int device_props(const DevProps** out) {
 }
 
 // tile-plan overrides for tuning sweeps (ctrlv_igemm_override; 0 = heuristic)
-static int g_force_bn = 0, g_force_cg = 0, g_force_stages = 0, g_force_batch = 0;
+static int g_force_bn = 0, g_force_cg = 0, g_force_stages = 0;
 
 // choose the (bx, by, bz) row box (<= 128 rows) that wastes the fewest MMA rows
 static void choose_box(int X, int Y, int Z, int* bx, int* by, int* bz) {
@@ -893,7 +869,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   p.a_bytes = 64 * p.bx * p.by * p.bz * 2;
   p.stage_bytes = kBM * kBK * 2 + (p.BN / p.cg) * kBK * 2;
   p.m_tiles = tiles_m;
-  int stages = p.bres ? p.bres_off / p.stage_bytes : (g_max_smem - 2048) / p.stage_bytes;
+  int stages = (g_max_smem - 2048) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (g_force_stages) stages = g_force_stages;
   CTRLV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for 2 stages");
@@ -902,7 +878,6 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   // when the ring is deep enough that waiting for four full stages does not starve the producer (measured on the
   // step's problems: conv3x3 levels 1-3 another 1-5 %, the K <= 2560 Linears lose with 4)
   p.mma_batch = (kblocks >= 40 && stages >= 6) ? 4 : 2;
-  if (g_force_batch) p.mma_batch = g_force_batch;
   if (p.mma_batch > stages) p.mma_batch = stages;
   if (p.mma_batch > kMmaBatch) p.mma_batch = kMmaBatch;
   p.tmem_cols = 2 * p.BN <= 128 ? 128 : (2 * p.BN <= 256 ? 256 : 512);
@@ -937,11 +912,9 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   }
 
   size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  if (p.bres) smem = (size_t)p.bres_off + (size_t)p.kblocks * p.BN * kBK * 2 + 1024;
   const int threads = kThreads;
   if (p.cg == 1) {
     int grid = p.tiles_total < g_num_sms ? p.tiles_total : g_num_sms;
-    if (p.bres) grid = (g_num_sms / p.tiles_n) * p.tiles_n;
     CTRLV_CUDA(launch_pdl(igemm_kernel<1>, dim3(grid), dim3(threads), smem, stream, p));
   } else {
     const int pairs = p.tiles_total < g_num_sms / 2 ? p.tiles_total : g_num_sms / 2;
