@@ -500,12 +500,12 @@ class _Transformer:
                 hm = self.xattn()[1](hm, aux, self.heads, ctx_mode=1, ctx_div=T * S)
         elif self.order == "s_major":  # diffusers 0.27.2: context of row (b, s) is ctx[(b*S + s) % B]
             # over the WHOLE batch (vB rows); a branch-sharded process owns global rows b0 .. b0+B-1, so
-            # its local index (b*S + s) is offset by b0*S: rotate the table instead of the index
-            tab = aux.ctx_all
-            rot = (aux.b0 * S) % aux.vB
-            if rot:
-                tab = torch.roll(tab, shifts=-rot, dims=0)
-            ctx_t = tab[:, self.tattn2.off:self.tattn2.off + self.C]
+            # its local index (b*S + s) is offset by b0*S
+            # — a rotation by (b0*S) % vB, which is 0 for every legal geometry: vB = 2*B_local, b0 = branch*B_local and
+            # S = h*w is even (h, w are multiples of 8), so the table is used as is
+            if (aux.b0 * S) % aux.vB:
+                raise NotImplementedError("branch-sharded S-major time_context with an odd number of sites")
+            ctx_t = aux.ctx_all[:, self.tattn2.off:self.tattn2.off + self.C]
             kw = dict(rb_mode=3, rb_div=T * S, rb_mod=S, rb_B=aux.vB)
         else:
             ctx_t = aux.ctx[:, self.tattn2.off:self.tattn2.off + self.C]
