@@ -60,18 +60,9 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {  // (the dynamic-smem
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
-               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
-
 // spin on the barrier phase without the hardware-suspend hint of mbar_wait: the handoffs of this kernel
 // (S full -> TMEM load -> S free -> MMA1, H full -> MMA2) sit on the critical path several times per chunk
 __device__ __forceinline__ void ff_wait(uint64_t* bar, uint32_t parity) {
-#ifdef FF_WAIT_SUSPEND
-  mbar_wait(bar, parity);
-#else
   uint32_t done;
   do {
     asm volatile(
@@ -82,7 +73,6 @@ __device__ __forceinline__ void ff_wait(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   } while (!done);
-#endif
 }
 
 __device__ __forceinline__ void ff_add_bf16x16(float* v, const uint4& lo, const uint4& hi, float s) {
