@@ -349,3 +349,21 @@ def test_conditioning_image_is_resized_like_the_vae_image_processor():
     assert got.shape == (2, 3, 32, 64) and torch.equal(got[0], want) and torch.equal(got[1], want)
     assert torch.equal(P._preprocess_image(im, 48, 80)[0],
                        torch.from_numpy(np.array(im).astype("float32") / 255.0).permute(2, 0, 1))
+
+
+def test_groupnorm_statistics_table_geometry():
+    """ops.GNStats: replication factor (power of two, >= 128 table rows in total) and which norm widths the
+    producers' epilogues can serve (an aligned 8-column piece must fall into at most two groups; the residual-add
+    kernel reduces channel pairs)."""
+    from ctrlv_b200 import ops
+    for units in (1, 2, 3, 28, 50, 127, 128, 129, 500):
+        r = ops.GNStats.replicas(units)
+        assert r & (r - 1) == 0 and r * units >= 128 and (r == 1 or (r // 2) * units < 128)
+        assert ops.GNStats.numel(units) == r * units * 64
+    for C, ok in ((64, False), (128, True), (192, True), (256, True), (320, True), (640, True), (960, True), (1280, True),
+                  (1920, True), (2560, True), (160, False), (96, False)):
+        assert ops.GNStats.fusable(C) == ok, C
+    for C in (128, 192, 320, 960, 1920):  # every aligned 8-column piece of a fusable width spans <= 2 groups
+        cg = C // 32
+        for c0 in range(0, C, 8):
+            assert len({(c0 + j) // cg for j in range(8)}) <= 2, (C, c0)
