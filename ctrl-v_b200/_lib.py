@@ -48,6 +48,7 @@ class Epilogue(C.Structure):
         ("gn_c_off", C.c_int32),
         ("gn_units", C.c_int32),
         ("gn_rep", C.c_int32),
+        ("rb_off", C.c_int32),
     ]
 
 

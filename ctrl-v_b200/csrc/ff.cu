@@ -52,7 +52,7 @@ __device__ __forceinline__ int ff_rowbias_index(const ctrlv_epilogue& ep, int m)
   const int a = m / ep.rb_div;
   if (ep.rb_mode == 1) return a;
   if (ep.rb_mode == 2) return a % ep.rb_mod;
-  return (a * ep.rb_mod + m % ep.rb_mod) % ep.rb_B;
+  return (a * ep.rb_mod + m % ep.rb_mod + ep.rb_off) % ep.rb_B;
 }
 
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {  // (the dynamic-smem pointers are generic: be explicit)

@@ -64,7 +64,7 @@ __device__ __forceinline__ int rowbias_index(const ctrlv_epilogue& ep, int m) {
   int a = m / ep.rb_div;
   if (ep.rb_mode == 1) return a;
   if (ep.rb_mode == 2) return a % ep.rb_mod;
-  return (a * ep.rb_mod + m % ep.rb_mod) % ep.rb_B;
+  return (a * ep.rb_mod + m % ep.rb_mod + ep.rb_off) % ep.rb_B;
 }
 
 // residual rows of one chunk, fetched BEFORE the TMEM load so their latency overlaps it
@@ -887,7 +887,7 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   if (p.ep.rb_mode != 0)
     CTRLV_CHECK_ARG(p.ep.rowbias != nullptr && p.ep.rb_div > 0, "igemm: rowbias mode without table");
   if (p.ep.rb_mode == 2 || p.ep.rb_mode == 3)
-    CTRLV_CHECK_ARG(p.ep.rb_mod > 0 && (p.ep.rb_mode == 2 || p.ep.rb_B > 0), "igemm: bad rowbias modulus");
+    CTRLV_CHECK_ARG(p.ep.rb_mod > 0 && (p.ep.rb_mode == 2 || p.ep.rb_B > 0) && p.ep.rb_off >= 0, "igemm: bad rowbias modulus");
   if (p.ep.gn_sums) {
     CTRLV_CHECK_ARG(!p.ep.geglu && p.ep.out != nullptr && p.ep.n_store == 0 && d->N % p.BN == 0,
                     "igemm: GroupNorm statistics need a full-width bf16 output without GEGLU");

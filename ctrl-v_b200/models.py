@@ -501,12 +501,9 @@ class _Transformer:
         elif self.order == "s_major":  # diffusers 0.27.2: context of row (b, s) is ctx[(b*S + s) % B]
             # over the WHOLE batch (vB rows); a branch-sharded process owns global rows b0 .. b0+B-1, so
             # its local index (b*S + s) is offset by b0*S
-            # — a rotation by (b0*S) % vB, which is 0 for every legal geometry: vB = 2*B_local, b0 = branch*B_local and
-            # S = h*w is even (h, w are multiples of 8), so the table is used as is
-            if (aux.b0 * S) % aux.vB:
-                raise NotImplementedError("branch-sharded S-major time_context with an odd number of sites")
+            # (an index offset, `rb_off`: no rotated copy of the table)
             ctx_t = aux.ctx_all[:, self.tattn2.off:self.tattn2.off + self.C]
-            kw = dict(rb_mode=3, rb_div=T * S, rb_mod=S, rb_B=aux.vB)
+            kw = dict(rb_mode=3, rb_div=T * S, rb_mod=S, rb_B=aux.vB, rb_off=(aux.b0 * S) % aux.vB)
         else:
             ctx_t = aux.ctx[:, self.tattn2.off:self.tattn2.off + self.C]
             kw = dict(rb_mode=1, rb_div=T * S)

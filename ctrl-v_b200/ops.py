@@ -103,7 +103,8 @@ class GNStats:
 
 
 def make_ep(out=None, out_f32=None, bias=None, rowbias=None, rb_mode=0, rb_div=1, rb_mod=1, rb_B=1,
-            geglu=False, s_acc=1.0, res1=None, s_res1=1.0, res2=None, s_res2=1.0, n_store=0, gn=None) -> Epilogue:
+            geglu=False, s_acc=1.0, res1=None, s_res1=1.0, res2=None, s_res2=1.0, n_store=0, gn=None,
+            rb_off=0) -> Epilogue:
     """gn = (GNStats, c_off): also accumulate the statistics of `out` for the GroupNorm that consumes it,
     `out` being channels c_off.. of that norm's (possibly concatenated) input."""
     ep = Epilogue()
@@ -119,6 +120,7 @@ def make_ep(out=None, out_f32=None, bias=None, rowbias=None, rb_mode=0, rb_div=1
         ep.ld_rowbias = rowbias.stride(0)
     ep.rowbias = _p(rowbias)
     ep.rb_mode, ep.rb_div, ep.rb_mod, ep.rb_B = rb_mode if rowbias is not None else 0, rb_div, rb_mod, rb_B
+    ep.rb_off = rb_off
     ep.geglu = 1 if geglu else 0
     ep.s_acc = s_acc
     for name, t in (("res1", res1), ("res2", res2), ("out", out)):

@@ -75,8 +75,9 @@ int ctrlv_memset_zero(void* ptr, int64_t bytes, void* stream);
  * cross-attention (a per-sample vector); ControlNet `* conditioning_scale`
  * (controlnet.py:343-344).
  *   rb_mode 0: no rowbias        1: ridx = m / rb_div        2: ridx = (m / rb_div) % rb_mod
- *   rb_mode 3: ridx = ((m / rb_div) * rb_mod + m % rb_mod) % rb_B   (diffusers-0.27.2
- *              S-major `time_context` broadcast)
+ *   rb_mode 3: ridx = ((m / rb_div) * rb_mod + m % rb_mod + rb_off) % rb_B   (diffusers-0.27.2
+ *              S-major `time_context` broadcast; rb_off = offset of this process's rows in the
+ *              whole batch's site sequence when the CFG branches are sharded over two processes)
  * ---------------------------------------------------------------------------------------- */
 typedef struct ctrlv_epilogue {
   const float* bias;    /* [N] fp32 or NULL */
@@ -109,6 +110,7 @@ typedef struct ctrlv_epilogue {
    * gn_c_off % 8 == 0, a bf16 `out`, no GEGLU, n_store == 0. */
   void* gn_sums;     /* int64 [gn_rep][gn_units][32][2] or NULL */
   int32_t gn_rows_per_unit, gn_cg, gn_c_off, gn_units, gn_rep;
+  int32_t rb_off;    /* rb_mode 3 only (see above); 0 otherwise */
 } ctrlv_epilogue;
 
 /* One operand source of the implicit GEMM: a channels-last view [Z][Y][X][C] with element
