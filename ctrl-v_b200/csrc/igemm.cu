@@ -776,9 +776,12 @@ static int choose_bn(int N, long long tiles_m, int num_sms) {
 
 // CTA pairs (cta_group::2) or single CTAs for a problem (see the comment at the call site)
 static int choose_cg(int BN, int N, int tiles_m, int kblocks) {
+  // refit on the round-2 sweep (profiles/r02_igemm_tile_sweep.json, after the MMA warp started issuing several
+  // k-blocks per round): pairs also pay for the level-3 problems (10 m-tiles) from K = 1280 on and for the
+  // K = 640 projections from N = 1920 on
   return (BN % 32 == 0 && N % BN == 0 &&
-          ((tiles_m >= 16 && (kblocks >= 20 || (kblocks >= 10 && N >= 2560))) ||
-           (tiles_m >= 8 && kblocks >= 100)))  // (few m-tiles: only the long-K convs gain)
+          ((tiles_m >= 16 && (kblocks >= 20 || (kblocks >= 10 && N >= 1920))) ||
+           (tiles_m >= 8 && kblocks >= 20 && (N >= 2560 || kblocks >= 60))))
              ? 2 : 1;
 }
 

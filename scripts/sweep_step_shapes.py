@@ -29,27 +29,34 @@ def t(fn, n=5):
         ts.append(e0.elapsed_time(e1) * 1e3)
     return sorted(ts)[len(ts) // 2]
 def rnd(*s): return torch.randn(*s, device=dev).to(BF)
+def gn_arg(flag, M, N):
+    if not flag or not ops.GNStats.fusable(N):
+        return None
+    units = 28 if M % 28 == 0 else 1
+    return (ops.GNStats(torch.zeros(ops.GNStats.numel(units), dtype=torch.int64, device=dev), units, M // units, N), 0)
 def make(op, key):
     if op == "linear":
-        M, K, N, geglu, r1, r2 = key
+        M, K, N, geglu, r1, r2, gn = key
         a = rnd(M, K); wt = (torch.randn(N, K, device=dev) / K ** 0.5).to(BF); b = torch.randn(N, device=dev)
         No = N // 2 if geglu else N
         kw = dict(bias=b, out=torch.empty(M, No, device=dev, dtype=BF), geglu=geglu)
         if r1: kw["res1"] = rnd(M, No)
         if r2: kw["res2"] = rnd(M, No)
+        kw["gn"] = gn_arg(gn, M, No)
         return (lambda: ops.linear(a, wt, **kw)), N
     if op == "conv3x3":
-        F_, H, W, stride, Cin, SC, N = key
+        F_, H, W, stride, Cin, SC, N, gn = key
         x = rnd(F_ * H * W, Cin); kk = 9 * Cin + SC
         wt = (torch.randn(N, kk, device=dev) / kk ** 0.5).to(BF); b = torch.randn(N, device=dev)
-        kw = dict(bias=b, stride=stride)
+        kw = dict(bias=b, stride=stride, gn=gn_arg(gn, F_ * (H // stride) * (W // stride), N))
         if SC: kw["sc0"] = rnd(F_ * H * W, SC)
         return (lambda: ops.conv3x3(x, F_, H, W, wt, **kw)), N
     if op == "conv_t3":
-        B, T_, HW, C, N = key
+        B, T_, HW, C, N, gn = key
         x = rnd(B * T_ * HW, C); wt = (torch.randn(N, 3 * C, device=dev) / (3 * C) ** 0.5).to(BF); b = torch.randn(N, device=dev)
         r = rnd(B * T_ * HW, N)
-        return (lambda: ops.conv_t3(x, B, T_, HW, wt, bias=b, res1=r)), N
+        g_ = gn_arg(gn, B * T_ * HW, N)
+        return (lambda: ops.conv_t3(x, B, T_, HW, wt, bias=b, res1=r, gn=g_)), N
     if op == "upconv3x3":
         F_, H, W, C, N = key
         x = rnd(F_ * H * W, C); wp = ops.pack_upconv3x3(torch.randn(N, C, 3, 3, device=dev) / (9 * C) ** 0.5); b = torch.randn(N, device=dev)

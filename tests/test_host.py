@@ -273,7 +273,8 @@ int main() {
 
 def test_tile_plan_heuristics_cpu():
     """ctrlv_igemm_plan (no CUDA calls): the n-tile / cta_group choices for the step's characteristic
-    problems on a 148-SM device, as measured best in profiles/r01_igemm_tile_sweep.json."""
+    problems on a 148-SM device, as measured best in profiles/r01_igemm_tile_sweep.json and, after the MMA warp
+    started issuing several k-blocks per round, profiles/r02_igemm_tile_sweep.json."""
     from ctrlv_b200 import _lib
     lib = _lib.load(build_if_missing=False)
 
@@ -291,13 +292,16 @@ def test_tile_plan_heuristics_cpu():
     assert plan(71680, 1, 1, 320, 2560)[1:] == (256, 1)
     # level-2 GEGLU (was BN=128 before the cost-model refit: 115 -> 86 us), level-1 QKV, level-1 residual linear
     assert plan(4480, 1, 1, 1280, 10240)[1:] == (256, 2)
-    assert plan(17920, 1, 1, 640, 1920)[1:] == (192, 1)
+    assert plan(17920, 1, 1, 640, 1920)[1:] == (192, 2)   # r02 sweep: pairs 48-50 us, single CTAs 52-54 us
     assert plan(17920, 1, 1, 640, 640)[1:] == (160, 1)
     # 3x3 convs: level 0 (K = 2880) pairs; level 3 (9 m-tiles, K = 11520) pairs since the refit
     box, bn, cg = plan(64, 40, 28, 2880, 320)
     assert box[0] * box[1] * box[2] <= 128 and (bn, cg) == (160, 2)
     assert plan(8, 5, 28, 11520, 1280)[2] == 2
-    # tiny M, short K: single CTA
+    # level 3 (10 m-tiles): pairs for the long-K problems since the r02 refit (conv(3,1,1) 31.6 -> 27.7 us,
+    # Linear 5120 -> 1280 35.8 -> 29.7 us); tiny M with short K and narrow N stays on single CTAs
+    assert plan(40, 14, 2, 3840, 1280)[2] == 2
+    assert plan(1120, 1, 1, 5120, 1280)[2] == 2
     assert plan(1120, 1, 1, 1280, 1280)[2] == 1
     # the box never exceeds one 128-row MMA tile and covers the row space
     for X, Y, Z in ((64, 40, 28), (16, 10, 28), (2560, 14, 2), (7, 3, 5)):
