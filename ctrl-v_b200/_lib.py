@@ -49,6 +49,8 @@ class Epilogue(C.Structure):
         ("gn_units", C.c_int32),
         ("gn_rep", C.c_int32),
         ("rb_off", C.c_int32),
+        ("splitk_ws", C.c_void_p),
+        ("splitk_bytes", C.c_int64),
     ]
 
 
@@ -100,6 +102,7 @@ SIGNATURES = {
     "ctrlv_igemm": (_I, [C.POINTER(IgemmDesc), _P]),
     "ctrlv_igemm_plan": (_I, [C.POINTER(IgemmDesc), _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ctrlv_igemm_override": (_I, [_I, _I, _I]),
+    "ctrlv_igemm_streamk": (_I, [_I]),
     "ctrlv_linear": (_I, [_P, _L, _I, _I, _P, _I, C.POINTER(Epilogue), _P]),
     "ctrlv_feedforward": (_I, [_P, _L, _I, _I, _P, _P, _P, C.POINTER(Epilogue), _P]),
     "ctrlv_feedforward_override": (_I, [_I]),

@@ -57,7 +57,46 @@ struct IgemmParams {
   int m_tiles;    // tiles_x * tiles_y * tiles_z
   int mma_batch;  // k-blocks per round of the MMA warp (<= kMmaBatch, <= stages)
   FastDiv fd_rpu, fd_cg;  // GroupNorm statistics: division by rows per unit / channels per group
+  // stream-K schedule (igemm_kernel<CG, true>): the tiles_total * kblocks k-blocks of the problem, tile-major, are
+  // dealt to the CTAs (pairs) as contiguous ranges of sk_per k-blocks
+  int sk_per, sk_total;
+  FastDiv fd_kb, fd_per;  // division by kblocks / sk_per
+  float* sk_part;         // fp32 partial tiles [gridDim.x * 2][128][BN]
   ctrlv_epilogue ep;
+};
+
+// ---- work schedule ------------------------------------------------------------------------------
+// SK = false: whole tiles, dealt round-robin to the CTAs (pairs).  SK = true (stream-K): CTA g owns the k-blocks
+// [g * sk_per, (g + 1) * sk_per) of the tile-major k-block sequence, i.e. the tail of one tile, whole tiles, the
+// head of another — every SM gets the same amount of tensor work whatever the tile count.
+template <bool SK>
+struct WorkIter {
+  int a, b, c;  // SK: position, end of the range, -;  !SK: next tile, stride, tiles_total
+  __device__ __forceinline__ void init(const IgemmParams& p, int g, int ng) {
+    if (SK) {
+      a = g * p.sk_per;
+      b = min(p.sk_total, a + p.sk_per);
+      c = 0;
+    } else {
+      a = g; b = ng; c = p.tiles_total;
+    }
+  }
+  // next unit of work: k-blocks [kb0, kb1) of `tile`
+  __device__ __forceinline__ bool next(const IgemmParams& p, int& tile, int& kb0, int& kb1) {
+    if (SK) {
+      if (a >= b) return false;
+      tile = (int)fd_div((uint32_t)a, p.fd_kb);
+      kb0 = a - tile * p.kblocks;
+      kb1 = min(p.kblocks, kb0 + (b - a));
+      a += kb1 - kb0;
+      return true;
+    } else {
+      if (a >= c) return false;
+      tile = a; kb0 = 0; kb1 = p.kblocks;
+      a += b;
+      return true;
+    }
+  }
 };
 
 __device__ __forceinline__ int rowbias_index(const ctrlv_epilogue& ep, int m) {
@@ -377,21 +416,69 @@ __device__ __forceinline__ void ep_finish(float* v, const ctrlv_epilogue& ep, lo
   }
 }
 
+constexpr int kSkMaxContrib = 4;  // most CTAs (pairs) that share one tile (the launcher sizes the k-ranges accordingly)
+// 256-bit load that observes other SMs' stores of this launch (L2, never L1); p 32-byte aligned
+__device__ __forceinline__ void ld_global_coherent_v8(const void* p, uint32_t* v) {
+  asm volatile("ld.relaxed.gpu.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p)
+               : "memory");
+}
+
+// stream-K: where the fp32 partial tiles of one output tile lie (one slot per contributing CTA, see igemm_kernel)
+struct SkParts {
+  const float* base;  // p.sk_part + this thread's (chunk-independent) row offset
+  size_t slot_elems;  // 128 * BN
+  int gf, gl;         // first / last contributing CTA (pair)
+  int w_first;        // slot parity of contributor gf (every later contributor starts inside the tile: parity 0)
+  int cg, crank;
+  __device__ __forceinline__ const float* slot(int g) const {
+    return base + (size_t)((g * 2 + (g == gf ? w_first : 0)) * cg + crank) * slot_elems;
+  }
+};
+
 // one 32-column accumulator chunk of one row: TMEM load, bias, (GEGLU), residual, store
-template <bool GEGLU>
+// WS: the accumulator is the sum of the tile's stream-K partials (fixed contributor order: reproducible) instead
+template <bool GEGLU, bool WS = false>
 __device__ __forceinline__ void ep_chunk(const ctrlv_epilogue& ep, uint32_t taddr, long long m, bool valid, int n0,
                                          int n_store, float* sb, uint4* wst, const float* rb, float bv,
                                          const ResPrefetch<GEGLU ? 16 : 32>& pf,
                                          const EpRows<GEGLU ? 16 : 32>& rows, const GnTile& gn, const IgemmParams& p,
-                                         bool rowown) {
+                                         bool rowown, const SkParts* sk = nullptr, int sk_off = 0) {
   constexpr int NV = GEGLU ? 16 : 32;
   uint32_t raw[32];
-  tmem_ld32(taddr, raw);
+  if (WS) {
+    // two half-chunks of 16 columns; the loads of ALL contributors of a half (<= kSkMaxContrib x two 256-bit
+    // loads, whole sectors, L2-coherent) are in flight together — the fix-up is a chain of L2 round trips
+    const int nc = sk->gl - sk->gf + 1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t t[kSkMaxContrib][16];
+#pragma unroll
+      for (int i = 0; i < kSkMaxContrib; ++i) {
+        if (i < nc) {
+          const float* src = sk->slot(sk->gf + i) + sk_off + 16 * h;
+          ld_global_coherent_v8(src, t[i]);
+          ld_global_coherent_v8(src + 8, t[i] + 8);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = __uint_as_float(t[0][j]);  // contributor order: the sum is the same from run to run
+#pragma unroll
+        for (int i = 1; i < kSkMaxContrib; ++i)
+          if (i < nc) a += __uint_as_float(t[i][j]);
+        raw[16 * h + j] = __float_as_uint(a);
+      }
+    }
+  } else {
+    tmem_ld32(taddr, raw);
+  }
   // bias (+ warp-uniform rowbias): lane j fetched column j; broadcast through this warp's smem row
   __syncwarp();  // previous chunk's readers are done with the row
   sb[threadIdx.x & 31] = bv;
   __syncwarp();
-  tmem_ld_wait();
+  if (!WS) tmem_ld_wait();
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -464,7 +551,7 @@ __device__ __forceinline__ void ep_tile(const ctrlv_epilogue& ep, uint64_t* tful
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) shares
 // one 256-row x BN tile: each CTA loads its own 128 A rows and HALF of the B tile, the leader issues
 // M=256 MMAs that read both halves — halves the shared-memory and L2 traffic of the B operand.
-template <int CG>
+template <int CG, bool SK>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -511,7 +598,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   // clusters; inside a pair CTA r owns m-tile CG*super + r
   const int unit0 = (int)blockIdx.x / CG;
   const int nunits = (int)gridDim.x / CG;
-  const int nloc = (p.tiles_total - unit0 + nunits - 1) / nunits;
   // register reallocation between the warpgroups: each warpgroup executes ONE setmaxnreg at the head of
   // its role branch (ptxas budgets the code below it accordingly)
   if (warp < kFirstEpiWarp) {
@@ -521,8 +607,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     {  // warp-uniform loop, one elected lane issues (see the MMA issuer below)
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < nloc; ++it) {
-        const int tile = unit0 + it * nunits;
+      WorkIter<SK> wi;
+      wi.init(p, unit0, nunits);
+      int tile, kb0, kb1;
+      while (wi.next(p, tile, kb0, kb1)) {
         uint32_t q_, nt_, tx_, ty_, tz_;
         fd_divmod((uint32_t)tile, p.fd_n, q_, nt_);
         fd_divmod(q_ * CG + crank, p.fd_x, q_, tx_);
@@ -530,10 +618,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const int nt = (int)nt_, tx = (int)tx_, ty = (int)ty_;
         const int tz = (int)tz_;  // may run past tiles_z for the odd tail: TMA zero-fills
         const int x0 = tx * p.bx, y0 = ty * p.by, z0 = tz * p.bz;
-        int kb = 0;
+        int kbs = 0;  // first k-block of segment s
         for (int s = 0; s < p.nseg; ++s) {
           const IgemmSeg sg = p.seg[s];
-          for (int ch = 0; ch < sg.nchunk; ++ch, ++kb) {
+          const int ch0 = SK ? max(0, kb0 - kbs) : 0;
+          const int ch1 = SK ? min(sg.nchunk, kb1 - kbs) : sg.nchunk;
+          for (int ch = ch0; ch < ch1; ++ch) {
+            const int kb = kbs + ch;
             mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
             uint8_t* sb = sa + kBM * kBK * 2;
@@ -556,6 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
               phase ^= 1;
             }
           }
+          kbs += sg.nchunk;
         }
       }
     }
@@ -568,7 +660,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const uint32_t idesc = make_idesc(kBM * CG, p.BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < nloc; ++it) {
+      WorkIter<SK> wi;
+      wi.init(p, unit0, nunits);
+      int tile, kb0, kb1;
+      for (int it = 0; wi.next(p, tile, kb0, kb1); ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait_relaxed(&tempty_bar[as], aphase ^ 1);
@@ -578,8 +673,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         // 400-600 cycles of a single warp's dependent uniform-datapath work) then carries 4 * kMmaBatch MMAs.
         // With one k-block per round the issue stream outlasted the tensor work of every tile narrower than 256
         // columns (a 64-wide k-block of a 128-column tile is 256 tensor cycles).
-        for (int kb = 0; kb < p.kblocks; kb += p.mma_batch) {
-          const int nb = min(p.mma_batch, p.kblocks - kb);
+        for (int kb = kb0; kb < kb1; kb += p.mma_batch) {
+          const int nb = min(p.mma_batch, kb1 - kb);
           int st[kMmaBatch];
           {
             int s_ = stage;
@@ -604,9 +699,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 for (int k = 0; k < kBK / 16; ++k) {
                   // advance 32 bytes (16 bf16) inside the 128B swizzle atom: +2 in the >>4 address field
                   if (CG == 1)
-                    umma_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)(((kb + b) | k) != 0));
+                    umma_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)(((kb - kb0 + b) | k) != 0));
                   else
-                    umma_ss_cg2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)(((kb + b) | k) != 0));
+                    umma_ss_cg2(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)(((kb - kb0 + b) | k) != 0));
                 }
                 if (CG == 1) umma_commit(&empty_bar[st[b]]);
                 else umma_commit_cg2(&empty_bar[st[b]]);
@@ -648,8 +743,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const int ix = r % p.bx;
     const int iy = (r / p.bx) % p.by;
     const int iz = r / (p.bx * p.by);
-    for (int it = 0; it < nloc; ++it) {
-      const int tile = unit0 + it * nunits;
+    WorkIter<SK> wi;
+    wi.init(p, unit0, nunits);
+    int tile, kb0, kb1;
+    for (int it = 0; wi.next(p, tile, kb0, kb1); ++it) {
       uint32_t q_, nt_, tx_, ty_, tz_;
       fd_divmod((uint32_t)tile, p.fd_n, q_, nt_);
       fd_divmod(q_ * CG + crank, p.fd_x, q_, tx_);
@@ -678,7 +775,32 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       float* sbias = wbias[warp - kFirstEpiWarp];
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
       uint4* wst = wstage[warp - kFirstEpiWarp];
-      if (ep.geglu)
+      if (SK && (kb0 != 0 || kb1 != p.kblocks)) {
+        // ---- a k-range of a split tile: park the fp32 partial; igemm_fixup_kernel sums the parts and finishes ----
+        const int first_tile = (int)fd_div((uint32_t)(unit0 * p.sk_per), p.fd_kb);
+        const size_t slot_elems = (size_t)kBM * p.BN;
+        float* mine = p.sk_part + (size_t)((unit0 * 2 + (tile == first_tile ? 0 : 1)) * CG + (int)crank) * slot_elems;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        for (int c = sub; c < p.BN / 32; c += kEpiWarps / 4) {
+          uint32_t raw[32];
+          tmem_ld32(t_row + (uint32_t)(c * 32), raw);
+          tmem_ld_wait();
+          float* dst = mine + (size_t)(c * kBM + r) * 32;  // 128 bytes per lane: four whole-sector 256-bit stores
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+            st_global_v8(dst + 8 * h, raw[8 * h], raw[8 * h + 1], raw[8 * h + 2], raw[8 * h + 3], raw[8 * h + 4],
+                         raw[8 * h + 5], raw[8 * h + 6], raw[8 * h + 7]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 1) mbar_arrive(&tempty_bar[as]);
+          else mbar_arrive_cluster(as ? tempty_lead1 : tempty_lead0);
+        }
+        continue;
+      }
+      if (!SK && ep.geglu)  // (the stream-K schedule is never chosen for a GEGLU epilogue)
         ep_tile<true>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform, p, false);
       else
         ep_tile<false>(ep, &tfull_bar[as], aphase, t_row, m, nt * p.BN, p.N, p.BN, n_store, valid, sub, sbias, wst, rb, rb_uniform, p, rowown);
@@ -702,6 +824,77 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   }
 }
 
+// Stream-K fix-up, launched behind igemm_kernel<CG, true>: one 128-thread block per (split tile, CTA of the pair,
+// 32-column chunk), thread = accumulator row as in the epilogue warps.  It adds the tile's fp32 partials in
+// contributor order (no atomics: the sum is the same from run to run) and runs the ordinary fused epilogue on it.
+// Whole tiles were finished by the GEMM kernel's own epilogue: their blocks exit at once.
+__global__ void __launch_bounds__(128) igemm_fixup_kernel(const __grid_constant__ IgemmParams p) {
+  __shared__ __align__(16) float wbias[4][32];
+  __shared__ __align__(16) uint4 wstage[4][128];
+  pdl_trigger();
+  const int nch = p.BN / 32;
+  int b = (int)blockIdx.x;
+  const int c = b % nch; b /= nch;
+  const int crank = b % p.cg;
+  const int tile = b / p.cg;
+  SkParts sk;
+  sk.gf = (int)fd_div((uint32_t)(tile * p.kblocks), p.fd_per);
+  sk.gl = (int)fd_div((uint32_t)((tile + 1) * p.kblocks - 1), p.fd_per);
+  // (every block waits for the GEMM kernel, also the ones with nothing to do: this grid must not complete — and
+  // release ITS dependents — before the whole tiles written by the GEMM kernel's own epilogue are complete)
+  if (sk.gf == sk.gl) {
+    pdl_wait();
+    return;
+  }
+  sk.base = p.sk_part;
+  sk.slot_elems = (size_t)kBM * p.BN;
+  sk.w_first = ((int)fd_div((uint32_t)(sk.gf * p.sk_per), p.fd_kb) == tile) ? 0 : 1;
+  sk.cg = p.cg; sk.crank = crank;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = threadIdx.x;
+  const ctrlv_epilogue& ep = p.ep;
+  const int n_store = ep.n_store > 0 ? ep.n_store : p.N;
+  const bool rowown = CTRLV_EPI_ROWOWN && ep.gn_sums == nullptr && ep.out != nullptr && (ep.ld_out % 16) == 0 &&
+                      (reinterpret_cast<uintptr_t>(ep.out) & 31) == 0 &&
+                      (ep.res1 == nullptr || ((ep.ld_res1 % 16) == 0 && (reinterpret_cast<uintptr_t>(ep.res1) & 31) == 0));
+  uint32_t q_, nt_, tx_, ty_, tz_;
+  fd_divmod((uint32_t)tile, p.fd_n, q_, nt_);
+  fd_divmod(q_ * (uint32_t)p.cg + (uint32_t)crank, p.fd_x, q_, tx_);
+  fd_divmod(q_, p.fd_y, tz_, ty_);
+  const int ix = r % p.bx, iy = (r / p.bx) % p.by, iz = r / (p.bx * p.by);
+  const int x = (int)tx_ * p.bx + ix, y = (int)ty_ * p.by + iy, z = (int)tz_ * p.bz + iz;
+  const bool valid = (iz < p.bz) && (x < p.X) && (y < p.Y) && (z < p.Z);
+  const long long m = ((long long)z * p.oY + y * p.omy + p.ooy) * p.oX + x * p.omx + p.oox;
+  const int n0 = (int)nt_ * p.BN + c * 32;
+  const float* rb = nullptr;
+  const float* rb_uniform = nullptr;
+  if (ep.rb_mode != 0) {
+    const int my_ridx = valid ? rowbias_index(ep, (int)m) : -1;
+    int ref = my_ridx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ref = max(ref, __shfl_xor_sync(0xffffffffu, ref, o));
+    const bool uni = __all_sync(0xffffffffu, my_ridx < 0 || my_ridx == ref);
+    if (uni && ref >= 0) rb_uniform = ep.rowbias + (size_t)ref * ep.ld_rowbias;
+    else if (valid) rb = ep.rowbias + (size_t)my_ridx * ep.ld_rowbias;
+  }
+  pdl_wait();  // the partial tiles (and the residual rows / row-bias table of chained launches) are complete from here
+  float bv = 0.f;  // lane j: bias (+ warp-uniform rowbias) of column n0 + j
+  if (n0 + lane < p.N) {
+    if (ep.bias) bv = __ldg(ep.bias + n0 + lane);
+    if (rb_uniform) bv += __ldg(rb_uniform + n0 + lane);
+  }
+  EpRows<32> rows;
+  rows.init(m, valid);
+  GnTile gn;
+  gn.u0 = -1; gn.multi = false;
+  if (ep.gn_sums) gn.init(p, m, valid);
+  ResPrefetch<32> pf;
+  pf.issue(ep, rows, n0, n_store, n0, p.N, rowown, m, valid);
+  __syncwarp();
+  ep_chunk<false, true>(ep, 0u, m, valid, n0, n_store, wbias[warp], wstage[warp], rb, bv, pf, rows, gn, p, rowown, &sk,
+                        (c * kBM + r) * 32);
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -719,10 +912,12 @@ static int device_props(const DevProps** out) {
     CTRLV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CTRLV_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     cudaFuncAttributes fa;
-    CTRLV_CUDA(cudaFuncGetAttributes(&fa, igemm_kernel<1>));
+    CTRLV_CUDA(cudaFuncGetAttributes(&fa, igemm_kernel<1, false>));
     smem -= (int)fa.sharedSizeBytes;  // static shared memory (barriers, epilogue tiles) counts against the limit
-    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CTRLV_CUDA(cudaFuncSetAttribute(igemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dp.max_smem = smem;
     dp.sms = sms;
   }
@@ -732,6 +927,22 @@ static int device_props(const DevProps** out) {
 
 // tile-plan overrides for tuning sweeps (ctrlv_igemm_override; 0 = heuristic)
 static int g_force_bn = 0, g_force_cg = 0, g_force_stages = 0;
+static int g_streamk_mode = 0;  // ctrlv_igemm_streamk: 0 = heuristic, 1 = never, 2 = whenever the problem allows it
+
+constexpr int kSkMinKblocks = 16;           // shorter K loops are epilogue-paced: nothing to balance
+
+// Stream-K is worth its fix-up launch only where whole tiles fill the SMs badly AND the K loop is very long.
+// Measured on a B200 (profiles/r02_streamk_microbench.json, cold L2): conv3x3 5x8 2560 -> 1280 (K = 23040, 10 row
+// tiles) 90.8 -> 78.7 us; conv3x3 1280 -> 1280 (K = 11520) 52.1 -> 51.2; conv(3,1,1) (K = 3840) 25.4 -> 35.6; Linear
+// 1280 -> 1280 at M = 1120 16.4 -> 29.7.  These problems are not limited by idle SMs but by the L2 -> SM operand
+// stream (about 6300 B/clk for the whole chip): cutting K spreads the same bytes over more SMs and adds the partial
+// tiles and a second launch.  `slots` = CTAs (pairs) that run concurrently.
+static bool sk_wanted(int tiles_total, int slots, int kblocks) {
+  if (g_streamk_mode == 1 || kblocks < kSkMinKblocks) return false;
+  if (g_streamk_mode == 2) return true;
+  const int waves = (tiles_total + slots - 1) / slots;
+  return kblocks >= 256 && (double)tiles_total < 0.8 * (double)waves * slots && waves <= 2;
+}
 
 // choose the (bx, by, bz) row box (<= 128 rows) that wastes the fewest MMA rows
 static void choose_box(int X, int Y, int Z, int* bx, int* by, int* bz) {
@@ -837,6 +1048,41 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
   p.cg = choose_cg(p.BN, d->N, tiles_m, kblocks_pre);
   if (g_force_cg) p.cg = g_force_cg;
   p.tiles_total = ((tiles_m + p.cg - 1) / p.cg) * p.tiles_n;
+  // Stream-K (needs the caller's workspace, ctrlv_epilogue.splitk_ws): with every SM busy for the same number of
+  // k-blocks whatever the tile count, the widest tile is the cheapest — 256 columns, CTA pairs
+  bool sk = false;
+  if (d->ep.splitk_ws != nullptr && !d->ep.geglu && d->N % p.BN == 0 &&
+      sk_wanted(p.tiles_total, g_num_sms / p.cg, kblocks_pre)) {
+    int bn = p.BN, cg = p.cg;
+    if (!g_force_bn && d->bn <= 0) {
+      const int wide[] = {256, 192, 160, 128};
+      for (int w : wide)
+        if (d->N % w == 0) { bn = w; break; }
+    }
+    if (!g_force_cg && tiles_m >= 2) cg = 2;
+    const int tiles_n = d->N / bn;
+    const long long tt = (long long)((tiles_m + cg - 1) / cg) * tiles_n;
+    const long long total = tt * kblocks_pre;
+    int G = g_num_sms / cg;
+    if (total < (long long)G * 8) G = (int)(total / 8);  // at least 8 k-blocks per CTA
+    {  // a tile of K k-blocks starting anywhere inside a range of `per` touches <= ceil((per - 1 + K) / per) ranges
+      const long long per_min = (kblocks_pre - 1 + kSkMaxContrib - 2) / (kSkMaxContrib - 1);
+      if (G >= 1 && (total + G - 1) / G < per_min) G = (int)(total / per_min);
+    }
+    const long long need = (long long)G * cg * 2 * kBM * bn * (long long)sizeof(float);
+    if (G >= 2 && need <= d->ep.splitk_bytes && total < (1ll << 30) && tt * cg * (bn / 32) < (1ll << 30) &&
+        (reinterpret_cast<uintptr_t>(d->ep.splitk_ws) & 31) == 0) {
+      sk = true;
+      p.BN = bn; p.cg = cg;
+      p.tiles_n = tiles_n;
+      p.tiles_total = (int)tt;
+      p.sk_per = (int)((total + G - 1) / G);
+      p.sk_total = (int)total;
+      p.fd_kb = make_fastdiv((uint32_t)kblocks_pre);
+      p.fd_per = make_fastdiv((uint32_t)p.sk_per);
+      p.sk_part = reinterpret_cast<float*>(d->ep.splitk_ws);
+    }
+  }
   if (d->out_X > 0) {
     CTRLV_CHECK_ARG(d->out_Y > 0 && d->out_mul_x >= 1 && d->out_mul_y >= 1 && d->out_off_x >= 0 && d->out_off_y >= 0 &&
                         (d->X - 1) * d->out_mul_x + d->out_off_x < d->out_X && (d->Y - 1) * d->out_mul_y + d->out_off_y < d->out_Y,
@@ -916,12 +1162,17 @@ static int igemm_launch(const ctrlv_igemm_desc* d, cudaStream_t stream) {
 
   size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   const int threads = kThreads;
-  if (p.cg == 1) {
+  if (sk) {
+    const int G = (p.sk_total + p.sk_per - 1) / p.sk_per;  // CTAs (pairs) with a non-empty k-block range
+    if (p.cg == 1) CTRLV_CUDA(launch_pdl(igemm_kernel<1, true>, dim3(G), dim3(threads), smem, stream, p));
+    else CTRLV_CUDA(launch_cluster2(igemm_kernel<2, true>, dim3(2 * G), dim3(threads), smem, stream, p));
+    CTRLV_CUDA(launch_pdl(igemm_fixup_kernel, dim3(p.tiles_total * p.cg * (p.BN / 32)), dim3(128), (size_t)0, stream, p));
+  } else if (p.cg == 1) {
     int grid = p.tiles_total < g_num_sms ? p.tiles_total : g_num_sms;
-    CTRLV_CUDA(launch_pdl(igemm_kernel<1>, dim3(grid), dim3(threads), smem, stream, p));
+    CTRLV_CUDA(launch_pdl(igemm_kernel<1, false>, dim3(grid), dim3(threads), smem, stream, p));
   } else {
     const int pairs = p.tiles_total < g_num_sms / 2 ? p.tiles_total : g_num_sms / 2;
-    CTRLV_CUDA(launch_cluster2(igemm_kernel<2>, dim3(2 * pairs), dim3(threads), smem, stream, p));
+    CTRLV_CUDA(launch_cluster2(igemm_kernel<2, false>, dim3(2 * pairs), dim3(threads), smem, stream, p));
   }
   return CTRLV_OK;
 }
@@ -935,6 +1186,12 @@ extern "C" int ctrlv_igemm_override(int32_t bn, int32_t cta_group, int32_t stage
                       stages >= 0 && stages <= kMaxStages && stages != 1,
                   "igemm_override: bn=%d cta_group=%d stages=%d", bn, cta_group, stages);
   g_force_bn = bn; g_force_cg = cta_group; g_force_stages = stages;
+  return CTRLV_OK;
+}
+
+extern "C" int ctrlv_igemm_streamk(int32_t mode) {
+  CTRLV_CHECK_ARG(mode >= 0 && mode <= 2, "igemm_streamk: mode %d (0 = heuristic, 1 = never, 2 = whenever possible)", mode);
+  g_streamk_mode = mode;
   return CTRLV_OK;
 }
 

@@ -5,6 +5,7 @@ failure — there is no eager/PyTorch fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -102,6 +103,24 @@ class GNStats:
         return C_total % 32 == 0 and cg % 2 == 0 and cg >= 4
 
 
+# Stream-K workspaces of the implicit GEMM (ctrlv_epilogue.splitk_ws): fp32 partial-tile slots, two per CTA; one
+# workspace per (device, stream), because launches on different streams may run concurrently.
+# Off unless CTRLV_SPLITK=1: on the denoise step's shapes the schedule is measured level with whole tiles (step
+# 33.8 vs 33.7 ms, profiles/r02_streamk_microbench.json), so the product path keeps one launch per contraction.
+SPLITK = os.environ.get("CTRLV_SPLITK", "0") == "1"
+_sk_ws = {}
+
+
+def _splitk_workspace() -> torch.Tensor:
+    dev = torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream().cuda_stream)
+    ws = _sk_ws.get(key)
+    if ws is None:
+        nbytes = 2 * torch.cuda.get_device_properties(dev).multi_processor_count * (128 << 10)
+        ws = _sk_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    return ws
+
+
 def make_ep(out=None, out_f32=None, bias=None, rowbias=None, rb_mode=0, rb_div=1, rb_mod=1, rb_B=1,
             geglu=False, s_acc=1.0, res1=None, s_res1=1.0, res2=None, s_res2=1.0, n_store=0, gn=None,
             rb_off=0) -> Epilogue:
@@ -135,6 +154,9 @@ def make_ep(out=None, out_f32=None, bias=None, rowbias=None, rb_mode=0, rb_div=1
         _req(out_f32, torch.float32, "out_f32")
     ep.out_f32, ep.ld_out_f32 = _p(out_f32), (out_f32.stride(0) if out_f32 is not None else 0)
     ep.n_store = n_store
+    if SPLITK:
+        ws = _splitk_workspace()
+        ep.splitk_ws, ep.splitk_bytes = ws.data_ptr(), ws.numel()
     return ep
 
 

@@ -111,6 +111,15 @@ typedef struct ctrlv_epilogue {
   void* gn_sums;     /* int64 [gn_rep][gn_units][32][2] or NULL */
   int32_t gn_rows_per_unit, gn_cg, gn_c_off, gn_units, gn_rep;
   int32_t rb_off;    /* rb_mode 3 only (see above); 0 otherwise */
+  /* Optional stream-K workspace of the implicit GEMM (NULL: whole tiles only).  Problems whose tiles fill the SMs
+   * badly and whose K loop is long (the deepest UNet level: 10 row tiles on 148 SMs, K up to 25600) are cut along
+   * K as well: every SM runs the same number of k-blocks; the k-ranges of a shared tile are parked here as fp32
+   * partial tiles, and a second, small launch adds them up in contributor order (bit-reproducible, no atomics)
+   * and runs this epilogue on the sum.  32-byte aligned, splitk_bytes >= 2 * (number of SMs) * 128 KiB for every
+   * problem to qualify (37 MiB on a B200); needs no initialisation.  One workspace per stream: launches that
+   * may run concurrently must not share it. */
+  void* splitk_ws;
+  int64_t splitk_bytes;
 } ctrlv_epilogue;
 
 /* One operand source of the implicit GEMM: a channels-last view [Z][Y][X][C] with element
@@ -158,6 +167,9 @@ int ctrlv_igemm_plan(const ctrlv_igemm_desc* desc, int32_t num_sms, int32_t* box
 /* Tuning hook for tile sweeps (process-global, not for production use): force the n-tile width, the
  * cta_group and the pipeline depth of every following ctrlv_igemm launch; 0 = the launcher's heuristic. */
 int ctrlv_igemm_override(int32_t bn, int32_t cta_group, int32_t stages);
+/* Tuning / test hook (process-global): stream-K scheduling of launches that carry a workspace
+ * (ctrlv_epilogue.splitk_ws): 0 = the launcher's heuristic, 1 = never, 2 = whenever the problem allows it. */
+int ctrlv_igemm_streamk(int32_t mode);
 
 /* nn.Linear (diffusers Attention.to_q/k/v/to_out, FeedForward, proj_in/out, 1x1 convs incl. the
  * ControlNet zero-convs controlnet.py:148-185,331-339):  out[M][N] = A[M][K] * W[N][K]^T. */

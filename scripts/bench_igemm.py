@@ -7,6 +7,8 @@ import torch
 from ctrlv_b200 import ops
 BF, dev = torch.bfloat16, "cuda"
 tag = sys.argv[1] if len(sys.argv) > 1 else "run"
+# STREAMK=1: whole tiles only, 2: stream-K wherever the problem allows it (default 0: the launcher's heuristic)
+ops.lib().ctrlv_igemm_streamk(int(os.environ.get("STREAMK", "0")))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 def timeit(fn, iters=8):
@@ -72,10 +74,13 @@ CASES = [
     ("qkv L2 1280->3840", lambda: lin(4480, 1280, 3840), 14),
     ("lin L2 1280->1280 +res", lambda: lin(4480, 1280, 1280, res1=True, rowbias=True), 21),
     ("lin L3 1280->1280 +res", lambda: lin(1120, 1280, 1280, res1=True), 6),
+    ("down L3 5120->1280 +res", lambda: lin(1120, 5120, 1280, res1=True), 6),
+    ("qkv L3 1280->3840", lambda: lin(1120, 1280, 3840), 4),
     ("conv3x3 L0 320->320", lambda: conv(28, 40, 64, 320, 320), 8),
     ("conv3x3 L1 640->640", lambda: conv(28, 20, 32, 640, 640), 4),
     ("conv3x3 L2 1280->1280", lambda: conv(28, 10, 16, 1280, 1280), 5),
     ("conv3x3 L3 1280->1280", lambda: conv(28, 5, 8, 1280, 1280), 16),
+    ("conv3x3 L3 2560->1280", lambda: conv(28, 5, 8, 2560, 1280), 3),
     ("conv_t3 L0 320", lambda: convt(2, 14, 2560, 320, 320), 14),
     ("conv_t3 L1 640", lambda: convt(2, 14, 640, 640, 640), 14),
     ("conv_t3 L2 1280", lambda: convt(2, 14, 160, 1280, 1280), 14),

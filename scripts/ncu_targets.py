@@ -50,3 +50,10 @@ if which == "tattn":
     qkv = torch.randn(28 * 2560, 960, device=dev).to(BF)
     for _ in range(3): ops.attn_temporal(qkv, 2, 14, 2560, 5)
     torch.cuda.synchronize()
+if which == "sk":  # stream-K schedule on the level-3 problems (10 row tiles)
+    a = torch.randn(1120, 1280, device=dev).to(BF); w = (torch.randn(1280, 1280, device=dev) / 36).to(BF); b = torch.randn(1280, device=dev)
+    r = torch.randn(1120, 1280, device=dev).to(BF)
+    for _ in range(3): ops.linear(a, w, bias=b, res1=r)
+    x = torch.randn(28 * 5 * 8, 1280, device=dev).to(BF); w = (torch.randn(1280, 9 * 1280, device=dev) / 107).to(BF)
+    for _ in range(3): ops.conv3x3(x, 28, 5, 8, w, bias=b)
+    torch.cuda.synchronize()

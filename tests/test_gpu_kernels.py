@@ -470,3 +470,121 @@ def test_upsample2x_conv3x3_fused(ops, frames, H, W, C, N):
     got = ops.upsample2x_conv3x3(rows, frames, H, W, ops.pack_upconv3x3(w), bias=b)
     got = got.float().reshape(frames, 2 * H, 2 * W, N).permute(0, 3, 1, 2)
     assert rel(got, want) < 6e-3, rel(got, want)
+
+
+# ---- stream-K schedule of the implicit GEMM (ctrlv_epilogue.splitk_ws) -------------------------------------------
+def _sk_problem(ops, kind, geom, C, N, extra):
+    """-> (run(gn) launching the problem, fp32 reference rows, statistics geometry)"""
+    dev = "cuda"
+    if kind == "linear":
+        M = geom
+        a = torch.randn(M, C, device=dev).to(BF)
+        w = (torch.randn(N, C, device=dev) / C ** 0.5).to(BF)
+        b = torch.randn(N, device=dev)
+        r1 = torch.randn(M, N, device=dev).to(BF)
+        rb = torch.randn(3, N, device=dev)
+        div = max(M // 5, 1)
+        ref = 0.6 * (a.float() @ w.float().t() + b + rb[(torch.arange(M, device=dev) // div) % 3]) + 0.7 * r1.float()
+        run = lambda gn: ops.linear(a, w, bias=b, res1=r1, s_res1=0.7, s_acc=0.6, rowbias=rb, rb_mode=2, rb_div=div,
+                                    rb_mod=3, gn=gn)
+        return run, ref, (1, M)
+    if kind in ("conv3x3", "conv3x3_s2", "conv3x3_sc"):
+        F_, H, W = geom
+        stride = 2 if kind.endswith("s2") else 1
+        x = torch.randn(F_, C, H, W, device=dev).to(BF)
+        w = (torch.randn(N, C, 3, 3, device=dev) / (9 * C) ** 0.5).to(BF)
+        b = torch.randn(N, device=dev)
+        ref = F.conv2d(x.float(), w.float(), b, stride=stride, padding=1)
+        rows = lambda t: t.permute(0, 2, 3, 1).reshape(-1, t.shape[1]).contiguous()
+        wp, kw = _pack9(w), {}
+        if kind.endswith("sc"):  # second source (skip concat) is folded into x here; raw 1x1 shortcut appended to K
+            x2 = torch.randn(F_, 64, H, W, device=dev).to(BF)
+            ws = (torch.randn(N, 64, device=dev) / 8.0).to(BF)
+            ref = ref + F.conv2d(x2.float(), ws.float()[:, :, None, None])
+            wp = torch.cat([wp, ws], 1).contiguous()
+            kw["sc0"] = rows(x2)
+        xl = rows(x)
+        run = lambda gn: ops.conv3x3(xl, F_, H, W, wp, stride=stride, bias=b, gn=gn, **kw)
+        return run, rows(ref), (F_, (H // stride) * (W // stride))
+    B, T, HW = geom
+    x = torch.randn(B, C, T, HW, 1, device=dev).to(BF)
+    w = (torch.randn(N, C, 3, 1, 1, device=dev) / (3 * C) ** 0.5).to(BF)
+    b = torch.randn(N, device=dev)
+    res = torch.randn(B * T * HW, N, device=dev).to(BF)
+    ref = 0.5 * F.conv3d(x.float(), w.float(), b, padding=(1, 0, 0))[..., 0].permute(0, 2, 3, 1).reshape(-1, N) + 0.5 * res.float()
+    xl = x[..., 0].permute(0, 2, 3, 1).reshape(-1, C).contiguous()
+    wp = w[:, :, :, 0, 0].permute(0, 2, 1).reshape(N, 3 * C).contiguous()
+    run = lambda gn: ops.conv_t3(xl, B, T, HW, wp, bias=b, res1=res, s_res1=0.5, s_acc=0.5, gn=gn)
+    return run, ref, (B, T * HW)
+
+
+@pytest.mark.parametrize("kind,geom,C,N", [
+    ("linear", 1120, 1280, 1280),            # deepest UNet level: 10 row tiles
+    ("linear", 1000, 2048, 320),             # ragged M, 160-wide pair tiles
+    ("linear", 100, 1024, 64),               # ONE tile cut between two CTAs
+    ("linear", 4096, 1024, 1280),            # ranges spanning tail + head (+ whole tiles) of several tiles
+    ("linear", 130, 4096, 96),               # single CTAs would not pair: 2 row tiles, narrow ragged-N tile
+    ("conv3x3", (28, 5, 8), 1280, 1280),     # config-2 level-3 conv, K = 11520
+    ("conv3x3_sc", (6, 5, 8), 192, 128),     # shortcut segment at the end of the K loop
+    ("conv3x3_s2", (4, 10, 16), 256, 256),   # Downsample2D: four parity maps
+    ("conv_t3", (2, 14, 40), 1280, 1280),    # config-2 level-3 temporal conv
+    ("conv_t3", (1, 5, 24), 448, 64),
+])
+def test_streamk_schedule_matches_whole_tiles(ops, monkeypatch, kind, geom, C, N):
+    """The stream-K schedule (k-ranges per CTA, fp32 partials, fix-up launch) gives the reference result, agrees
+    with the whole-tile schedule up to the order of the fp32 partial sums, is bit-reproducible from run to run
+    (fixed reduction order, also with a dirty workspace), and accumulates the same GroupNorm statistics in its
+    fix-up epilogue."""
+    lib = ops.lib()
+    monkeypatch.setattr(ops, "SPLITK", True)  # every launch of this test carries a workspace
+    run, ref, (units, rows) = _sk_problem(ops, kind, geom, C, N, None)
+    C_total, c_off = 2 * N, N  # the output is the upper half of a concatenated norm input
+    fus = ops.GNStats.fusable(C_total)
+    try:
+        assert lib.ctrlv_igemm_streamk(1) == 0
+        whole = run(None)
+        assert lib.ctrlv_igemm_streamk(2) == 0
+        ops._splitk_workspace().fill_(0xFF)  # (NaN patterns: every partial that is read was written by this launch)
+        n0 = lib.ctrlv_launch_count()
+        y = run(None)
+        assert lib.ctrlv_launch_count() == n0 + 2  # GEMM + fix-up
+        st = _gn_table(ops, units, rows, C_total) if fus else None
+        y2 = run((st, c_off) if fus else None)
+        torch.cuda.synchronize()
+    finally:
+        lib.ctrlv_igemm_streamk(0)
+    assert rel(y, ref) < TOL_BF16
+    assert rel(y, whole) < 2e-3
+    assert torch.equal(y, y2)
+    if fus:
+        _gn_check(st, _gn_expected(y, units, rows, C_total, c_off), rows * (C_total // 32))
+
+
+def test_streamk_heuristic_splits_only_badly_filled_long_k_problems(ops, monkeypatch):
+    """Without a forced mode only a badly filled problem with a very long K loop is cut along K (the result then
+    differs from whole tiles by the order of the partial sums only); everything else keeps its whole-tile schedule
+    bit for bit, and so does every problem when no workspace is passed."""
+    lib = ops.lib()
+    monkeypatch.setattr(ops, "SPLITK", True)
+    for (M, K, N), launches in (((1120, 16384, 1280), 2), ((1120, 1280, 1280), 1), ((71680 // 4, 320, 320), 1),
+                                ((4480, 5120, 1280), 1)):
+        a = torch.randn(M, K, device="cuda").to(BF)
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(BF)
+        try:
+            lib.ctrlv_igemm_streamk(1)
+            whole = ops.linear(a, w)
+        finally:
+            lib.ctrlv_igemm_streamk(0)
+        n0 = lib.ctrlv_launch_count()
+        auto = ops.linear(a, w)
+        assert lib.ctrlv_launch_count() - n0 == launches
+        torch.cuda.synchronize()
+        assert rel(auto, whole) < 2e-3
+        if launches == 1:
+            assert torch.equal(auto, whole)
+    monkeypatch.setattr(ops, "SPLITK", False)
+    a = torch.randn(1120, 16384, device="cuda").to(BF)
+    w = (torch.randn(1280, 16384, device="cuda") / 128.0).to(BF)
+    n0 = lib.ctrlv_launch_count()
+    ops.linear(a, w)
+    assert lib.ctrlv_launch_count() - n0 == 1
