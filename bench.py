@@ -261,13 +261,13 @@ def class_rooflines(prof, peaks):
         return n, ms, fl, by
     n, ms, fl, _ = agg(("attn_spatial",))
     if ms > 0:
-        out["attention_spatial"] = {"bound": "tensor", "kernel": "ctrlv::attn2_kernel / attn_kernel<0>", "launches": n,
+        out["attention_spatial"] = {"bound": "tensor", "kernel": "ctrlv::attn2_kernel / attn_kernel", "launches": n,
                                     "ms_per_step": ms, "achieved": fl / ms / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
                                     "frac": fl / ms / 1e9 / tf_peak}
     for name, ops_, kern in (("groupnorm", ("groupnorm", "groupnorm_apply"),
                               "ctrlv::gn_apply_kernel (statistics from the producers' epilogues; gn_stats_kernel only where none)"),
                              ("layernorm", ("layernorm",), "ctrlv::layernorm_kernel"),
-                             ("attention_temporal", ("attn_temporal",), "ctrlv::attn_kernel<1>")):
+                             ("attention_temporal", ("attn_temporal",), "ctrlv::tattn_kernel")):
         n, ms, _, by = agg(ops_)
         if ms > 0:
             out[name] = {"bound": "hbm", "kernel": kern, "launches": n, "ms_per_step": ms, "achieved": by / ms / 1e6,

@@ -1,12 +1,13 @@
 // tcgen05 flash attention, head_dim 64, no mask — the core of diffusers' AttnProcessor2_0
 // (F.scaled_dot_product_attention) for both attention flavours of TransformerSpatioTemporalModel.
 //
-//  MODE 0, spatial : one CTA per (128-query tile, head, frame); keys/values streamed in blocks
-//                    of 128 through a 3-slot TMA ring; online softmax.
-//  MODE 1, temporal: sequences are the T frames of one spatial site.  G = 128/T sites are packed
+//  attn_kernel (spatial, short sequences): one CTA per (128-query tile, head, frame); keys/values
+//                    streamed in blocks of 128 through a 3-slot TMA ring; online softmax.
+//  attn2_kernel (spatial, S >= 160): two query tiles per CTA, P in TMEM (below).
+//  tattn_kernel (temporal): sequences are the T frames of one spatial site.  G = 128/T sites are packed
 //                    into one 128-row tile (row = t*G + g) fetched by ONE 4-D TMA box straight
 //                    from the [B][T][S][3C] projection buffer (no permute copies); a block-diagonal
-//                    mask (same site) restricts each query to its own T keys.  HBM-bound.
+//                    mask (same site) restricts each query to its own T keys.  HBM-bound (below).
 //
 //  S = Q K^T      : tcgen05.mma  M=128 N=128 K=64, both operands K-major from TMA (128B swizzle)
 //  softmax        : one thread per query row (TMEM lane == row): no shuffles; exp2 on raw scores
@@ -43,7 +44,6 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-template <int MODE>
 __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full, s_full, p_full, o_full;
@@ -63,12 +63,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   const int nkv = p.nkv;
   pdl_trigger();
 
-  if (MODE == 1) {
-    // the temporal box covers G*T < 128 rows; the rest must be zero (0 * garbage would be NaN)
-    uint4* z = reinterpret_cast<uint4*>(smem);
-    for (int i = threadIdx.x; i < 4 * kTile / 16; i += kAttnThreads) z[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async_smem();
-  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm);
     mbar_init(&q_full, 1);
@@ -95,10 +89,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
     if (lane == 0) {
       const int colq = head * 64, colk = p.C + head * 64, colv = 2 * p.C + head * 64;
       mbar_expect_tx(&q_full, (uint32_t)p.box_bytes);
-      if (MODE == 0)
-        tma_load_3d(sQ, &p.tm, &q_full, colq, blockIdx.x * 128, blockIdx.z);
-      else
-        tma_load_4d(sQ, &p.tm, &q_full, colq, blockIdx.x * p.G, 0, blockIdx.z);
+      tma_load_3d(sQ, &p.tm, &q_full, colq, blockIdx.x * 128, blockIdx.z);
       for (int n = 0; n < 2 * nkv; ++n) {
         const int slot = n % 3;
         const uint32_t ph = (uint32_t)((n / 3) & 1);
@@ -106,10 +97,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
         mbar_expect_tx(&kv_full[slot], (uint32_t)p.box_bytes);
         const int j = n >> 1;
         const int col = (n & 1) ? colv : colk;
-        if (MODE == 0)
-          tma_load_3d(sKV + slot * kTile, &p.tm, &kv_full[slot], col, j * 128, blockIdx.z);
-        else
-          tma_load_4d(sKV + slot * kTile, &p.tm, &kv_full[slot], col, blockIdx.x * p.G, 0, blockIdx.z);
+        tma_load_3d(sKV + slot * kTile, &p.tm, &kv_full[slot], col, j * 128, blockIdx.z);
       }
     }
   } else if (warp == 1) {
@@ -161,17 +149,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 #pragma unroll
     for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
-    const int rg = (MODE == 1) ? (r % p.G) : 0;
-    // temporal mode: the T keys of this row's site sit at columns rg + t*G (block-diagonal mask)
-    uint32_t tmask[4] = {0u, 0u, 0u, 0u};
-    if (MODE == 1) {
-      for (int t = 0; t < p.T; ++t) {
-        const int col = rg + t * p.G;
-        tmask[col >> 5] |= 1u << (col & 31);
-      }
-    }
-    auto chunk_mask = [&](int kv0, int c) -> uint32_t {
-      if (MODE == 1) return c == 0 ? tmask[0] : (c == 1 ? tmask[1] : (c == 2 ? tmask[2] : tmask[3]));
+    auto chunk_mask = [&](int kv0, int c) -> uint32_t {  // valid key columns of chunk c (ragged last block)
       const int nvalid = p.S - kv0 - c * 32;
       return nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << nvalid) - 1u));
     };
@@ -281,18 +259,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
     xsum[half][r] = l_run;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float inv = 1.0f / (l_run + xsum[half ^ 1][r]);
-    long long orow;
-    bool valid;
-    if (MODE == 0) {
-      const int s = blockIdx.x * 128 + r;
-      valid = s < p.S;
-      orow = (long long)blockIdx.z * p.S + s;
-    } else {
-      const int t = r / p.G;
-      const int s = blockIdx.x * p.G + rg;
-      valid = (t < p.T) && (s < p.S);
-      orow = ((long long)blockIdx.z * p.T + t) * p.S + s;
-    }
+    const int s = blockIdx.x * 128 + r;
+    const bool valid = s < p.S;
+    const long long orow = (long long)blockIdx.z * p.S + s;
     if (valid) {
       bf16* op = p.out + orow * p.C + head * 64 + half * 32;  // 64 B = two whole sectors, 256-bit stores
 #pragma unroll
@@ -311,6 +280,170 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Temporal attention (sequences = the T frames of one spatial site; one key block): the single-block special case
+// of attn_kernel<1>, shrunk so that FOUR CTAs share an SM instead of two.  The launch is a stream of short
+// dependent chains (TMA Q|K|V -> S = Q K^T -> masked softmax -> P -> O = P V -> store, about 6 us per CTA) with
+// almost no arithmetic (HBM-bound: 8 * rows * C bytes), so its speed is the number of chains in flight per SM:
+//   * 4 softmax warps (one per TMEM lane quarter, a thread owns a whole 128-column score row): no exchange between
+//     column halves, 192 threads, no running (max, sum, O) state in registers;
+//   * shared memory 48 KB: P (128 x 128 bf16) is written over Q | K once S has been computed;
+//   * TMEM 128 columns: O (64) is accumulated over the first half of S after every softmax warp has read S;
+//   * only the rows past G * T of the Q, K, V tiles are zeroed (the TMA box covers rows [0, G * T)).
+// ------------------------------------------------------------------------------------------
+constexpr int kTattnThreads = 64 + 128;  // TMA warp, MMA warp, 4 softmax warps
+constexpr int kTattnSmem = 3 * kTile + 1024;
+
+__global__ void __launch_bounds__(kTattnThreads, 4) tattn_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t qkv_full, s_full, p_full, o_full;
+  __shared__ uint32_t tmem_base_smem;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kTile;
+  uint8_t* sV = smem + 2 * kTile;
+  uint8_t* sP = smem;  // two [128 x 64] atoms over Q | K (dead once S = Q K^T is complete)
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  pdl_trigger();
+
+  {  // rows the box does not cover must be finite: 0 * garbage would be NaN in P V (V) and in the masked scores
+    const int row0 = p.G * p.T, nz = (128 - row0) * 8;  // 16-byte pieces per tile
+    for (int i = threadIdx.x; i < 3 * nz; i += kTattnThreads) {
+      const int tile = i / nz, rem = i - tile * nz;
+      *reinterpret_cast<uint4*>(smem + (size_t)tile * kTile + (size_t)(row0 + (rem >> 3)) * 128 + (rem & 7) * 16) =
+          make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm);
+    mbar_init(&qkv_full, 1);
+    mbar_init(&s_full, 1);
+    mbar_init(&p_full, 4);
+    mbar_init(&o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tS = tmem_base_smem;
+  const uint32_t tO = tS;  // O over S[:, 0:64)
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int colq = head * 64, colk = p.C + head * 64, colv = 2 * p.C + head * 64;
+      mbar_expect_tx(&qkv_full, (uint32_t)(3 * p.box_bytes));
+      tma_load_4d(sQ, &p.tm, &qkv_full, colq, blockIdx.x * p.G, 0, blockIdx.z);
+      tma_load_4d(sK, &p.tm, &qkv_full, colk, blockIdx.x * p.G, 0, blockIdx.z);
+      tma_load_4d(sV, &p.tm, &qkv_full, colv, blockIdx.x * p.G, 0, blockIdx.z);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc(128, 128, 0, 0);
+      const uint32_t idesc_pv = make_idesc(128, 64, 0, 1);  // B (= V) is MN-major
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      mbar_wait(&qkv_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss(tS, make_sdesc(aQ + k * 32, 16, 1024), make_sdesc(aK + k * 32, 16, 1024), idesc_qk, (uint32_t)(k != 0));
+      umma_commit(&s_full);
+      mbar_wait(&p_full, 0);  // P in shared memory, S read by every softmax warp
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_ss(tO, make_sdesc(aP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024), make_sdesc(aV + k * 2048, 1024, 1024),
+                idesc_pv, (uint32_t)(k != 0));
+      umma_commit(&o_full);
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int rg = r % p.G;
+    uint32_t tmask[4] = {0u, 0u, 0u, 0u};  // the T keys of this row's site sit at columns rg + t * G
+    for (int t = 0; t < p.T; ++t) {
+      const int col = rg + t * p.G;
+      tmask[col >> 5] |= 1u << (col & 31);
+    }
+    mbar_wait(&s_full, 0);
+    tc_fence_after();
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tS + lane_off + c * 32, raw);
+      tmem_ld_wait();
+      const uint32_t okm = c == 0 ? tmask[0] : (c == 1 ? tmask[1] : (c == 2 ? tmask[2] : tmask[3]));
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if ((okm >> i) & 1u) m = fmaxf(m, __uint_as_float(raw[i]));
+    }
+    const float mc = m * p.c;
+    float l = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tS + lane_off + c * 32, raw);
+      tmem_ld_wait();
+      const uint32_t okm = c == 0 ? tmask[0] : (c == 1 ? tmask[1] : (c == 2 ? tmask[2] : tmask[3]));
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ((okm >> i) & 1u) ? ex2f(fmaf(__uint_as_float(raw[i]), p.c, -mc)) : 0.f;
+        const float p1 = ((okm >> (i + 1)) & 1u) ? ex2f(fmaf(__uint_as_float(raw[i + 1]), p.c, -mc)) : 0.f;
+        l += p0 + p1;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+      }
+      uint8_t* prow = sP + (c >> 1) * kTile + r * 128;  // key columns [64 * (c / 2), +64): one swizzle atom row
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ch = (c & 1) * 4 + i;
+        *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&p_full);
+    const float inv = 1.0f / l;
+    const int t = r / p.G;
+    const int s = blockIdx.x * p.G + rg;
+    const bool valid = (t < p.T) && (s < p.S);
+    bf16* op = p.out + (((long long)blockIdx.z * p.T + t) * p.S + s) * p.C + head * 64;
+    mbar_wait(&o_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tO + lane_off + c * 32, raw);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          auto f = [&](int j) { return __uint_as_float(raw[16 * i + j]) * inv; };
+          st_global_v8(op + c * 32 + 16 * i, pack_bf16x2(f(0), f(1)), pack_bf16x2(f(2), f(3)), pack_bf16x2(f(4), f(5)),
+                       pack_bf16x2(f(6), f(7)), pack_bf16x2(f(8), f(9)), pack_bf16x2(f(10), f(11)),
+                       pack_bf16x2(f(12), f(13)), pack_bf16x2(f(14), f(15)));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base_smem, 128);
   }
 }
 
@@ -628,8 +761,8 @@ static int attn_init() {
   CTRLV_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
   if (g_attn_init[dev]) return CTRLV_OK;
   const int smem = 6 * kTile + 1024;
-  CTRLV_CUDA(cudaFuncSetAttribute(attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CTRLV_CUDA(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CTRLV_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CTRLV_CUDA(cudaFuncSetAttribute(tattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTattnSmem));
   CTRLV_CUDA(cudaFuncSetAttribute(attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2Smem));
   g_attn_init[dev] = true;
   return CTRLV_OK;
@@ -667,7 +800,7 @@ extern "C" int ctrlv_attn_spatial(const void* qkv, int32_t frames, int32_t S, in
     return CTRLV_OK;
   }
   dim3 grid((S + 127) / 128, heads, frames);
-  CTRLV_CUDA(launch_pdl(attn_kernel<0>, grid, dim3(kAttnThreads), (size_t)(6 * kTile + 1024), stream, p));
+  CTRLV_CUDA(launch_pdl(attn_kernel, grid, dim3(kAttnThreads), (size_t)(6 * kTile + 1024), stream, p));
   return CTRLV_OK;
 }
 
@@ -696,6 +829,6 @@ extern "C" int ctrlv_attn_temporal(const void* qkv, int32_t B, int32_t T, int32_
   rc = encode_tmap_bf16(&p.tm, qkv, 4, dims, strides, box, true);
   if (rc) return rc;
   dim3 grid((S + p.G - 1) / p.G, heads, B);
-  CTRLV_CUDA(launch_pdl(attn_kernel<1>, grid, dim3(kAttnThreads), (size_t)(6 * kTile + 1024), stream, p));
+  CTRLV_CUDA(launch_pdl(tattn_kernel, grid, dim3(kTattnThreads), (size_t)kTattnSmem, stream, p));
   return CTRLV_OK;
 }
