@@ -45,6 +45,13 @@ struct FfParams {
   int stages, stage_bytes, tiles;
   int off_ring, off_b1, off_b2;  // byte offsets inside dynamic shared memory
   const float* b1;
+  // ln != 0: x holds the rows BEFORE the nn.LayerNorm(C, ln_eps) that feeds this FeedForward (its affine part is
+  // folded into W1 / b1); every x tile is normalised in shared memory before the first contraction reads it.
+  // ln_rb: optional fp32 row-bias added before the statistics, row m takes ln_rb[(m / ln_rb_div) % ln_rb_mod]
+  int ln;
+  float ln_eps;
+  const float* ln_rb;
+  int ln_rb_ld, ln_rb_div, ln_rb_mod;
   ctrlv_epilogue ep;  // output epilogue: bias (= b2), rowbias, s_acc, res1, res2, out (bf16)
 };
 
@@ -55,6 +62,14 @@ __device__ __forceinline__ int ff_rowbias_index(const ctrlv_epilogue& ep, int m)
   return (a * ep.rb_mod + m % ep.rb_mod + ep.rb_off) % ep.rb_B;
 }
 
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {  // (the dynamic-smem pointers are generic: be explicit)
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -89,6 +104,7 @@ template <int CG>
 __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant__ FfParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t x_full, x_empty, d_full, d_free;
+  __shared__ __align__(8) uint64_t x_land, x_ready;  // LayerNorm mode: x tile landed (per CTA) / normalised (on the leader)
   __shared__ __align__(8) uint64_t s_full[2], s_free[2], h_full[2], h_free[2];  // indexed by chunk parity
   __shared__ __align__(8) uint64_t full_bar[kFfMaxStages], empty_bar[kFfMaxStages];
   __shared__ uint32_t tmem_base_smem;
@@ -110,6 +126,8 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
     mbar_init(&x_empty, 1);
     mbar_init(&d_full, 1);
     mbar_init(&d_free, kFfEpiWarps * CG);  // CG = 2: both CTAs' epilogue warps report to the leader
+    mbar_init(&x_land, 1);
+    mbar_init(&x_ready, kFfEpiWarps * CG);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], kFfEpiWarps / 2 * CG);
@@ -182,7 +200,10 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
       const int m0 = tile_row0(it);
       mbar_wait_relaxed(&x_empty, (uint32_t)((it & 1) ^ 1));
       if (elect_one()) {
-        if (CG == 1) {
+        if (p.ln) {  // each CTA's tile reports to its OWN barrier: its epilogue warps normalise it before the MMAs
+          mbar_expect_tx(&x_land, (uint32_t)(p.KB1 * kFfXBlock));
+          for (int kb = 0; kb < p.KB1; ++kb) tma_load_2d(sX + (size_t)kb * kFfXBlock, &p.tmX, &x_land, kb * 64, m0);
+        } else if (CG == 1) {
           mbar_expect_tx(&x_full, (uint32_t)(p.KB1 * kFfXBlock));
           for (int kb = 0; kb < p.KB1; ++kb) tma_load_2d(sX + (size_t)kb * kFfXBlock, &p.tmX, &x_full, kb * 64, m0);
         } else {
@@ -289,7 +310,7 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
         }
         __syncwarp();
       };
-      ff_wait(&x_full, (uint32_t)(it & 1));
+      ff_wait(p.ln ? &x_ready : &x_full, (uint32_t)(it & 1));
       tc_fence_after();
       // MMA1 runs TWO chunks ahead of MMA2: S(j + 2) only waits for the epilogue to have pulled S(j + 1) out of
       // TMEM, so the S hand-off loop never queues behind a second contraction that is still waiting for its
@@ -318,6 +339,73 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
       if (CG == 1) mbar_arrive(bar);
       else mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
     };
+    // LayerNorm of the x tile in place (p.ln): 4 threads per row (8 rows per warp), three passes over the row in
+    // shared memory — sum, centred sum of squares, normalise — the arithmetic of layernorm_kernel (fp32 two-pass
+    // statistics, one rounding to bf16), so the tile the MMAs read equals what the separate launch would have
+    // written.  16-byte piece pc of row r sits at k-block pc / 8, byte ((pc % 8) ^ (r % 8)) * 16 of the 128-byte row
+    // (TMA 128B swizzle).  Generic-proxy writes are fenced for the async proxy before the MMA warp is released.
+    auto normalise_x = [&](int it) {
+      ff_wait(&x_land, (uint32_t)(it & 1));
+      const int row = (warp - 4) * 8 + (lane >> 2), jq = lane & 3;
+      const int npt = p.C >> 5;  // pieces per thread: pc = 4 * i + jq
+      const int m = tile_row0(it) + row;
+      const uint32_t xrow = smem_u32(sX) + (uint32_t)(row * 128);
+      const float* rbp = (p.ln_rb != nullptr && m < p.M)
+                             ? p.ln_rb + (size_t)((m / p.ln_rb_div) % p.ln_rb_mod) * p.ln_rb_ld : nullptr;
+      auto load8 = [&](int pc, float* v) {
+        const uint4 u = lds_u4(xrow + (uint32_t)((pc >> 3) * kFfXBlock) + (uint32_t)((((pc & 7) ^ (row & 7))) << 4));
+        float2 f;
+        f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+        if (rbp) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(rbp + pc * 8));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(rbp + pc * 8 + 4));
+          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+          v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+      };
+      float sum = 0.f;
+      for (int i = 0; i < npt; ++i) {
+        float v[8];
+        load8(4 * i + jq, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += v[k];
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float mean = sum / (float)p.C;
+      float sq = 0.f;
+      for (int i = 0; i < npt; ++i) {
+        float v[8];
+        load8(4 * i + jq, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float d = v[k] - mean;
+          sq += d * d;
+        }
+      }
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      const float rstd = rsqrtf(sq / (float)p.C + p.ln_eps);
+      const float nm = -mean * rstd;
+      for (int i = 0; i < npt; ++i) {
+        const int pc = 4 * i + jq;
+        float v[8];
+        load8(pc, v);
+        uint4 o;
+        o.x = pack_bf16x2(fmaf(v[0], rstd, nm), fmaf(v[1], rstd, nm));
+        o.y = pack_bf16x2(fmaf(v[2], rstd, nm), fmaf(v[3], rstd, nm));
+        o.z = pack_bf16x2(fmaf(v[4], rstd, nm), fmaf(v[5], rstd, nm));
+        o.w = pack_bf16x2(fmaf(v[6], rstd, nm), fmaf(v[7], rstd, nm));
+        sts_u4(xrow + (uint32_t)((pc >> 3) * kFfXBlock) + (uint32_t)((((pc & 7) ^ (row & 7))) << 4), o);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) arrive(&x_ready);
+    };
+    if (p.ln && nloc > 0) normalise_x(0);
     for (int it = 0; it < nloc; ++it) {
       const int m = tile_row0(it) + q * 32 + lane;
       const bool valid = m < p.M;
@@ -357,6 +445,9 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
         __syncwarp();
         if (lane == 0) arrive(&h_full[grp]);
       }
+      // the next tile's x lands under this tile's last contractions: normalise it first, so that the next tile's
+      // up-projections run under the output epilogue below
+      if (p.ln && it + 1 < nloc) normalise_x(it + 1);
       // ---- output epilogue of the tile: D + b2 + rowbias, scale, residuals, bf16 store (row-owner 32-byte accesses)
       const float* rbp = nullptr;
       if (ep.rb_mode != 0 && valid) rbp = ep.rowbias + (size_t)ff_rowbias_index(ep, m) * ep.ld_rowbias;
@@ -435,8 +526,9 @@ static int g_ff_force_cg = 0;
 
 using namespace ctrlv;
 
-extern "C" int ctrlv_feedforward(const void* x, int64_t ldx, int32_t M, int32_t C, const void* W1, const float* b1,
-                                 const void* W2, const ctrlv_epilogue* ep, void* stream_) {
+static int feedforward_impl(const void* x, int64_t ldx, int32_t M, int32_t C, int ln, float ln_eps, const float* ln_rb,
+                            int32_t ln_rb_ld, int32_t ln_rb_div, int32_t ln_rb_mod, const void* W1, const float* b1,
+                            const void* W2, const ctrlv_epilogue* ep, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTRLV_CHECK_ARG(x && W1 && b1 && W2 && ep, "feedforward: null argument");
   CTRLV_CHECK_ARG(M > 0 && C > 0 && C % 64 == 0 && C <= 320, "feedforward: C=%d must be a multiple of 64, <= 320 (TMEM: C + 192 columns)", C);
@@ -493,6 +585,8 @@ extern "C" int ctrlv_feedforward(const void* x, int64_t ldx, int32_t M, int32_t 
   p.off_b2 = p.off_b1 + 2 * p.H * 4;
   p.b1 = b1;
   p.ep = *ep;
+  p.ln = ln; p.ln_eps = ln_eps;
+  p.ln_rb = ln_rb; p.ln_rb_ld = ln_rb_ld; p.ln_rb_div = ln_rb_div; p.ln_rb_mod = ln_rb_mod;
   int rc;
   {
     uint64_t dims[2] = {(uint64_t)C, (uint64_t)M};
@@ -525,6 +619,23 @@ extern "C" int ctrlv_feedforward(const void* x, int64_t ldx, int32_t M, int32_t 
     CTRLV_CUDA(launch_cluster2(ff_kernel<2>, dim3(2 * pairs), dim3(kFfThreads), smem, stream, p));
   }
   return CTRLV_OK;
+}
+
+extern "C" int ctrlv_feedforward(const void* x, int64_t ldx, int32_t M, int32_t C, const void* W1, const float* b1,
+                                 const void* W2, const ctrlv_epilogue* ep, void* stream) {
+  return feedforward_impl(x, ldx, M, C, 0, 0.f, nullptr, 0, 1, 1, W1, b1, W2, ep, stream);
+}
+
+extern "C" int ctrlv_feedforward_ln(const void* x, int64_t ldx, int32_t M, int32_t C, float ln_eps, const float* ln_rowbias,
+                                    int32_t ld_ln_rowbias, int32_t ln_rb_div, int32_t ln_rb_mod, const void* W1,
+                                    const float* b1, const void* W2, const ctrlv_epilogue* ep, void* stream) {
+  CTRLV_CHECK_ARG(ln_eps > 0.f, "feedforward_ln: eps must be positive");
+  if (ln_rowbias)
+    CTRLV_CHECK_ARG(ld_ln_rowbias >= C && ld_ln_rowbias % 4 == 0 && ln_rb_div > 0 && ln_rb_mod > 0 &&
+                        (reinterpret_cast<uintptr_t>(ln_rowbias) & 15) == 0,
+                    "feedforward_ln: row-bias table needs ld >= C, ld %% 4 == 0, 16-byte alignment, div / mod > 0");
+  return feedforward_impl(x, ldx, M, C, 1, ln_eps, ln_rowbias, ld_ln_rowbias, ln_rowbias ? ln_rb_div : 1,
+                          ln_rowbias ? ln_rb_mod : 1, W1, b1, W2, ep, stream);
 }
 
 /* Tuning / test hook: force the CTA-group size of ctrlv_feedforward (0 = automatic). */

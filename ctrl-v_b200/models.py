@@ -310,6 +310,7 @@ def _gn(st, c_off: int = 0):
 GN_FUSED = os.environ.get("CTRLV_GN_FUSED", "1") != "0"
 # FeedForward as one fused launch where the width allows it (True) or as two igemm launches (False: A/B runs)
 FF_FUSED = os.environ.get("CTRLV_FF_FUSED", "1") != "0"
+FF_LN = os.environ.get("CTRLV_FF_LN", "1") != "0"  # the LayerNorm in front of a fused FeedForward runs inside its launch
 if os.environ.get("CTRLV_FF_CG"):  # A/B runs: force single CTAs (1) or CTA pairs (2) in the fused FeedForward
     from . import _lib as _l
     _l.check(_l.load().ctrlv_feedforward_override(int(os.environ["CTRLV_FF_CG"])))
@@ -381,13 +382,22 @@ class _FF:
         self.w1, self.b1 = _w(w1), _f(b1)
         self.w2, self.b2 = _w(sd[pfx + ".net.2.weight"]), _f(sd[pfx + ".net.2.bias"])
 
-    def __call__(self, n, **kw):
-        """GEGLU up-projection + down-projection with the output epilogue `kw` (res1, rowbias, ...): one fused
-        launch where the width allows it (the 4C-wide intermediate stays in tensor memory), two igemm launches
-        otherwise."""
-        if FF_FUSED and n.shape[1] <= ops.FF_FUSED_MAX_C:
-            return ops.feedforward(n, self.w1, self.b1, self.w2, bias=self.b2, **kw)
-        return ops.linear(ops.linear(n, self.w1, bias=self.b1, geglu=True), self.w2, bias=self.b2, **kw)
+    def __call__(self, x, ln=None, **kw):
+        """[LayerNorm +] GEGLU up-projection + down-projection with the output epilogue `kw` (res1, rowbias, ...):
+        one fused launch where the width allows it (the rows are normalised tile by tile in shared memory, the
+        4C-wide intermediate stays in tensor memory), otherwise a LayerNorm launch and two igemm launches.
+        ln = None: x is already normalised; ln = dict of ops.layernorm's row-bias arguments (possibly empty): x are
+        the rows BEFORE the norm whose affine part this FeedForward has folded into its weights."""
+        fused = FF_FUSED and x.shape[1] <= ops.FF_FUSED_MAX_C
+        if ln is not None and not (fused and FF_LN):
+            x, ln = ops.layernorm(x, **ln), None
+        if fused:
+            if ln is not None:
+                return ops.feedforward(x, self.w1, self.b1, self.w2, bias=self.b2, ln_eps=1e-5,
+                                       ln_rowbias=ln.get("rowbias"), ln_rb_div=ln.get("rb_div", 1),
+                                       ln_rb_mod=ln.get("rb_mod", 1), **kw)
+            return ops.feedforward(x, self.w1, self.b1, self.w2, bias=self.b2, **kw)
+        return ops.linear(ops.linear(x, self.w1, bias=self.b1, geglu=True), self.w2, bias=self.b2, **kw)
 
 
 class _SelfAttn:
@@ -483,12 +493,10 @@ class _Transformer:
         else:
             ctx = aux.ctx[:, self.attn2.off:self.attn2.off + self.C]
             h = ops.linear(att, self.attn1.out.w, bias=self.attn1.out.b, rowbias=ctx, rb_mode=1, rb_div=T * S, res1=h)
-        n = ops.layernorm(h)
-        h = self.ff(n, res1=h)
+        h = self.ff(h, ln={}, res1=h)
         # --- TemporalBasicTransformerBlock on h + pos[t]; sequences are the T frames of a site
         pos = self.pos_emb(T)
-        n = ops.layernorm(h, rowbias=pos, rb_div=S, rb_mod=T)
-        hm = self.tff_in(n, res1=h, rowbias=pos, rb_mode=2, rb_div=S, rb_mod=T)
+        hm = self.tff_in(h, ln=dict(rowbias=pos, rb_div=S, rb_mod=T), res1=h, rowbias=pos, rb_mode=2, rb_div=S, rb_mod=T)
         n = ops.layernorm(hm)
         qkv = ops.linear(n, self.tattn1.wqkv, bias=self.tattn1.bqkv)
         att = ops.attn_temporal(qkv, B, T, S, self.heads)
@@ -509,9 +517,8 @@ class _Transformer:
             kw = dict(rb_mode=1, rb_div=T * S)
         if not general:
             hm = ops.linear(att, self.tattn1.out.w, bias=self.tattn1.out.b, rowbias=ctx_t, res1=hm, **kw)
-        n = ops.layernorm(hm)
-        # ff(n) + hm, then AlphaBlender: a*h + (1-a)*(ff + hm)
-        h = self.tff(n, s_acc=1.0 - self.alpha, res1=hm, s_res1=1.0 - self.alpha, res2=h, s_res2=self.alpha)
+        # ff(norm3(hm)) + hm, then AlphaBlender: a*h + (1-a)*(ff + hm)
+        h = self.tff(hm, ln={}, s_acc=1.0 - self.alpha, res1=hm, s_res1=1.0 - self.alpha, res2=h, s_res2=self.alpha)
         return ops.linear(h, self.proj_out.w, bias=self.proj_out.b, res1=x, gn=_gn(st_out))
 
 

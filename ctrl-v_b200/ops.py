@@ -184,9 +184,12 @@ def linear(a: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
 FF_FUSED_MAX_C = 320  # ctrlv_feedforward keeps D [128 x C], S [128 x 128] and H [128 x 64] in the 512 TMEM columns
 
 
-def feedforward(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, **kw) -> torch.Tensor:
+def feedforward(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, ln_eps: Optional[float] = None,
+                ln_rowbias: Optional[torch.Tensor] = None, ln_rb_div: int = 1, ln_rb_mod: int = 1, **kw) -> torch.Tensor:
     """out = epilogue(GEGLU(x @ w1^T + b1) @ w2^T) in ONE launch (C <= 320); w1 / b1 with interleaved
-    (value, gate) rows; kw = the output epilogue (bias = b2, rowbias, s_acc, res1, res2, out)."""
+    (value, gate) rows; kw = the output epilogue (bias = b2, rowbias, s_acc, res1, res2, out).
+    ln_eps: x are the rows BEFORE the LayerNorm in front of the FeedForward (affine part folded into w1 / b1);
+    they are normalised tile by tile inside the launch (+ ln_rowbias[(m // ln_rb_div) % ln_rb_mod] first)."""
     _req(x, BF16, "x"); _req(w1, BF16, "w1"); _req(w2, BF16, "w2"); _req(b1, torch.float32, "b1")
     M, Cc = x.shape
     assert x.stride(1) == 1 and w1.is_contiguous() and w2.is_contiguous()
@@ -194,8 +197,16 @@ def feedforward(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.T
     kw = _alloc_out(M, Cc, False, kw)
     ep = make_ep(**kw)
     tok = _prof("feedforward", (M, Cc, kw.get("res1") is not None, kw.get("res2") is not None), 2.0 * M * Cc * 12 * Cc)
-    check(lib().ctrlv_feedforward(x.data_ptr(), x.stride(0), M, Cc, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                                  C.byref(ep), _stream()), "ctrlv_feedforward")
+    if ln_eps is not None:
+        if ln_rowbias is not None:
+            _req(ln_rowbias, torch.float32, "ln_rowbias")
+        check(lib().ctrlv_feedforward_ln(x.data_ptr(), x.stride(0), M, Cc, ln_eps, _p(ln_rowbias),
+                                         ln_rowbias.stride(0) if ln_rowbias is not None else 0, ln_rb_div, ln_rb_mod,
+                                         w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), C.byref(ep), _stream()),
+              "ctrlv_feedforward_ln")
+    else:
+        check(lib().ctrlv_feedforward(x.data_ptr(), x.stride(0), M, Cc, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                      C.byref(ep), _stream()), "ctrlv_feedforward")
     _prof_end(tok)
     return kw["out"]
 

@@ -186,6 +186,15 @@ int ctrlv_linear(const void* A, int64_t lda, int32_t M, int32_t K, const void* W
  * the hidden activations are rounded to bf16 before the second contraction in both forms). */
 int ctrlv_feedforward(const void* x, int64_t ldx, int32_t M, int32_t C, const void* W1, const float* b1,
                       const void* W2, const ctrlv_epilogue* ep, void* stream);
+/* The same FeedForward with the nn.LayerNorm(C, ln_eps) in front of it (BasicTransformerBlock.norm3,
+ * TemporalBasicTransformerBlock.norm_in / .norm3) in the same launch: x holds the rows BEFORE the norm, every
+ * 128-row tile is normalised in shared memory (fp32 two-pass statistics, one rounding to bf16 — the arithmetic of
+ * ctrlv_layernorm with gamma == beta == NULL) before the first contraction reads it; the norm's affine part is
+ * folded into W1 / b1 by the caller.  ln_rowbias (or NULL): fp32 [rows][ld_ln_rowbias] added to x before the
+ * statistics, row m takes ln_rowbias[(m / ln_rb_div) % ln_rb_mod] (the frame-position embedding in front of norm_in). */
+int ctrlv_feedforward_ln(const void* x, int64_t ldx, int32_t M, int32_t C, float ln_eps, const float* ln_rowbias,
+                         int32_t ld_ln_rowbias, int32_t ln_rb_div, int32_t ln_rb_mod, const void* W1, const float* b1,
+                         const void* W2, const ctrlv_epilogue* ep, void* stream);
 /* Tuning / test hook (process-global): force single CTAs (1) or CTA pairs (2) in ctrlv_feedforward; 0 = automatic. */
 int ctrlv_feedforward_override(int32_t cta_group);
 

@@ -248,6 +248,52 @@ def test_feedforward_fused(ops, M, C, flags, cta_group):
     assert rel(fused, two) < 2e-3
 
 
+@pytest.mark.parametrize("M,C,posemb", [
+    (128, 64, False),
+    (1000, 128, True),       # ragged M (zero rows past the end normalise to zero), frame-position embedding first
+    (300, 320, False),       # C = 320: ten 16-byte pieces per thread, five k-blocks
+    (2 * 14 * 160, 320, True),
+    (71680, 320, False),     # BASELINE config-2 level-0 shape: four tiles per CTA pair (x re-normalised per tile)
+])
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_feedforward_fused_with_layernorm(ops, M, C, posemb, cta_group):
+    """ctrlv_feedforward_ln (the LayerNorm in front of the FeedForward normalises each x tile in shared memory)
+    against ctrlv_layernorm + ctrlv_feedforward and against torch."""
+    dev = "cuda"
+    x = (torch.randn(M, C, device=dev) * 1.7 + 0.4).to(BF)
+    w1 = (torch.randn(8 * C, C, device=dev) / C ** 0.5).to(BF)
+    b1 = torch.randn(8 * C, device=dev) * 0.5
+    w2 = (torch.randn(C, 4 * C, device=dev) / (4 * C) ** 0.5).to(BF)
+    b2 = torch.randn(C, device=dev)
+    kw = dict(bias=b2, res1=x)
+    ln = {}
+    xin = x.float()
+    if posemb:
+        T, S = 14, max(M // 28, 1)
+        pos = torch.randn(T, C, device=dev)
+        ln = dict(rowbias=pos, rb_div=S, rb_mod=T)
+        xin = xin + pos[(torch.arange(M, device=dev) // S) % T]
+    from ctrlv_b200 import _lib
+    _lib.check(_lib.load().ctrlv_feedforward_override(cta_group))
+    try:
+        fused = ops.feedforward(x, w1, b1, w2, ln_eps=1e-5, ln_rowbias=ln.get("rowbias"), ln_rb_div=ln.get("rb_div", 1),
+                                ln_rb_mod=ln.get("rb_mod", 1), **kw)
+        fused2 = ops.feedforward(x, w1, b1, w2, ln_eps=1e-5, ln_rowbias=ln.get("rowbias"), ln_rb_div=ln.get("rb_div", 1),
+                                 ln_rb_mod=ln.get("rb_mod", 1), **kw)
+        n = ops.layernorm(x, **ln)
+        two = ops.feedforward(n, w1, b1, w2, **kw)
+    finally:
+        _lib.load().ctrlv_feedforward_override(0)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, fused2) and not torch.isnan(fused).any()
+    assert rel(fused, two) < 1e-3  # same arithmetic up to the order of the fp32 row sums
+    nr = F.layer_norm(xin, (C,), eps=1e-5).to(BF).float()
+    u = nr @ w1.float().t() + b1
+    hid = (u[:, 0::2] * F.gelu(u[:, 1::2])).to(BF).float()
+    ref = hid @ w2.float().t() + b2 + x.float()
+    assert rel(fused, ref) < TOL_BF16
+
+
 @pytest.mark.parametrize("B,T,S,heads,L,mode", [(2, 3, 40, 2, 5, 1), (2, 4, 24, 1, 77, 3), (3, 2, 16, 4, 256, 1), (2, 2, 9, 2, 33, 3)])
 def test_cross_attn_short_context(ops, B, T, S, heads, L, mode):
     dev = "cuda"
