@@ -106,6 +106,7 @@ SIGNATURES = {
     "ctrlv_linear": (_I, [_P, _L, _I, _I, _P, _I, C.POINTER(Epilogue), _P]),
     "ctrlv_feedforward": (_I, [_P, _L, _I, _I, _P, _P, _P, C.POINTER(Epilogue), _P]),
     "ctrlv_feedforward_ln": (_I, [_P, _L, _I, _I, _F, _P, _I, _I, _I, _P, _P, _P, C.POINTER(Epilogue), _P]),
+    "ctrlv_linear_ln": (_I, [_P, _L, _I, _I, _F, _P, _I, _I, _I, _P, _I, C.POINTER(Epilogue), _P]),
     "ctrlv_feedforward_override": (_I, [_I]),
     "ctrlv_conv3x3": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I,
                            C.POINTER(Epilogue), _P]),

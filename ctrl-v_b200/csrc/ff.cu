@@ -48,6 +48,10 @@ struct FfParams {
   // ln != 0: x holds the rows BEFORE the nn.LayerNorm(C, ln_eps) that feeds this FeedForward (its affine part is
   // folded into W1 / b1); every x tile is normalised in shared memory before the first contraction reads it.
   // ln_rb: optional fp32 row-bias added before the statistics, row m takes ln_rb[(m / ln_rb_div) % ln_rb_mod]
+  // proj != 0 (ctrlv_linear_ln): no GEGLU, no second contraction — out[m][n] = LN(x)[m] . W1[n] + b1[n] for N
+  // outputs, written chunk by chunk from S (W1 = the projection's [N][C] weights, J = ceil(N / 128) chunks); the x
+  // tile is double-buffered (nxb = 2) so that tile i + 1 is loaded and normalised under the chunks of tile i
+  int proj, N, nxb;
   int ln;
   float ln_eps;
   const float* ln_rb;
@@ -103,8 +107,8 @@ __device__ __forceinline__ void ff_add_bf16x16(float* v, const uint4& lo, const 
 template <int CG>
 __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant__ FfParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t x_full, x_empty, d_full, d_free;
-  __shared__ __align__(8) uint64_t x_land, x_ready;  // LayerNorm mode: x tile landed (per CTA) / normalised (on the leader)
+  __shared__ __align__(8) uint64_t x_full[2], x_empty[2], d_full, d_free;  // x barriers: one per x buffer (p.nxb)
+  __shared__ __align__(8) uint64_t x_land[2], x_ready[2];  // LayerNorm mode: x tile landed (per CTA) / normalised (on the leader)
   __shared__ __align__(8) uint64_t s_full[2], s_free[2], h_full[2], h_free[2];  // indexed by chunk parity
   __shared__ __align__(8) uint64_t full_bar[kFfMaxStages], empty_bar[kFfMaxStages];
   __shared__ uint32_t tmem_base_smem;
@@ -122,12 +126,14 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
     tma_prefetch_desc(&p.tmX);
     tma_prefetch_desc(&p.tmW1);
     tma_prefetch_desc(&p.tmW2);
-    mbar_init(&x_full, 1);
-    mbar_init(&x_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+      mbar_init(&x_land[i], 1);
+      mbar_init(&x_ready[i], kFfEpiWarps * CG);
+    }
     mbar_init(&d_full, 1);
     mbar_init(&d_free, kFfEpiWarps * CG);  // CG = 2: both CTAs' epilogue warps report to the leader
-    mbar_init(&x_land, 1);
-    mbar_init(&x_ready, kFfEpiWarps * CG);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], kFfEpiWarps / 2 * CG);
@@ -145,8 +151,12 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
     else tmem_alloc_cg2(&tmem_base_smem, 512);
   }
   // biases are weights (not written by the predecessor kernel): staged once per CTA
-  for (int i = threadIdx.x; i < 2 * p.H; i += kFfThreads) sb1[i] = __ldg(p.b1 + i);
-  for (int i = threadIdx.x; i < p.C; i += kFfThreads) sb2[i] = p.ep.bias ? __ldg(p.ep.bias + i) : 0.f;
+  {
+    const int nb1 = p.proj ? p.N : 2 * p.H;  // (projection: its bias, zero past N)
+    for (int i = threadIdx.x; i < p.J * 128; i += kFfThreads) sb1[i] = (p.b1 != nullptr && i < nb1) ? __ldg(p.b1 + i) : 0.f;
+    if (!p.proj)
+      for (int i = threadIdx.x; i < p.C; i += kFfThreads) sb2[i] = p.ep.bias ? __ldg(p.ep.bias + i) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / TMA credit
@@ -161,6 +171,10 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
   const int nloc = group < nunits ? (nunits - group + ngroups - 1) / ngroups : 0;
   auto tile_row0 = [&](int it) { return ((group + it * ngroups) * CG + (int)crank) * 128; };
   const uint32_t tD = tmem_base, tS = tmem_base + (uint32_t)p.C, tH = tmem_base + (uint32_t)p.C + 128u;
+  // x buffer / barrier phase of this CTA's it-th unit
+  auto xbuf = [&](int it) { return p.nxb == 2 ? (it & 1) : 0; };
+  auto xpar = [&](int it) { return (uint32_t)((p.nxb == 2 ? (it >> 1) : it) & 1); };
+  const int xbytes = p.KB1 * kFfXBlock;
 
   // register reallocation between the warpgroups (each executes ONE setmaxnreg at the head of its role branch).
   // Budget: 640 threads x 96 registers at launch; warps 0-3 release 128 x (96 - 40) = 7168, the four epilogue
@@ -198,18 +212,20 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
     auto w2 = [&](int j) { load_group(&p.tmW2, p.ntile2, p.n2, false, j); };
     auto load_x = [&](int it) {  // the x tile of this CTA's it-th unit, once MMA1 of the previous unit is done with x
       const int m0 = tile_row0(it);
-      mbar_wait_relaxed(&x_empty, (uint32_t)((it & 1) ^ 1));
+      const int xb = xbuf(it);
+      uint8_t* dstx = sX + (size_t)xb * xbytes;
+      mbar_wait_relaxed(&x_empty[xb], xpar(it) ^ 1u);
       if (elect_one()) {
         if (p.ln) {  // each CTA's tile reports to its OWN barrier: its epilogue warps normalise it before the MMAs
-          mbar_expect_tx(&x_land, (uint32_t)(p.KB1 * kFfXBlock));
-          for (int kb = 0; kb < p.KB1; ++kb) tma_load_2d(sX + (size_t)kb * kFfXBlock, &p.tmX, &x_land, kb * 64, m0);
+          mbar_expect_tx(&x_land[xb], (uint32_t)xbytes);
+          for (int kb = 0; kb < p.KB1; ++kb) tma_load_2d(dstx + (size_t)kb * kFfXBlock, &p.tmX, &x_land[xb], kb * 64, m0);
         } else if (CG == 1) {
-          mbar_expect_tx(&x_full, (uint32_t)(p.KB1 * kFfXBlock));
-          for (int kb = 0; kb < p.KB1; ++kb) tma_load_2d(sX + (size_t)kb * kFfXBlock, &p.tmX, &x_full, kb * 64, m0);
+          mbar_expect_tx(&x_full[xb], (uint32_t)xbytes);
+          for (int kb = 0; kb < p.KB1; ++kb) tma_load_2d(dstx + (size_t)kb * kFfXBlock, &p.tmX, &x_full[xb], kb * 64, m0);
         } else {
-          const uint32_t lead_bar = smem_u32(&x_full) & 0xFEFFFFFFu;
-          if (crank == 0) mbar_expect_tx(&x_full, (uint32_t)(2 * p.KB1 * kFfXBlock));
-          for (int kb = 0; kb < p.KB1; ++kb) tma_load_2d_cg2(sX + (size_t)kb * kFfXBlock, &p.tmX, lead_bar, kb * 64, m0);
+          const uint32_t lead_bar = smem_u32(&x_full[xb]) & 0xFEFFFFFFu;
+          if (crank == 0) mbar_expect_tx(&x_full[xb], (uint32_t)(2 * xbytes));
+          for (int kb = 0; kb < p.KB1; ++kb) tma_load_2d_cg2(dstx + (size_t)kb * kFfXBlock, &p.tmX, lead_bar, kb * 64, m0);
         }
       }
       __syncwarp();
@@ -222,12 +238,13 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
       if (p.J > 1) w1(1);
     }
     for (int it = 0; it < nloc; ++it) {
+      if (p.nxb == 2 && it + 1 < nloc) load_x(it + 1);  // second x buffer: the next unit's rows land a whole unit early
       for (int j = 0; j < p.J; ++j) {
         if (j + 2 < p.J) w1(j + 2);
-        w2(j);
+        if (!p.proj) w2(j);
       }
       if (it + 1 < nloc) {  // the next unit's x and first chunks stream in under this unit's tail
-        load_x(it + 1);
+        if (p.nxb != 2) load_x(it + 1);
         w1(0);
         if (p.J > 1) w1(1);
       }
@@ -240,20 +257,28 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
       if (CG == 1) umma_commit(bar);
       else umma_commit_cg2(bar);
     };
-    const uint32_t aX = smem_u32(sX), aR = smem_u32(ring);
+    const uint32_t aR = smem_u32(ring);
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < nloc; ++it) {
       auto mma1 = [&](int j) {  // S = x W1_j^T
         const int g = it * p.J + j;
-        if (g > 0) {  // S of the previous chunk sits in its epilogue group's registers
+        // projection mode: D is unused, so S is double-buffered (columns [0, 128) / [128, 256)) and chunk g only waits
+        // for chunk g - 2 to have left ITS buffer: the up-projections run back to back under the stores
+        const uint32_t tSg = p.proj ? tmem_base + (uint32_t)((g & 1) * 128) : tS;
+        if (p.proj) {
+          if (g >= 2) {
+            ff_wait(&s_free[g & 1], (uint32_t)(((g >> 1) - 1) & 1));
+            tc_fence_after();
+          }
+        } else if (g > 0) {  // S of the previous chunk sits in its epilogue group's registers
           ff_wait(&s_free[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1));
           tc_fence_after();
         }
         ff_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t da0 = make_sdesc(aX, 16, 1024);
+          const uint64_t da0 = make_sdesc(smem_u32(sX) + (uint32_t)(xbuf(it) * xbytes), 16, 1024);
           const uint64_t db0 = make_sdesc(aR + (uint32_t)(stage * p.stage_bytes), 16, 1024);
           for (int kb = 0; kb < p.KB1; ++kb) {
             // k-block kb of x / of this CTA's share of the W1 chunk; +2 in the >>4 address field = 32 bytes = K 16
@@ -261,8 +286,8 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
             const uint64_t db = db0 + (uint64_t)((kb * (128 / CG) * 128) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (CG == 1) umma_ss(tS, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (uint32_t)((kb | k) != 0));
-              else umma_ss_cg2(tS, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (uint32_t)((kb | k) != 0));
+              if (CG == 1) umma_ss(tSg, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (uint32_t)((kb | k) != 0));
+              else umma_ss_cg2(tSg, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (uint32_t)((kb | k) != 0));
             }
           }
           commit(&empty_bar[stage]);
@@ -271,7 +296,7 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
         if (elect_one()) {
           commit(&s_full[g & 1]);
-          if (j == p.J - 1) commit(&x_empty);
+          if (j == p.J - 1) commit(&x_empty[xbuf(it)]);
         }
         __syncwarp();
       };
@@ -310,7 +335,7 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
         }
         __syncwarp();
       };
-      ff_wait(p.ln ? &x_ready : &x_full, (uint32_t)(it & 1));
+      ff_wait(p.ln ? &x_ready[xbuf(it)] : &x_full[xbuf(it)], xpar(it));
       tc_fence_after();
       // MMA1 runs TWO chunks ahead of MMA2: S(j + 2) only waits for the epilogue to have pulled S(j + 1) out of
       // TMEM, so the S hand-off loop never queues behind a second contraction that is still waiting for its
@@ -319,7 +344,7 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
       if (p.J > 1) mma1(1);
       for (int j = 0; j < p.J; ++j) {
         if (j + 2 < p.J) mma1(j + 2);
-        mma2(j);
+        if (!p.proj) mma2(j);
       }
     }
   }
@@ -345,11 +370,11 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
     // written.  16-byte piece pc of row r sits at k-block pc / 8, byte ((pc % 8) ^ (r % 8)) * 16 of the 128-byte row
     // (TMA 128B swizzle).  Generic-proxy writes are fenced for the async proxy before the MMA warp is released.
     auto normalise_x = [&](int it) {
-      ff_wait(&x_land, (uint32_t)(it & 1));
+      ff_wait(&x_land[xbuf(it)], xpar(it));
       const int row = (warp - 4) * 8 + (lane >> 2), jq = lane & 3;
       const int npt = p.C >> 5;  // pieces per thread: pc = 4 * i + jq
       const int m = tile_row0(it) + row;
-      const uint32_t xrow = smem_u32(sX) + (uint32_t)(row * 128);
+      const uint32_t xrow = smem_u32(sX) + (uint32_t)(xbuf(it) * xbytes) + (uint32_t)(row * 128);
       const float* rbp = (p.ln_rb != nullptr && m < p.M)
                              ? p.ln_rb + (size_t)((m / p.ln_rb_div) % p.ln_rb_mod) * p.ln_rb_ld : nullptr;
       auto load8 = [&](int pc, float* v) {
@@ -403,9 +428,55 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) arrive(&x_ready);
+      if (lane == 0) arrive(&x_ready[xbuf(it)]);
     };
     if (p.ln && nloc > 0) normalise_x(0);
+    if (p.proj) {
+      // ================= projection mode: S chunk -> + bias -> bf16 rows of out (no GEGLU, no second contraction)
+      const int jn = p.J >> 1;  // the next tile (second x buffer) is normalised half-way through this one
+      for (int it = 0; it < nloc; ++it) {
+        const int m = tile_row0(it) + q * 32 + lane;
+        // (loop-invariant tests as predicates: a per-chunk reload of a spilled bound queued behind this loop's
+        // stores in the L1 pipeline and cost a third of the kernel's stall samples)
+        const bool norm_next = p.ln && it + 1 < nloc;
+        const bool norm_mid = norm_next && p.nxb == 2;
+        bf16* orow = (m < p.M) ? reinterpret_cast<bf16*>(ep.out) + (size_t)m * ep.ld_out + half * 64 : nullptr;
+        for (int j = 0; j < p.J; ++j) {
+          if (norm_mid && j == jn) normalise_x(it + 1);  // (both groups, before their own chunk test)
+          const int g = it * p.J + j;
+          if ((g & 1) != grp) continue;
+          ff_wait(&s_full[grp], (uint32_t)((g >> 1) & 1));
+          tc_fence_after();
+          uint32_t ra[32], rb[32];
+          const uint32_t tSg = tmem_base + (uint32_t)(grp * 128) + lane_off;  // (g & 1 == grp: this group's S buffer)
+          tmem_ld32(tSg + (uint32_t)(half * 64), ra);
+          tmem_ld32(tSg + (uint32_t)(half * 64 + 32), rb);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive(&s_free[grp]);
+          const int col0 = j * 128 + half * 64;
+          if (orow != nullptr && col0 < p.N) {  // (N % 64 == 0: a 64-column half is stored whole or not at all)
+            const uint32_t bb = sb1_addr + (uint32_t)(col0 * 4);
+            bf16* op = orow + j * 128;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {  // 16 columns = one 32-byte sector per store
+              const uint32_t* r = (h < 2 ? ra : rb) + (h & 1) * 16;
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 bv = lds_f4(bb + (uint32_t)((h * 16 + i) * 4));
+                pk[i >> 1] = pack_bf16x2(__uint_as_float(r[i]) + bv.x, __uint_as_float(r[i + 1]) + bv.y);
+                pk[(i >> 1) + 1] = pack_bf16x2(__uint_as_float(r[i + 2]) + bv.z, __uint_as_float(r[i + 3]) + bv.w);
+              }
+              st_global_v8(op + h * 16, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+        }
+        // one x buffer: it is refilled only after this tile's last up-projection, normalise it now
+        if (norm_next && !norm_mid) normalise_x(it + 1);
+      }
+    } else
     for (int it = 0; it < nloc; ++it) {
       const int m = tile_row0(it) + q * 32 + lane;
       const bool valid = m < p.M;
@@ -447,7 +518,7 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_kernel(const __grid_constant
       }
       // the next tile's x lands under this tile's last contractions: normalise it first, so that the next tile's
       // up-projections run under the output epilogue below
-      if (p.ln && it + 1 < nloc) normalise_x(it + 1);
+      if (p.ln && it + 1 < nloc) normalise_x(it + 1);  // (one x buffer in this mode: it has just been refilled)
       // ---- output epilogue of the tile: D + b2 + rowbias, scale, residuals, bf16 store (row-owner 32-byte accesses)
       const float* rbp = nullptr;
       if (ep.rb_mode != 0 && valid) rbp = ep.rowbias + (size_t)ff_rowbias_index(ep, m) * ep.ld_rowbias;
@@ -526,11 +597,14 @@ static int g_ff_force_cg = 0;
 
 using namespace ctrlv;
 
+// proj_N > 0: projection mode (ctrlv_linear_ln): W1 = [proj_N][C] weights, b1 = its bias (or NULL), W2 unused
 static int feedforward_impl(const void* x, int64_t ldx, int32_t M, int32_t C, int ln, float ln_eps, const float* ln_rb,
                             int32_t ln_rb_ld, int32_t ln_rb_div, int32_t ln_rb_mod, const void* W1, const float* b1,
-                            const void* W2, const ctrlv_epilogue* ep, void* stream_) {
+                            const void* W2, const ctrlv_epilogue* ep, void* stream_, int32_t proj_N = 0) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CTRLV_CHECK_ARG(x && W1 && b1 && W2 && ep, "feedforward: null argument");
+  const bool proj = proj_N > 0;
+  if (proj) W2 = W1;  // (alignment checks below)
+  CTRLV_CHECK_ARG(x && W1 && (b1 || proj) && W2 && ep, "feedforward: null argument");
   CTRLV_CHECK_ARG(M > 0 && C > 0 && C % 64 == 0 && C <= 320, "feedforward: C=%d must be a multiple of 64, <= 320 (TMEM: C + 192 columns)", C);
   CTRLV_CHECK_ARG(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(W1) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(W2) & 15) == 0, "feedforward: operands must be 16-byte aligned");
@@ -563,7 +637,8 @@ static int feedforward_impl(const void* x, int64_t ldx, int32_t M, int32_t C, in
   memset(&p, 0, sizeof(p));
   p.M = M; p.C = C; p.H = 4 * C;
   p.KB1 = C / 64;
-  p.J = p.H / 64;
+  p.J = proj ? (proj_N + 127) / 128 : p.H / 64;
+  p.proj = proj ? 1 : 0; p.N = proj_N; p.nxb = 1;
   p.n2 = C > 256 ? C / 2 : C;
   p.ntile2 = C / p.n2;
   CTRLV_CHECK_ARG(p.n2 % 16 == 0, "feedforward: MMA2 n-tile %d", p.n2);
@@ -572,17 +647,19 @@ static int feedforward_impl(const void* x, int64_t ldx, int32_t M, int32_t C, in
   p.cg = (g_ff_force_cg ? g_ff_force_cg : ((p.tiles >= 2 && p.n2 % 16 == 0) ? 2 : 1));
   CTRLV_CHECK_ARG(p.cg == 1 || p.n2 % 16 == 0, "feedforward: cta_group 2 needs an MMA2 n-tile that is a multiple of 16");
   {  // one ring slot = one operand group: a whole W1 chunk (KB1 k-blocks) or a whole W2 chunk (ntile2 n-tiles)
-    const int g1 = p.KB1 * (128 / p.cg) * 128, g2 = p.ntile2 * (p.n2 / p.cg) * 128;
+    const int g1 = p.KB1 * (128 / p.cg) * 128, g2 = proj ? 0 : p.ntile2 * (p.n2 / p.cg) * 128;
     p.stage_bytes = ((g1 > g2 ? g1 : g2) + 1023) / 1024 * 1024;
   }
-  p.off_ring = p.KB1 * kFfXBlock;
-  const int bias_bytes = (2 * p.H + C) * 4;
+  const int bias_bytes = (p.J * 128 + C) * 4;
+  // projection mode: a second x buffer when it still leaves a ring of three chunks (narrow models only)
+  if (proj && (dp.max_smem - 1024 - 2 * p.KB1 * kFfXBlock - bias_bytes) / p.stage_bytes >= 3) p.nxb = 2;
+  p.off_ring = p.nxb * p.KB1 * kFfXBlock;
   int stages = (dp.max_smem - 1024 - p.off_ring - bias_bytes) / p.stage_bytes;
   if (stages > kFfMaxStages) stages = kFfMaxStages;
   CTRLV_CHECK_ARG(stages >= 1, "feedforward: not enough shared memory");
   p.stages = stages;
   p.off_b1 = p.off_ring + stages * p.stage_bytes;
-  p.off_b2 = p.off_b1 + 2 * p.H * 4;
+  p.off_b2 = p.off_b1 + p.J * 128 * 4;
   p.b1 = b1;
   p.ep = *ep;
   p.ln = ln; p.ln_eps = ln_eps;
@@ -596,18 +673,20 @@ static int feedforward_impl(const void* x, int64_t ldx, int32_t M, int32_t C, in
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)C, (uint64_t)(2 * p.H)};
+    uint64_t dims[2] = {(uint64_t)C, (uint64_t)(proj ? proj_N : 2 * p.H)};
     uint64_t strides[1] = {(uint64_t)C * 2};
     uint32_t box[2] = {64, (uint32_t)(128 / p.cg)};
     rc = encode_tmap_bf16(&p.tmW1, W1, 2, dims, strides, box, true);
     if (rc) return rc;
   }
-  {
+  if (!proj) {
     uint64_t dims[2] = {(uint64_t)p.H, (uint64_t)C};
     uint64_t strides[1] = {(uint64_t)p.H * 2};
     uint32_t box[2] = {64, (uint32_t)(p.n2 / p.cg)};
     rc = encode_tmap_bf16(&p.tmW2, W2, 2, dims, strides, box, true);
     if (rc) return rc;
+  } else {
+    p.tmW2 = p.tmW1;  // (prefetched, never loaded from)
   }
   const size_t smem = (size_t)p.off_b2 + (size_t)C * 4 + 1024;
   if (p.cg == 1) {
@@ -636,6 +715,20 @@ extern "C" int ctrlv_feedforward_ln(const void* x, int64_t ldx, int32_t M, int32
                     "feedforward_ln: row-bias table needs ld >= C, ld %% 4 == 0, 16-byte alignment, div / mod > 0");
   return feedforward_impl(x, ldx, M, C, 1, ln_eps, ln_rowbias, ld_ln_rowbias, ln_rowbias ? ln_rb_div : 1,
                           ln_rowbias ? ln_rb_mod : 1, W1, b1, W2, ep, stream);
+}
+
+extern "C" int ctrlv_linear_ln(const void* x, int64_t ldx, int32_t M, int32_t K, float ln_eps, const float* ln_rowbias,
+                               int32_t ld_ln_rowbias, int32_t ln_rb_div, int32_t ln_rb_mod, const void* W, int32_t N,
+                               const ctrlv_epilogue* ep, void* stream) {
+  CTRLV_CHECK_ARG(ep != nullptr && ln_eps > 0.f && N > 0 && N % 64 == 0, "linear_ln: eps > 0, N a positive multiple of 64");
+  CTRLV_CHECK_ARG(ep->rb_mode == 0 && ep->res1 == nullptr && ep->res2 == nullptr && ep->s_acc == 1.0f,
+                  "linear_ln: the epilogue takes a bias and a bf16 out only");
+  if (ln_rowbias)
+    CTRLV_CHECK_ARG(ld_ln_rowbias >= K && ld_ln_rowbias % 4 == 0 && ln_rb_div > 0 && ln_rb_mod > 0 &&
+                        (reinterpret_cast<uintptr_t>(ln_rowbias) & 15) == 0,
+                    "linear_ln: row-bias table needs ld >= K, ld %% 4 == 0, 16-byte alignment, div / mod > 0");
+  return feedforward_impl(x, ldx, M, K, 1, ln_eps, ln_rowbias, ld_ln_rowbias, ln_rowbias ? ln_rb_div : 1,
+                          ln_rowbias ? ln_rb_mod : 1, W, ep->bias, nullptr, ep, stream, N);
 }
 
 /* Tuning / test hook: force the CTA-group size of ctrlv_feedforward (0 = automatic). */

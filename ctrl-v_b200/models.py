@@ -311,6 +311,14 @@ GN_FUSED = os.environ.get("CTRLV_GN_FUSED", "1") != "0"
 # FeedForward as one fused launch where the width allows it (True) or as two igemm launches (False: A/B runs)
 FF_FUSED = os.environ.get("CTRLV_FF_FUSED", "1") != "0"
 FF_LN = os.environ.get("CTRLV_FF_LN", "1") != "0"  # the LayerNorm in front of a fused FeedForward runs inside its launch
+QKV_LN = os.environ.get("CTRLV_QKV_LN", "1") != "0"  # norm1 + the fused q | k | v projection in one launch (C <= 320)
+
+
+def _qkv(h, attn):
+    """LayerNorm(norm1, affine part folded) + the fused to_q | to_k | to_v projection of a self-attention"""
+    if QKV_LN and h.shape[1] <= ops.FF_FUSED_MAX_C and attn.wqkv.shape[0] % 64 == 0:
+        return ops.linear_ln(h, attn.wqkv, bias=attn.bqkv)
+    return ops.linear(ops.layernorm(h), attn.wqkv, bias=attn.bqkv)
 if os.environ.get("CTRLV_FF_CG"):  # A/B runs: force single CTAs (1) or CTA pairs (2) in the fused FeedForward
     from . import _lib as _l
     _l.check(_l.load().ctrlv_feedforward_override(int(os.environ["CTRLV_FF_CG"])))
@@ -483,8 +491,7 @@ class _Transformer:
         a = ops.groupnorm(x, F_, S, self.norm.g, self.norm.b, 1e-6, False, stats=st_in)
         h = ops.linear(a, self.proj_in.w, bias=self.proj_in.b)
         # --- BasicTransformerBlock (spatial)
-        n = ops.layernorm(h)
-        qkv = ops.linear(n, self.attn1.wqkv, bias=self.attn1.bqkv)
+        qkv = _qkv(h, self.attn1)
         att = ops.attn_spatial(qkv, F_, S, self.heads)
         general = aux.L > 1  # context of several tokens: real cross-attention; one token: a per-sample vector
         if general:
@@ -497,8 +504,7 @@ class _Transformer:
         # --- TemporalBasicTransformerBlock on h + pos[t]; sequences are the T frames of a site
         pos = self.pos_emb(T)
         hm = self.tff_in(h, ln=dict(rowbias=pos, rb_div=S, rb_mod=T), res1=h, rowbias=pos, rb_mode=2, rb_div=S, rb_mod=T)
-        n = ops.layernorm(hm)
-        qkv = ops.linear(n, self.tattn1.wqkv, bias=self.tattn1.bqkv)
+        qkv = _qkv(hm, self.tattn1)
         att = ops.attn_temporal(qkv, B, T, S, self.heads)
         if general:
             hm = ops.linear(att, self.tattn1.out.w, bias=self.tattn1.out.b, res1=hm)

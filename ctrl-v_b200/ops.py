@@ -211,6 +211,28 @@ def feedforward(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.T
     return kw["out"]
 
 
+def linear_ln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
+              ln_rowbias: Optional[torch.Tensor] = None, ln_rb_div: int = 1, ln_rb_mod: int = 1,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M, N] = LayerNorm(x [+ ln_rowbias])[M, K] @ w[N, K]^T + bias in ONE launch (K <= 320, N % 64 == 0): the
+    rows are normalised tile by tile in shared memory (the norm's affine part folded into w / bias by the caller)."""
+    _req(x, BF16, "x"); _req(w, BF16, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and w.is_contiguous() and x.stride(1) == 1 and K <= FF_FUSED_MAX_C and N % 64 == 0
+    if out is None:
+        out = torch.empty((M, N), dtype=BF16, device="cuda")
+    ep = make_ep(out=out, bias=bias)
+    if ln_rowbias is not None:
+        _req(ln_rowbias, torch.float32, "ln_rowbias")
+    tok = _prof("linear", (M, K, N, False, False, False, False), 2.0 * M * K * N)
+    check(lib().ctrlv_linear_ln(x.data_ptr(), x.stride(0), M, K, ln_eps, _p(ln_rowbias),
+                                ln_rowbias.stride(0) if ln_rowbias is not None else 0, ln_rb_div, ln_rb_mod,
+                                w.data_ptr(), N, C.byref(ep), _stream()), "ctrlv_linear_ln")
+    _prof_end(tok)
+    return out
+
+
 def conv3x3(x: torch.Tensor, frames: int, H: int, W: int, w: torch.Tensor, stride: int = 1,
             src1: Optional[torch.Tensor] = None, sc0: Optional[torch.Tensor] = None,
             sc1: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:

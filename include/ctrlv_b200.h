@@ -195,6 +195,14 @@ int ctrlv_feedforward(const void* x, int64_t ldx, int32_t M, int32_t C, const vo
 int ctrlv_feedforward_ln(const void* x, int64_t ldx, int32_t M, int32_t C, float ln_eps, const float* ln_rowbias,
                          int32_t ld_ln_rowbias, int32_t ln_rb_div, int32_t ln_rb_mod, const void* W1, const float* b1,
                          const void* W2, const ctrlv_epilogue* ep, void* stream);
+/* nn.LayerNorm(K, ln_eps) + nn.Linear(K, N) in one launch for K <= 320 (BasicTransformerBlock.norm1 -> attn1.to_q /
+ * to_k / to_v fused, TemporalBasicTransformerBlock.norm1 -> attn1): the machinery of ctrlv_feedforward_ln without the
+ * GEGLU and the second contraction — the x tile is normalised in shared memory, out[m][n] = LN(x)[m] . W[n] + bias[n]
+ * leaves the launch chunk by chunk (128 columns at a time) as bf16.  W [N][K] bf16 (the norm's affine part folded in
+ * by the caller), N % 64 == 0; `ep` carries the bias (or NULL) and the bf16 out (32-byte aligned rows), nothing else. */
+int ctrlv_linear_ln(const void* x, int64_t ldx, int32_t M, int32_t K, float ln_eps, const float* ln_rowbias,
+                    int32_t ld_ln_rowbias, int32_t ln_rb_div, int32_t ln_rb_mod, const void* W, int32_t N,
+                    const ctrlv_epilogue* ep, void* stream);
 /* Tuning / test hook (process-global): force single CTAs (1) or CTA pairs (2) in ctrlv_feedforward; 0 = automatic. */
 int ctrlv_feedforward_override(int32_t cta_group);
 

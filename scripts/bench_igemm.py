@@ -54,7 +54,16 @@ def ff(M, C, fused, res2=False):
         return (lambda: ops.feedforward(x, w1, b1, w2, **kw)), 2.0 * M * C * 12 * C
     return (lambda: ops.linear(ops.linear(x, w1, bias=b1, geglu=True, out=hid), w2, **kw)), 2.0 * M * C * 12 * C
 
+def lnlin(M, K, N, fused):
+    x = torch.randn(M, K, device=dev).to(BF); w = (torch.randn(N, K, device=dev) / K ** 0.5).to(BF)
+    b = torch.randn(N, device=dev); out = torch.empty(M, N, device=dev, dtype=BF); n = torch.empty_like(x)
+    if fused:
+        return (lambda: ops.linear_ln(x, w, bias=b, out=out)), 2.0 * M * K * N
+    return (lambda: ops.linear(ops.layernorm(x, out=n), w, bias=b, out=out)), 2.0 * M * K * N
+
 CASES = [
+    ("ln+qkv L0 one launch 320->960", lambda: lnlin(71680, 320, 960, True), 14),
+    ("ln+qkv L0 two launches 320->960", lambda: lnlin(71680, 320, 960, False), 0),
     ("ff L0 fused 71680x320", lambda: ff(71680, 320, True), 14),
     ("ff L0 fused 71680x320 +res2", lambda: ff(71680, 320, True, True), 7),
     ("ff L0 two-launch 71680x320", lambda: ff(71680, 320, False), 0),

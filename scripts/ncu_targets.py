@@ -57,3 +57,8 @@ if which == "sk":  # stream-K schedule on the level-3 problems (10 row tiles)
     x = torch.randn(28 * 5 * 8, 1280, device=dev).to(BF); w = (torch.randn(1280, 9 * 1280, device=dev) / 107).to(BF)
     for _ in range(3): ops.conv3x3(x, 28, 5, 8, w, bias=b)
     torch.cuda.synchronize()
+if which == "lnqkv":  # LayerNorm + q|k|v projection in one launch (ctrlv_linear_ln), level-0 shape
+    x = torch.randn(71680, 320, device=dev).to(BF); w = (torch.randn(960, 320, device=dev) / 18).to(BF); b = torch.randn(960, device=dev)
+    o = torch.empty(71680, 960, device=dev, dtype=BF)
+    for _ in range(3): ops.linear_ln(x, w, bias=b, out=o)
+    torch.cuda.synchronize()

@@ -294,6 +294,47 @@ def test_feedforward_fused_with_layernorm(ops, M, C, posemb, cta_group):
     assert rel(fused, ref) < TOL_BF16
 
 
+@pytest.mark.parametrize("M,K,N,posemb", [
+    (128, 64, 64, False),       # one chunk, half of it stored
+    (1000, 128, 384, True),     # ragged M, three chunks, two x buffers
+    (300, 320, 960, False),     # level-0 q | k | v: 7.5 chunks (the last half chunk is not stored)
+    (2 * 14 * 160, 256, 768, False),
+    (71680, 320, 960, False),   # BASELINE config-2 level-0 shape
+])
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_linear_with_layernorm(ops, M, K, N, posemb, cta_group):
+    """ctrlv_linear_ln (LayerNorm + Linear in one launch, rows normalised in shared memory) against
+    ctrlv_layernorm + ctrlv_linear and against torch."""
+    dev = "cuda"
+    x = (torch.randn(M, K, device=dev) * 1.3 - 0.2).to(BF)
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).to(BF)
+    b = torch.randn(N, device=dev)
+    ln = {}
+    xin = x.float()
+    if posemb:
+        T, S = 5, max(M // 10, 1)
+        pos = torch.randn(T, K, device=dev)
+        ln = dict(rowbias=pos, rb_div=S, rb_mod=T)
+        xin = xin + pos[(torch.arange(M, device=dev) // S) % T]
+    from ctrlv_b200 import _lib
+    _lib.check(_lib.load().ctrlv_feedforward_override(cta_group))
+    try:
+        out = torch.full((M, N), 7.0, device=dev, dtype=BF)
+        ops.linear_ln(x, w, bias=b, ln_rowbias=ln.get("rowbias"), ln_rb_div=ln.get("rb_div", 1), ln_rb_mod=ln.get("rb_mod", 1), out=out)
+        out2 = ops.linear_ln(x, w, bias=b, ln_rowbias=ln.get("rowbias"), ln_rb_div=ln.get("rb_div", 1), ln_rb_mod=ln.get("rb_mod", 1))
+        nob = ops.linear_ln(x, w)
+    finally:
+        _lib.load().ctrlv_feedforward_override(0)
+    two = ops.linear(ops.layernorm(x, **ln), w, bias=b)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2) and not torch.isnan(out).any()
+    assert rel(out, two) < 1e-3
+    ref = F.layer_norm(xin, (K,), eps=1e-5).to(BF).float() @ w.float().t()
+    assert rel(out, ref + b) < TOL_BF16
+    if not posemb:
+        assert rel(nob, ref) < TOL_BF16
+
+
 @pytest.mark.parametrize("B,T,S,heads,L,mode", [(2, 3, 40, 2, 5, 1), (2, 4, 24, 1, 77, 3), (3, 2, 16, 4, 256, 1), (2, 2, 9, 2, 33, 3)])
 def test_cross_attn_short_context(ops, B, T, S, heads, L, mode):
     dev = "cuda"
