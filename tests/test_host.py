@@ -371,3 +371,35 @@ def test_groupnorm_statistics_table_geometry():
         cg = C // 32
         for c0 in range(0, C, 8):
             assert len({(c0 + j) // cg for j in range(8)}) <= 2, (C, c0)
+
+
+def test_new_entry_points_reject_bad_arguments_before_touching_the_device():
+    """Argument validation of the round-2 entry points runs before any CUDA call: usable on a host without a GPU.
+    (ctrlv_linear_ln / ctrlv_feedforward_ln / ctrlv_igemm_streamk; messages via ctrlv_last_error.)"""
+    import ctypes as C
+    from ctrlv_b200 import _lib
+    lib = _lib.load()
+    ep = _lib.Epilogue()
+    ep.s_acc = 1.0
+    ep.out, ep.ld_out = 0x1000, 960
+    x, w = 0x2000, 0x3000  # never dereferenced: every call below fails its argument checks
+    # N must be a multiple of 64, eps positive
+    assert lib.ctrlv_linear_ln(x, 320, 128, 320, 1e-5, None, 0, 1, 1, w, 100, C.byref(ep), None) == -1
+    assert b"multiple of 64" in lib.ctrlv_last_error()
+    assert lib.ctrlv_linear_ln(x, 320, 128, 320, 0.0, None, 0, 1, 1, w, 960, C.byref(ep), None) == -1
+    # the projection epilogue takes a bias and a bf16 out only
+    ep.res1, ep.ld_res1 = 0x4000, 960
+    assert lib.ctrlv_linear_ln(x, 320, 128, 320, 1e-5, None, 0, 1, 1, w, 960, C.byref(ep), None) == -1
+    assert b"bias and a bf16 out only" in lib.ctrlv_last_error()
+    ep.res1, ep.ld_res1 = None, 0
+    # row-bias table in front of the norm: ld >= K, 16-byte aligned
+    assert lib.ctrlv_linear_ln(x, 320, 128, 320, 1e-5, 0x5000, 64, 1, 1, w, 960, C.byref(ep), None) == -1
+    assert lib.ctrlv_feedforward_ln(x, 320, 128, 320, 1e-5, 0x5004, 320, 1, 1, w, 0x6000, w, C.byref(ep), None) == -1
+    assert b"row-bias" in lib.ctrlv_last_error()
+    assert lib.ctrlv_feedforward_ln(x, 320, 128, 320, -1.0, None, 0, 1, 1, w, 0x6000, w, C.byref(ep), None) == -1
+    # widths above 320 do not fit the 512 TMEM columns
+    assert lib.ctrlv_linear_ln(x, 640, 128, 640, 1e-5, None, 0, 1, 1, w, 1920, C.byref(ep), None) == -1
+    assert b"320" in lib.ctrlv_last_error()
+    # stream-K hook: three modes
+    assert lib.ctrlv_igemm_streamk(3) == -1
+    assert lib.ctrlv_igemm_streamk(0) == 0
