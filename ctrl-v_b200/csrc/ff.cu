@@ -17,6 +17,16 @@
 //   W1(0), W1(1), then for j = 0..J-1: [W1(j+2)], W2(j)   (MMA1 runs two chunks ahead of MMA2).
 // TMEM columns: D [0, C), S [C, C+128), H double-buffered [C+128, C+192)  (C = 320: exactly 512).
 //
+// LayerNorm mode (ctrlv_feedforward_ln): x holds the rows BEFORE the nn.LayerNorm in front of the FeedForward.  The
+// resident x tile has whole rows, so the 16 epilogue warps normalise it in place (4 threads per row, three passes over
+// the swizzled tile, the fp32 arithmetic of layernorm_kernel) and release the MMA warp through `x_ready`; the tile of
+// the next unit is normalised between this unit's last GEGLU chunk and its output epilogue.  In this mode every CTA
+// of a pair receives its x tile on its own barrier (`x_land`) instead of the leader's.
+//
+// Projection mode (ctrlv_linear_ln: LayerNorm + Linear, e.g. norm1 + to_q | to_k | to_v): the same launch without
+// GEGLU, H, MMA2 and D — W1 is the projection's [N][C] matrix, S is double-buffered in the TMEM columns D does not
+// need, and each 128-column chunk leaves the launch from S as bf16 rows (+ bias).
+//
 // CG = 2 (the production form): a CTA pair (cluster of 2, tcgen05 cta_group::2) works on two adjacent row
 // tiles at once; each CTA loads HALF of every weight tile and the leader's M = 256 MMAs read both halves.
 // One weight chunk is 120 KB, exactly the shared memory left beside the resident x tile, so a single CTA

@@ -17,6 +17,10 @@
 //   set-up barrier warpgroup 0 shrinks to 40 registers per thread and the epilogue warpgroups grow to
 //   152 (setmaxnreg): the epilogue holds an accumulator chunk, a prefetched residual chunk and its
 //   row bookkeeping in registers without spilling.
+// * Optional stream-K schedule (igemm_kernel<CG, true> + igemm_fixup_kernel, ctrlv_epilogue.splitk_ws): contiguous
+//   k-block ranges per CTA instead of whole tiles, fp32 partial tiles in the caller's workspace, a fix-up launch that
+//   adds them in contributor order and runs the same fused epilogue.  Off on the denoise step's shapes (measured
+//   level, see sk_wanted()).
 #include <cstdlib>
 
 #include "common.cuh"
