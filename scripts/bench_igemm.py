@@ -43,6 +43,15 @@ def convt(B, T, HW, C, N):
     res = torch.randn(B * T * HW, N, device=dev).to(BF)
     return (lambda: ops.conv_t3(x, B, T, HW, w, bias=b, out=out, res1=res, s_acc=0.5)), 2.0 * B * T * HW * 3 * C * N
 
+def ffln(M, C, fused):
+    x = torch.randn(M, C, device=dev).to(BF); n = torch.empty_like(x)
+    w1 = (torch.randn(8 * C, C, device=dev) / C ** 0.5).to(BF); b1 = torch.randn(8 * C, device=dev)
+    w2 = (torch.randn(C, 4 * C, device=dev) / (4 * C) ** 0.5).to(BF); b2 = torch.randn(C, device=dev)
+    out = torch.empty(M, C, device=dev, dtype=BF)
+    if fused:
+        return (lambda: ops.feedforward(x, w1, b1, w2, ln_eps=1e-5, bias=b2, out=out, res1=x)), 2.0 * M * C * 12 * C
+    return (lambda: ops.feedforward(ops.layernorm(x, out=n), w1, b1, w2, bias=b2, out=out, res1=x)), 2.0 * M * C * 12 * C
+
 def ff(M, C, fused, res2=False):
     x = torch.randn(M, C, device=dev).to(BF)
     w1 = (torch.randn(8 * C, C, device=dev) / C ** 0.5).to(BF); b1 = torch.randn(8 * C, device=dev)
@@ -64,6 +73,8 @@ def lnlin(M, K, N, fused):
 CASES = [
     ("ln+qkv L0 one launch 320->960", lambda: lnlin(71680, 320, 960, True), 14),
     ("ln+qkv L0 two launches 320->960", lambda: lnlin(71680, 320, 960, False), 0),
+    ("ln+ff L0 one launch 71680x320", lambda: ffln(71680, 320, True), 21),
+    ("ln+ff L0 two launches 71680x320", lambda: ffln(71680, 320, False), 0),
     ("ff L0 fused 71680x320", lambda: ff(71680, 320, True), 14),
     ("ff L0 fused 71680x320 +res2", lambda: ff(71680, 320, True, True), 7),
     ("ff L0 two-launch 71680x320", lambda: ff(71680, 320, False), 0),
