@@ -403,3 +403,57 @@ def test_new_entry_points_reject_bad_arguments_before_touching_the_device():
     # stream-K hook: three modes
     assert lib.ctrlv_igemm_streamk(3) == -1
     assert lib.ctrlv_igemm_streamk(0) == 0
+
+
+def test_streamk_schedule_arithmetic():
+    """The index arithmetic of the stream-K schedule (csrc/igemm.cu: WorkIter<true>, the partial-slot rule of the
+    GEMM kernel and the contributor range / slot parity igemm_fixup_kernel recomputes), restated in Python and
+    checked over random problems: every k-block of every tile is covered exactly once, a tile is either whole
+    (one CTA, no slot) or split into contiguous partial ranges whose CTAs are exactly [gf, gl], no two partial
+    ranges share a slot, and the fix-up's slot rule finds each contributor's slot.  (The device code itself is
+    covered by tests/test_gpu_kernels.py::test_streamk_schedule_matches_whole_tiles.)"""
+    import random
+    rnd = random.Random(1)
+    max_contrib = 4
+    for _ in range(3000):
+        tiles, kb, slots = rnd.randint(1, 300), rnd.randint(16, 420), rnd.choice([74, 148, 66, 132])
+        total = tiles * kb
+        G = slots
+        if total < G * 8:
+            G = total // 8                                   # at least 8 k-blocks per CTA
+        per_min = (kb - 1 + max_contrib - 2) // (max_contrib - 1)
+        if G >= 1 and -(-total // G) < per_min:
+            G = total // per_min                             # at most four CTAs per tile
+        if G < 2:
+            continue
+        per = -(-total // G)
+        G = -(-total // per)
+        cover = {t: [] for t in range(tiles)}
+        slot_of = {}
+        for g in range(G):
+            a, b = g * per, min(total, g * per + per)
+            first_tile = (g * per) // kb
+            while a < b:                                     # WorkIter<true>::next
+                t = a // kb
+                kb0 = a - t * kb
+                kb1 = min(kb, kb0 + (b - a))
+                a += kb1 - kb0
+                partial = not (kb0 == 0 and kb1 == kb)
+                if partial:
+                    slot = g * 2 + (0 if t == first_tile else 1)
+                    assert slot not in slot_of
+                    slot_of[slot] = (t, g)
+                cover[t].append((kb0, kb1, g, partial))
+        for t in range(tiles):
+            segs = sorted(cover[t])
+            assert segs[0][0] == 0 and segs[-1][1] == kb
+            assert all(x[1] == y[0] for x, y in zip(segs, segs[1:]))
+            gf, gl = (t * kb) // per, ((t + 1) * kb - 1) // per   # igemm_fixup_kernel
+            if gf == gl:
+                assert len(segs) == 1 and not segs[0][3]
+                continue
+            assert [s[2] for s in segs] == list(range(gf, gl + 1)) and all(s[3] for s in segs)
+            assert gl - gf + 1 <= max_contrib
+            w_first = 0 if (gf * per) // kb == t else 1
+            for _, _, g, _ in segs:
+                assert slot_of[g * 2 + (w_first if g == gf else 0)] == (t, g)
