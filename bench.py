@@ -433,7 +433,7 @@ def run_b200(a):
                 break
             except Exception:
                 continue
-    roofline = {"bound": "tensor", "kernel": "ctrlv::igemm_kernel (tcgen05 implicit GEMM: Linear / 3x3 / temporal conv) + ctrlv::ff_kernel (fused FeedForward at C = 320)",
+    roofline = {"bound": "tensor", "kernel": "ctrlv::igemm_kernel (tcgen05 implicit GEMM: Linear / 3x3 / temporal conv) + ctrlv::ff_kernel (fused LayerNorm + FeedForward and LayerNorm + q|k|v projection at C = 320)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": int(gemm_n),
                 "timing": "CUDA events around every igemm launch of one eager (un-captured) step in this process, on the "
