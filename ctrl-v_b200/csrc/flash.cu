@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 
 // ------------------------------------------------------------------------------------------
 // Temporal attention (sequences = the T frames of one spatial site; one key block): the single-block special case
-// of attn_kernel<1>, shrunk so that FOUR CTAs share an SM instead of two.  The launch is a stream of short
+// of the one-tile kernel above (its former temporal mode), shrunk so that FOUR CTAs share an SM instead of two.  The launch is a stream of short
 // dependent chains (TMA Q|K|V -> S = Q K^T -> masked softmax -> P -> O = P V -> store, about 6 us per CTA) with
 // almost no arithmetic (HBM-bound: 8 * rows * C bytes), so its speed is the number of chains in flight per SM:
 //   * 4 softmax warps (one per TMEM lane quarter, a thread owns a whole 128-column score row): no exchange between
